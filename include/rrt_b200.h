@@ -1,0 +1,164 @@
+/*
+ * rrt_b200.h -- C ABI of the B200-native differentiable ray-tracer hot path.
+ *
+ * Drop-in boundary for ONE path of lebek/reversible-raytracer (Python 2 + Theano):
+ * primary rays -> ray/shape intersection -> nearest hit -> Phong / depth shading
+ * -> reverse pass to scene-parameter gradients.  The reference has no FFI of its
+ * own; the interface replaced is the Python class API
+ *     Scene(shapes, lights, camera, shader).build(antialias_samples)   scene.py:11-52
+ *     T.grad(loss, params) over that graph                             optimize.py:25,73
+ * and each entry point below cites the reference code it stands in for
+ * (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, int return: 0 = OK, <0 = error
+ *     (RRT_ERR_*); rrt_last_error() gives a thread-local message.  No exceptions
+ *     cross the ABI.
+ *   - Every buffer is DEVICE memory owned by the caller (except where a parameter
+ *     is documented as host).  The library never allocates, frees or synchronises
+ *     (rrt_measure_fp32_peak is the one documented exception: it is a benchmark).
+ *   - All work is enqueued on the caller's CUDA stream (`stream` is a
+ *     cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - No global mutable state: re-entrant from several host threads, one process
+ *     per GPU.
+ *   - Gradient / loss outputs are zero-initialised by the callee (on the stream).
+ *
+ * Index conventions: image[a][b][c] is the reference's
+ * (x_dims, y_dims, 3) array.  With transpose=1 (root variant, scene.py:55-75)
+ * pixel (a,b) is shaded with camera ray [b][a] -- the spatial transpose that
+ * Transform.__call__ performs once (transform.py:46).  With transpose=0 (orbit
+ * variant, orbit_experiments/scene.py:55-80: camera.o2w then shape.w2o, two
+ * transposes) pixel (a,b) is shaded with camera ray [a][b].
+ *
+ * Row slabs (multi-GPU sharding): a call renders image rows
+ * [row_begin, row_begin+row_count).  All per-pixel buffers passed to that call
+ * (image, hit_index, tmin, target, dl_dimage, jitter) are SLAB-LOCAL: their row
+ * index is (a - row_begin) and they hold row_count rows.
+ */
+#ifndef RRT_B200_H
+#define RRT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RRT_VERSION 100 /* 0.1.0 */
+
+/* shape kinds: shape.py:72 (Sphere), shape.py:16 (Square) */
+#define RRT_OBJ_SPHERE 0
+#define RRT_OBJ_SQUARE 1
+
+/* shaders: shader.py:23-53 (Phong), orbit_experiments/shader.py:45,48 (Phong with
+ * the specular term commented out), shader.py:9-20 (DepthMapShader) */
+#define RRT_SHADER_PHONG 0
+#define RRT_SHADER_PHONG_NOSPEC 1
+#define RRT_SHADER_DEPTH 2
+
+/* packed strides (floats) */
+#define RRT_W2O_STRIDE 12      /* rows 0..2 of shape.w2o.m, row-major 3x4 = [A | b]       */
+#define RRT_MAT_STRIDE 7       /* ka, kd, ks, shininess, color r, g, b   scene.py:89-101   */
+#define RRT_LIGHT_STRIDE 6     /* direction[3], intensity[3]             scene.py:78-86    */
+#define RRT_CAMERA_STRIDE 15   /* rows 0..2 of camera.o2w.m (3x4), look_at[3]              */
+#define RRT_OBJ_GRAD_STRIDE 19 /* d/d w2o[12] then d/d material[7]                         */
+#define RRT_GLOBAL_GRAD 21     /* d/d light dir[3], intensity[3], camera o2w[12], look_at[3] */
+
+/* flat gradient vector per scene: [N][RRT_OBJ_GRAD_STRIDE] then [RRT_GLOBAL_GRAD] */
+#define RRT_GRAD_SIZE(num_objects) ((size_t)(num_objects) * RRT_OBJ_GRAD_STRIDE + RRT_GLOBAL_GRAD)
+
+#define RRT_OK 0
+#define RRT_ERR_INVALID (-1)   /* bad argument (message in rrt_last_error)            */
+#define RRT_ERR_CUDA (-2)      /* CUDA runtime error at launch                        */
+#define RRT_ERR_UNSUPPORTED (-3)
+
+/*
+ * Scene descriptor: everything Scene.build() reads (scene.py:11-52).
+ * Passed by pointer from host memory; the pointers inside are device pointers.
+ * Batches of scenes (num_scenes = B > 1) use a per-scene stride in floats for each
+ * table; a stride of 0 shares the table across the batch.
+ */
+typedef struct rrt_scene {
+    int32_t n;            /* image side: camera.x_dims == camera.y_dims (scene.py:21,24) */
+    int32_t samples;      /* antialias_samples S (scene.py:18)                           */
+    int32_t num_objects;  /* N = len(scene.shapes)                                        */
+    int32_t num_scenes;   /* B >= 1                                                       */
+    int32_t shader;       /* RRT_SHADER_*                                                 */
+    int32_t transpose;    /* 1 = root camera variant, 0 = orbit variant (see above)       */
+    int32_t row_begin;    /* first image row rendered by this call                        */
+    int32_t row_count;    /* rows rendered; 0 means n - row_begin                         */
+    float max_depth;      /* DepthMapShader.maxDepth (shader.py:11)                       */
+    int32_t camera_grad;  /* 1: also produce d/d camera.o2w and d/d look_at               */
+    uint64_t seed;        /* jitter seed, used only when jitter_x == NULL                 */
+
+    const int32_t* obj_type; /* [N] RRT_OBJ_*, list order = scene.shapes order           */
+    const float* w2o;        /* [B][N][RRT_W2O_STRIDE]                                    */
+    const float* material;   /* [B][N][RRT_MAT_STRIDE]                                    */
+    const float* light;      /* [B][RRT_LIGHT_STRIDE]   only lights[0] is used, shader.py:33 */
+    const float* camera;     /* [B][RRT_CAMERA_STRIDE]                                    */
+    /* Anti-alias jitter in [0,1), IMAGE index space, slab-local:
+     * jitter_x[scene][a - row_begin][b][s] is the value the reference adds to ray
+     * channel 0 of the ray that shades pixel (a,b) (scene.py:24-25,31-32,73-74).
+     * NULL => in-kernel counter RNG keyed by (seed, scene, a*n+b, s).                   */
+    const float* jitter_x;
+    const float* jitter_y;
+
+    int64_t w2o_scene_stride;      /* floats between scenes; 0 = shared */
+    int64_t material_scene_stride;
+    int64_t light_scene_stride;
+    int64_t camera_scene_stride;
+    int64_t jitter_scene_stride;
+} rrt_scene;
+
+int rrt_version(void);
+const char* rrt_last_error(void);
+
+/*
+ * Forward render.  Replaces Scene.build() + theano.function([], image)()
+ * (scene.py:18-52; optimize_brightness.py:43-46).
+ *   image      [B][rows][n][3] float32   mean over S samples, background 0
+ *   hit_index  [B][S][rows][n] int32 or NULL: winning shape per ray, -1 = none
+ *   tmin       [B][S][rows][n] float32 or NULL: min_dists (scene.py:47), +inf = none
+ */
+int rrt_render_forward(const rrt_scene* scene, float* image, int32_t* hit_index,
+                       float* tmin, void* stream);
+
+/*
+ * Reverse pass.  Replaces T.grad(loss, params) through the render graph
+ * (optimize.py:25,73; orbit_experiments/optimize.py:76) for an arbitrary upstream
+ * gradient.
+ *   dl_dimage  [B][rows][n][3] float32
+ *   hit_index  as written by rrt_render_forward, or NULL to re-run the nearest-hit
+ *              sweep (hit records themselves are always recomputed, never stored)
+ *   grad       [B][RRT_GRAD_SIZE(N)] float32, zeroed by the callee then accumulated
+ */
+int rrt_render_backward(const rrt_scene* scene, const float* dl_dimage,
+                        const int32_t* hit_index, float* grad, void* stream);
+
+/*
+ * Fused forward + squared-error loss + reverse pass in one kernel: hit records
+ * stay in registers.  Covers cost = sum_c w_c * sum((image - target)^2)
+ * (match_mirror.py:45; autoencoder.py:76; autoencoder_2ly.py:91; test_balls.py via
+ * channel weights (1,0,0)).
+ *   target          [B][rows][n][3] float32
+ *   channel_weight  HOST float[3] or NULL (= 1,1,1)
+ *   image, hit_index  optional outputs (NULL to skip the stores)
+ *   loss            [B] float64, zeroed by the callee
+ *   grad            [B][RRT_GRAD_SIZE(N)] float32, zeroed by the callee
+ */
+int rrt_render_fused_mse(const rrt_scene* scene, const float* target,
+                         const float* channel_weight, float* image, int32_t* hit_index,
+                         double* loss, float* grad, void* stream);
+
+/*
+ * FP32 pipe micro-benchmark used as the roofline denominator (MEASURED_PEAKS.json
+ * has no FP32 entry).  mode 0 = scalar FFMA, 1 = packed FFMA2 (fma.rn.f32x2).
+ * Synchronises the stream.  tflops is a HOST pointer.
+ */
+int rrt_measure_fp32_peak(int mode, int iters, double* tflops, double* ms, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RRT_B200_H */
