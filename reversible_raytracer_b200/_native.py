@@ -1,0 +1,92 @@
+"""ctypes binding of the C ABI in include/rrt_b200.h (librrt_b200.so).
+
+The product path has NO fallback: if the CUDA library is missing or a call
+fails, an exception is raised.  Nothing under oracle/ is ever imported here.
+"""
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+LIB_PATH = os.path.join(HERE, 'librrt_b200.so')
+SRC = os.path.join(HERE, 'csrc', 'rrt_kernels.cu')
+INCLUDE = os.path.join(REPO, 'include')
+
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+              '-Xcompiler', '-fPIC', '-shared']
+
+OBJ_SPHERE, OBJ_SQUARE = 0, 1
+SHADER_PHONG, SHADER_PHONG_NOSPEC, SHADER_DEPTH = 0, 1, 2
+W2O_STRIDE, MAT_STRIDE, LIGHT_STRIDE, CAMERA_STRIDE = 12, 7, 6, 15
+OBJ_GRAD_STRIDE, GLOBAL_GRAD = 19, 21
+
+
+def grad_size(num_objects):
+    return num_objects * OBJ_GRAD_STRIDE + GLOBAL_GRAD
+
+
+class RrtScene(C.Structure):
+    """`struct rrt_scene` of include/rrt_b200.h."""
+    _fields_ = [
+        ('n', C.c_int32), ('samples', C.c_int32), ('num_objects', C.c_int32),
+        ('num_scenes', C.c_int32), ('shader', C.c_int32), ('transpose', C.c_int32),
+        ('row_begin', C.c_int32), ('row_count', C.c_int32), ('max_depth', C.c_float),
+        ('camera_grad', C.c_int32), ('seed', C.c_uint64),
+        ('obj_type', C.c_void_p), ('w2o', C.c_void_p), ('material', C.c_void_p),
+        ('light', C.c_void_p), ('camera', C.c_void_p),
+        ('jitter_x', C.c_void_p), ('jitter_y', C.c_void_p),
+        ('w2o_scene_stride', C.c_int64), ('material_scene_stride', C.c_int64),
+        ('light_scene_stride', C.c_int64), ('camera_scene_stride', C.c_int64),
+        ('jitter_scene_stride', C.c_int64),
+    ]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/rrt_kernels.cu for sm_100a into librrt_b200.so (in-tree)."""
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= max(
+            os.path.getmtime(SRC), os.path.getmtime(os.path.join(INCLUDE, 'rrt_b200.h'))):
+        return LIB_PATH
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    cmd = [nvcc] + NVCC_FLAGS + ['-I', INCLUDE, '-o', LIB_PATH, SRC]
+    if verbose:
+        cmd.insert(1, '-Xptxas=-v')
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; raises NativeError when it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError('librrt_b200.so is not built (run `python -c "import __graft_entry__ as g; g.build()"`); '
+                              'there is no CPU fallback')
+        L = C.CDLL(LIB_PATH)
+        L.rrt_version.restype = C.c_int
+        L.rrt_last_error.restype = C.c_char_p
+        P = C.c_void_p
+        L.rrt_render_forward.argtypes = [C.POINTER(RrtScene), P, P, P, P]
+        L.rrt_render_backward.argtypes = [C.POINTER(RrtScene), P, P, P, P]
+        L.rrt_render_fused_mse.argtypes = [C.POINTER(RrtScene), P, C.POINTER(C.c_float), P, P, P, P, P]
+        L.rrt_measure_fp32_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), P]
+        for f in (L.rrt_render_forward, L.rrt_render_backward, L.rrt_render_fused_mse, L.rrt_measure_fp32_peak):
+            f.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+EXPORTS = ['rrt_version', 'rrt_last_error', 'rrt_render_forward', 'rrt_render_backward',
+           'rrt_render_fused_mse', 'rrt_measure_fp32_peak']
+
+
+def check(rc, what):
+    if rc != 0:
+        raise NativeError('%s failed (%d): %s' % (what, rc, lib().rrt_last_error().decode()))

@@ -1,0 +1,1050 @@
+// rrt_kernels.cu -- hand-written sm_100a kernels + the C ABI of include/rrt_b200.h.
+//
+// One hot path of lebek/reversible-raytracer, rebuilt B200-first (paths below are
+// relative to the reference checkout; nothing here is translated from it -- the
+// reference is a dense Theano graph, this is a per-ray register-resident design):
+//   Camera.make_rays        scene.py:61-75 (+ orbit_experiments/scene.py:55-80)
+//   Transform.__call__      transform.py:40-47
+//   Sphere / Square         shape.py:25-69, 78-83, 109-138
+//   Phong / DepthMap        shader.py:14-20, 28-53
+//   Scene.build             scene.py:18-52
+//   T.grad(loss, params)    optimize.py:25,73
+//
+// Design (DESIGN.md has the long form):
+//   * one thread owns PIX pixels x SPT anti-alias samples = 8 rays, kept in
+//     registers as 4 packed pairs; the ray-object sweep is issued as packed
+//     FFMA2/FMUL2 (fma.rn.f32x2 / mul.rn.f32x2, sm_100+) with the object constants
+//     broadcast from shared memory (LDS.128, scalar-broadcast operand form);
+//   * the object table is transformed once per CTA into 64-byte sweep records in
+//     shared memory, streamed in chunks when N is large;
+//   * hits are rare per (ray, object): the hot loop only tests det > 0 and branches
+//     to a scalar canonical-order routine that computes t and updates the winner;
+//   * shading and the reverse pass run once per winning ray after the sweep; hit
+//     records are recomputed, never stored; per-object gradients are reduced
+//     thread -> warp (shuffle) -> CTA (shared-memory slots) -> one atomic per CTA.
+//   * every mask-determining operation is an explicit IEEE round-to-nearest
+//     intrinsic or PTX instruction in the canonical order shared with
+//     oracle/oracle_c.c, so hit masks are bit-exact against the oracle.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "rrt_b200.h"
+
+namespace {
+
+typedef unsigned long long u64;
+
+constexpr int kRays = 8;          // rays per thread (4 packed pairs)
+constexpr int kObjChunk = 1024;   // objects staged in shared memory at a time (64 KB)
+constexpr int kSlots = 32;        // per-CTA gradient slots (object -> 19 floats)
+constexpr int kSlotStride = 20;
+constexpr int kMaxWarps = 8;
+
+enum { MODE_FWD = 0, MODE_BWD = 1, MODE_FUSED = 2 };
+
+struct KParams {
+    rrt_scene sc;
+    int rows;
+    float* image;
+    int32_t* hit_out;
+    float* tmin_out;
+    const float* dl_dimage;
+    const int32_t* hit_in;
+    const float* target;
+    float cw[3];
+    double* loss;
+    float* grad;
+};
+
+// ---------------------------------------------------------------- packed f32x2
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+    u64 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void upk(u64 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 bc(float v) { return pk(v, v); }  // ptxas folds this into the .F32 broadcast operand
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// ---------------------------------------------------------------- jitter RNG
+// Same function (by specification) as orc_rng in oracle/oracle_c.c.
+__device__ __forceinline__ float rrt_rng(u64 seed, uint32_t scene, uint32_t pix, uint32_t s, uint32_t axis) {
+    u64 key = ((u64)scene << 40) ^ ((u64)pix << 8) ^ ((u64)s << 1) ^ (u64)axis;
+    u64 z = seed + (key + 1ull) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (float)(uint32_t)(z >> 40) * 5.9604644775390625e-08f;
+}
+
+// ---------------------------------------------------------------- primary rays
+// np.linspace(start, stop, n)[i] = fl(fl(i*step) + start), last element = stop.
+__device__ __forceinline__ double lin(int i, int n, double start, double stop) {
+    if (n == 1) return start;
+    if (i == n - 1) return stop;
+    double step = __ddiv_rn(stop - start, (double)(n - 1));
+    return __dadd_rn(__dmul_rn((double)i, step), start);
+}
+
+// Camera.make_rays scene.py:66-72: float64 grid, normalise, cast to float32.
+__device__ __forceinline__ void base_ray(int n, int i, int j, float& rx, float& ry, float& rz) {
+    double x = lin(i, n, 0.5, -0.5);
+    double y = lin(j, n, -0.5, 0.5);
+    double s = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), 1.0);
+    double nrm = __dsqrt_rn(s);
+    rx = __double2float_rn(__ddiv_rn(x, nrm));
+    ry = __double2float_rn(__ddiv_rn(y, nrm));
+    rz = __double2float_rn(__ddiv_rn(1.0, nrm));
+}
+
+// scene.py:31-32 then :73-74, all float32 round-to-nearest.
+__device__ __forceinline__ float jitter_offset(float u, int s, int S, int n) {
+    return __fdiv_rn(__fdiv_rn(__fadd_rn(u, (float)s), (float)S), (float)n);
+}
+
+__device__ __forceinline__ float dot3_canon(float a0, float a1, float a2, float v0, float v1, float v2) {
+    return __fmaf_rn(a2, v2, __fmaf_rn(a1, v1, __fmul_rn(a0, v0)));
+}
+
+// ---------------------------------------------------------------- object records
+// 64-byte sweep record (4 x float4) in shared memory:
+//   q0 = (a00, a11, a22, o'x)   q1 = (o'y, o'z, -cc, flags)
+//   q2 = (a01, a02, a10, a12)   q3 = (a20, a21, 0, 0)
+// flags bit0 = square, bit1 = general (some off-diagonal of A is non-zero).
+struct Obj {
+    float a[9];
+    float o[3];
+    float ncc;
+    int flags;
+};
+
+struct Globals {       // per-scene constants, held in shared memory
+    float C[9], ct[3]; // camera.o2w rows 0..2
+    float look[3];
+    float L[3], I[3];
+    float Lh[3], Ln;
+};
+
+__device__ __forceinline__ void make_obj(const float* __restrict__ w, int type, const float* ct, Obj& ob) {
+    float m[12];
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    float4 r0 = __ldg(w4), r1 = __ldg(w4 + 1), r2 = __ldg(w4 + 2);
+    m[0] = r0.x; m[1] = r0.y; m[2] = r0.z; m[3] = r0.w;
+    m[4] = r1.x; m[5] = r1.y; m[6] = r1.z; m[7] = r1.w;
+    m[8] = r2.x; m[9] = r2.y; m[10] = r2.z; m[11] = r2.w;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        ob.a[r * 3 + 0] = m[r * 4 + 0];
+        ob.a[r * 3 + 1] = m[r * 4 + 1];
+        ob.a[r * 3 + 2] = m[r * 4 + 2];
+        // o' = A.c + b  (transform.py:44)
+        ob.o[r] = __fmaf_rn(m[r * 4 + 2], ct[2], __fmaf_rn(m[r * 4 + 1], ct[1], __fmaf_rn(m[r * 4 + 0], ct[0], m[r * 4 + 3])));
+    }
+    float cc = __fsub_rn(__fmaf_rn(ob.o[2], ob.o[2], __fmaf_rn(ob.o[1], ob.o[1], __fmul_rn(ob.o[0], ob.o[0]))), 1.0f);
+    ob.ncc = -cc;
+    bool general = (ob.a[1] != 0.f) || (ob.a[2] != 0.f) || (ob.a[3] != 0.f) || (ob.a[5] != 0.f) || (ob.a[6] != 0.f) || (ob.a[7] != 0.f);
+    ob.flags = (type == RRT_OBJ_SQUARE ? 1 : 0) | (general ? 2 : 0);
+}
+
+__device__ __forceinline__ void store_rec(float4* rec, const Obj& ob) {
+    rec[0] = make_float4(ob.a[0], ob.a[4], ob.a[8], ob.o[0]);
+    rec[1] = make_float4(ob.o[1], ob.o[2], ob.ncc, __int_as_float(ob.flags));
+    rec[2] = make_float4(ob.a[1], ob.a[2], ob.a[3], ob.a[5]);
+    rec[3] = make_float4(ob.a[6], ob.a[7], 0.f, 0.f);
+}
+
+__device__ __forceinline__ void load_rec(const float4* rec, Obj& ob) {
+    float4 q0 = rec[0], q1 = rec[1], q2 = rec[2], q3 = rec[3];
+    ob.a[0] = q0.x; ob.a[4] = q0.y; ob.a[8] = q0.z; ob.o[0] = q0.w;
+    ob.o[1] = q1.x; ob.o[2] = q1.y; ob.ncc = q1.z; ob.flags = __float_as_int(q1.w);
+    ob.a[1] = q2.x; ob.a[2] = q2.y; ob.a[3] = q2.z; ob.a[5] = q2.w;
+    ob.a[6] = q3.x; ob.a[7] = q3.y;
+}
+
+// ---------------------------------------------------------------- one ray-object test
+// Canonical order: the scalar twin of the packed sweep; bit-identical
+// to orc_test in oracle/oracle_c.c.
+struct HitRec {
+    float d[3];
+    float vn, pd, det, t;
+};
+
+__device__ __forceinline__ float obj_test(const Obj& ob, float dwx, float dwy, float dwz, HitRec& h) {
+    h.d[0] = dot3_canon(ob.a[0], ob.a[1], ob.a[2], dwx, dwy, dwz);
+    h.d[1] = dot3_canon(ob.a[3], ob.a[4], ob.a[5], dwx, dwy, dwz);
+    h.d[2] = dot3_canon(ob.a[6], ob.a[7], ob.a[8], dwx, dwy, dwz);
+    const float inf = __int_as_float(0x7f800000);
+    if (!(ob.flags & 1)) {  // Sphere.distance shape.py:109-126
+        h.vn = dot3_canon(h.d[0], h.d[1], h.d[2], h.d[0], h.d[1], h.d[2]);
+        h.pd = dot3_canon(h.d[0], h.d[1], h.d[2], ob.o[0], ob.o[1], ob.o[2]);
+        h.det = __fmaf_rn(h.pd, h.pd, __fmul_rn(h.vn, ob.ncc));
+        if (!(h.det > 0.0f)) return h.t = inf;
+        float sq = __fsqrt_rn(h.det);
+        return h.t = __fdiv_rn(__fsub_rn(-h.pd, sq), h.vn);
+    } else {                // Square._hit shape.py:25-40
+        float t = __fdiv_rn(-ob.o[2], h.d[2]);
+        float px = __fmaf_rn(t, h.d[0], ob.o[0]);
+        float py = __fmaf_rn(t, h.d[1], ob.o[1]);
+        bool m = (h.d[2] != 0.0f) && (t > 0.0f) && (px > -0.5f) && (px < 0.5f) && (py > -0.5f) && (py < 0.5f);
+        h.vn = h.pd = h.det = 0.f;
+        return h.t = m ? t : inf;
+    }
+}
+
+// out-of-line on purpose: keeps the hot loop's register and code footprint small
+__device__ __noinline__ float rare_hit_t(const float4* rec, float dwx, float dwy, float dwz) {
+    Obj ob;
+    load_rec(rec, ob);
+    HitRec h;
+    return obj_test(ob, dwx, dwy, dwz, h);
+}
+
+// ---------------------------------------------------------------- packed sweep
+template <bool GENERAL>
+__device__ __forceinline__ u64 pair_det(const float4& q0, const float4& q1, const float4& q2, const float4& q3,
+                                        u64 dx, u64 dy, u64 dz) {
+    u64 ex, ey, ez;
+    if (GENERAL) {
+        ex = fma2(bc(q2.y), dz, fma2(bc(q2.x), dy, mul2(bc(q0.x), dx)));
+        ey = fma2(bc(q2.w), dz, fma2(bc(q0.y), dy, mul2(bc(q2.z), dx)));
+        ez = fma2(bc(q0.z), dz, fma2(bc(q3.y), dy, mul2(bc(q3.x), dx)));
+    } else {
+        ex = mul2(bc(q0.x), dx);
+        ey = mul2(bc(q0.y), dy);
+        ez = mul2(bc(q0.z), dz);
+    }
+    u64 vn = fma2(ez, ez, fma2(ey, ey, mul2(ex, ex)));
+    u64 pd = fma2(ez, bc(q1.y), fma2(ey, bc(q1.x), mul2(ex, bc(q0.w))));
+    return fma2(pd, pd, mul2(vn, bc(q1.z)));
+}
+
+struct RayPack {
+    u64 dx[kRays / 2], dy[kRays / 2], dz[kRays / 2];
+};
+
+#define RRT_RARE(r, detv)                                                      \
+    if ((detv) > 0.0f) {                                                       \
+        float lo_, hi_, x_, y_, z_;                                            \
+        upk(rp.dx[(r) >> 1], lo_, hi_); x_ = ((r) & 1) ? hi_ : lo_;            \
+        upk(rp.dy[(r) >> 1], lo_, hi_); y_ = ((r) & 1) ? hi_ : lo_;            \
+        upk(rp.dz[(r) >> 1], lo_, hi_); z_ = ((r) & 1) ? hi_ : lo_;            \
+        float t_ = rare_hit_t(rec, x_, y_, z_);                                \
+        if (t_ < tmin[(r)]) { tmin[(r)] = t_; idx[(r)] = kbase + k; }          \
+    }
+
+// Sweep `count` staged objects (global indices kbase..kbase+count-1) over the 8 rays.
+// list order + strict '<' == scene.py:46-47 (earlier shape wins ties).
+template <bool FAST>
+__device__ __forceinline__ void sweep_chunk(const float4* __restrict__ tab, int count, int kbase, const RayPack& rp,
+                                            float (&tmin)[kRays], int (&idx)[kRays]) {
+#pragma unroll 2
+    for (int k = 0; k < count; k++) {
+        const float4* rec = tab + 4 * k;
+        float4 q0 = rec[0], q1 = rec[1];
+        float4 q2, q3;
+        int flags = FAST ? 0 : __float_as_int(q1.w);
+        u64 det[kRays / 2];
+        if (FAST || flags == 0) {
+#pragma unroll
+            for (int p = 0; p < kRays / 2; p++) det[p] = pair_det<false>(q0, q1, q0, q0, rp.dx[p], rp.dy[p], rp.dz[p]);
+        } else if (flags == 2) {
+            q2 = rec[2];
+            q3 = rec[3];
+#pragma unroll
+            for (int p = 0; p < kRays / 2; p++) det[p] = pair_det<true>(q0, q1, q2, q3, rp.dx[p], rp.dy[p], rp.dz[p]);
+        } else {
+            // squares: every ray takes the scalar canonical routine
+            const float one = 1.0f;
+#pragma unroll
+            for (int p = 0; p < kRays / 2; p++) det[p] = pk(one, one);
+        }
+        float dl[kRays];
+#pragma unroll
+        for (int p = 0; p < kRays / 2; p++) upk(det[p], dl[2 * p], dl[2 * p + 1]);
+        bool any = false;
+#pragma unroll
+        for (int r = 0; r < kRays; r++) any |= (dl[r] > 0.0f);
+        if (__builtin_expect(any, 0)) {
+            RRT_RARE(0, dl[0]) RRT_RARE(1, dl[1]) RRT_RARE(2, dl[2]) RRT_RARE(3, dl[3])
+            RRT_RARE(4, dl[4]) RRT_RARE(5, dl[5]) RRT_RARE(6, dl[6]) RRT_RARE(7, dl[7])
+        }
+    }
+}
+
+// ---------------------------------------------------------------- shading (float32)
+struct ShadeRec {
+    float t, d[3], o[3], pn, nrm[3], ndl, rm[3], rv, pw, ph;
+    bool inside[3];
+};
+
+__device__ __forceinline__ void shade(int shader, float max_depth, const Obj& ob, const float* mat, const Globals& g,
+                                      const HitRec& h, ShadeRec& r, float rgb[3]) {
+    r.t = h.t;
+#pragma unroll
+    for (int c = 0; c < 3; c++) { r.d[c] = h.d[c]; r.o[c] = ob.o[c]; }
+    if (shader == RRT_SHADER_DEPTH) {  // shader.py:14-20
+        float v = 1.0f - r.t / max_depth;
+        rgb[0] = rgb[1] = rgb[2] = v;
+        return;
+    }
+    if (!(ob.flags & 1)) {  // Sphere.normals shape.py:134-137 (object-space normal)
+        float p0 = fmaf(r.t, r.d[0], r.o[0]), p1 = fmaf(r.t, r.d[1], r.o[1]), p2 = fmaf(r.t, r.d[2], r.o[2]);
+        r.pn = sqrtf(p0 * p0 + p1 * p1 + p2 * p2);
+        float inv = 1.0f / r.pn;
+        r.nrm[0] = p0 * inv; r.nrm[1] = p1 * inv; r.nrm[2] = p2 * inv;
+    } else {                // Square.normals shape.py:55-68
+        r.nrm[0] = r.nrm[1] = 0.f;
+        r.nrm[2] = (ob.o[2] > 0.0f) ? 1.0f : -1.0f;
+        r.pn = 1.0f;
+    }
+    r.ndl = -(r.nrm[0] * g.Lh[0] + r.nrm[1] * g.Lh[1] + r.nrm[2] * g.Lh[2]);  // shader.py:40
+    r.ph = mat[0] + mat[1] * r.ndl;
+    r.rv = 0.f; r.pw = 0.f;
+    if (shader == RRT_SHADER_PHONG) {  // shader.py:43-45
+#pragma unroll
+        for (int c = 0; c < 3; c++) r.rm[c] = 2.0f * r.ndl * r.nrm[c] + g.Lh[c];
+        r.rv = r.rm[0] * g.look[0] + r.rm[1] * g.look[1] + r.rm[2] * g.look[2];
+        r.pw = powf(r.rv, mat[3]);
+        r.ph += mat[2] * r.pw;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {      // shader.py:50-51
+        float v = r.ph * mat[4 + c] * g.I[c];
+        r.inside[c] = (v >= 0.0f && v <= 1.0f);
+        rgb[c] = fminf(fmaxf(v, 0.0f), 1.0f);
+    }
+}
+
+// ---------------------------------------------------------------- reverse pass, one winning ray
+// Closed form of T.grad through the winner (masks constant).  og[19] receives
+// [M = sum g_d' r_cam^T (9), g_b = sum g_o' (3), d/d(ka,kd,ks,sh,r,g,b)];
+// gg[9] receives [d/d Lhat (3), d/d intensity (3), d/d look_at (3)].
+// The chain M -> d/dA, d/d camera and Lhat -> L is applied by finalize_grads.
+__device__ __forceinline__ void backward_ray(int shader, float max_depth, const Obj& ob, const float* mat,
+                                             const Globals& g, const HitRec& h, const ShadeRec& r, const float rc[3],
+                                             const float gc[3], float og[19], float gg[9]) {
+    float g_t = 0.f;
+    float g_o[3] = {0.f, 0.f, 0.f}, g_d[3] = {0.f, 0.f, 0.f};
+    const bool sphere = !(ob.flags & 1);
+    if (shader == RRT_SHADER_DEPTH) {
+        g_t = -(gc[0] + gc[1] + gc[2]) / max_depth;
+    } else {
+        float g_ph = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (!r.inside[c]) continue;
+            g_ph += gc[c] * mat[4 + c] * g.I[c];
+            og[16 + c] += gc[c] * r.ph * g.I[c];
+            gg[3 + c] += gc[c] * r.ph * mat[4 + c];
+        }
+        og[12] += g_ph;
+        og[13] += g_ph * r.ndl;
+        float g_ndl = g_ph * mat[1];
+        float g_n[3] = {0.f, 0.f, 0.f}, g_Lh[3] = {0.f, 0.f, 0.f};
+        if (shader == RRT_SHADER_PHONG) {
+            og[14] += g_ph * r.pw;
+            if (r.rv > 0.0f) og[15] += g_ph * mat[2] * r.pw * logf(r.rv);
+            float dpw = (r.rv != 0.0f) ? r.pw / r.rv : powf(r.rv, mat[3] - 1.0f);  // rv^(sh-1)
+            float g_rv = g_ph * mat[2] * mat[3] * dpw;
+            float g_rm[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                g_rm[c] = g_rv * g.look[c];
+                gg[6 + c] += g_rv * r.rm[c];
+            }
+            g_ndl += 2.0f * (g_rm[0] * r.nrm[0] + g_rm[1] * r.nrm[1] + g_rm[2] * r.nrm[2]);
+#pragma unroll
+            for (int c = 0; c < 3; c++) { g_n[c] += 2.0f * r.ndl * g_rm[c]; g_Lh[c] += g_rm[c]; }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) { g_n[c] -= g_ndl * g.Lh[c]; g_Lh[c] -= g_ndl * r.nrm[c]; }
+#pragma unroll
+        for (int c = 0; c < 3; c++) gg[c] += g_Lh[c];
+        if (sphere) {
+            float ndg = r.nrm[0] * g_n[0] + r.nrm[1] * g_n[1] + r.nrm[2] * g_n[2];
+            float inv = 1.0f / r.pn;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                float gp = (g_n[c] - r.nrm[c] * ndg) * inv;
+                g_o[c] = gp;
+                g_t += gp * r.d[c];
+                g_d[c] = r.t * gp;
+            }
+        }
+    }
+    if (sphere) {
+        float ivn = 1.0f / h.vn;
+        float g_pd = -g_t * ivn, g_s = -g_t * ivn, g_vn = -g_t * r.t * ivn;
+        float g_det = g_s / (2.0f * sqrtf(h.det));
+        g_pd += 2.0f * h.pd * g_det;
+        g_vn += ob.ncc * g_det;            // -cc * g_det
+        float g_cc = -h.vn * g_det;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            g_o[c] += 2.0f * r.o[c] * g_cc + r.d[c] * g_pd;
+            g_d[c] += r.o[c] * g_pd + 2.0f * r.d[c] * g_vn;
+        }
+    } else {  // t = -o'_z / d'_z
+        g_o[2] += -g_t / r.d[2];
+        g_d[2] += -g_t * r.t / r.d[2];
+    }
+#pragma unroll
+    for (int rr = 0; rr < 3; rr++) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) og[rr * 3 + c] += g_d[rr] * rc[c];
+        og[9 + rr] += g_o[rr];
+    }
+}
+
+// ---------------------------------------------------------------- gradient reduction
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// find-or-insert a CTA slot for object `key` (called by one lane); -1 = table full
+__device__ __forceinline__ int slot_for(int* slot_key, int key) {
+    int h = key & (kSlots - 1);
+#pragma unroll 1
+    for (int probe = 0; probe < kSlots; probe++) {
+        int old = atomicCAS(&slot_key[h], -1, key);
+        if (old == -1 || old == key) return h;
+        h = (h + 1) & (kSlots - 1);
+    }
+    return -1;
+}
+
+// All 32 lanes call this together.  Each lane holds (key, acc[19]); lanes with the
+// same key are summed by shuffle and one lane adds the sum to the CTA slot.
+__device__ __forceinline__ void warp_flush(int key, float (&acc)[19], int* slot_key, float* slots, float* gobj, int lane) {
+    unsigned active = __ballot_sync(0xffffffffu, key >= 0);
+    while (active) {
+        int leader = __ffs(active) - 1;
+        int k = __shfl_sync(0xffffffffu, key, leader);
+        bool mine = (key == k);
+        active &= ~__ballot_sync(0xffffffffu, mine);
+        int slot = 0;
+        if (lane == 0) slot = slot_for(slot_key, k);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+#pragma unroll
+        for (int v = 0; v < 19; v++) {
+            float x = warp_sum(mine ? acc[v] : 0.f);
+            if (lane == 0 && x != 0.f) {
+                if (slot >= 0) atomicAdd(&slots[slot * kSlotStride + v], x);
+                else atomicAdd(&gobj[(size_t)k * RRT_OBJ_GRAD_STRIDE + v], x);
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < 19; v++) acc[v] = 0.f;
+}
+
+// ---------------------------------------------------------------- the render kernel
+// grid = (ceil(n / (32*PIX)), ceil(rows / warps), B); block = 32 * warps.
+// Thread (warp w, lane l) owns pixels (row = tile_row0 + w, cols = col0 + l*PIX .. +PIX-1),
+// each with SPT samples: PIX*SPT = 8 rays.  S > SPT (generic path, PIX = 1) loops
+// over chunks of SPT samples.
+template <int PIX, int SPT, int MODE>
+__global__ void __launch_bounds__(256, 2) render_kernel(const __grid_constant__ KParams P) {
+    extern __shared__ float4 smem_tab[];  // kObjChunk (or N) sweep records
+    __shared__ Globals g;
+    __shared__ int slot_key[kSlots];
+    __shared__ float slots[kSlots * kSlotStride];
+    __shared__ float gglob[9];
+    __shared__ float loss_warp[kMaxWarps];
+    __shared__ int all_fast_s;
+
+    const rrt_scene& sc = P.sc;
+    const int n = sc.n, S = sc.samples, N = sc.num_objects;
+    const int scene = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int al = blockIdx.y * nwarps + warp;      // slab-local row
+    const int a = sc.row_begin + al;                // image row
+    const int b0 = (blockIdx.x * 32 + lane) * PIX;  // first column of this thread
+    const bool row_ok = al < P.rows;
+
+    // ---- per-scene constants
+    if (tid < 32) {
+        const float* cam = sc.camera + (size_t)scene * sc.camera_scene_stride;
+        const float* li = sc.light + (size_t)scene * sc.light_scene_stride;
+        if (tid < 3) {
+            g.C[tid * 3 + 0] = cam[tid * 4 + 0];
+            g.C[tid * 3 + 1] = cam[tid * 4 + 1];
+            g.C[tid * 3 + 2] = cam[tid * 4 + 2];
+            g.ct[tid] = cam[tid * 4 + 3];
+            g.look[tid] = cam[12 + tid];
+            g.L[tid] = li[tid];
+            g.I[tid] = li[3 + tid];
+        }
+        __syncwarp();
+        if (tid == 0) {
+            float ln = sqrtf(g.L[0] * g.L[0] + g.L[1] * g.L[1] + g.L[2] * g.L[2]);  // scene.py:83-86
+            g.Ln = ln;
+            g.Lh[0] = g.L[0] / ln; g.Lh[1] = g.L[1] / ln; g.Lh[2] = g.L[2] / ln;
+            all_fast_s = 1;
+        }
+        if (tid < kSlots) slot_key[tid] = -1;
+        if (tid < 9) gglob[tid] = 0.f;
+    }
+    for (int q = tid; q < kSlots * kSlotStride; q += blockDim.x) slots[q] = 0.f;
+    __syncthreads();
+
+    const float* w2o = sc.w2o + (size_t)scene * sc.w2o_scene_stride;
+    const float* mats = sc.material + (size_t)scene * sc.material_scene_stride;
+    float* gobj = (MODE != MODE_FWD) ? P.grad + (size_t)scene * RRT_GRAD_SIZE(N) : nullptr;
+
+    // base rays (float64 grid -> float32), one per owned pixel
+    float bx[PIX], by[PIX], bz[PIX];
+#pragma unroll
+    for (int px = 0; px < PIX; px++) {
+        int b = b0 + px;
+        int i = sc.transpose ? b : a, j = sc.transpose ? a : b;
+        if (row_ok && b < n) base_ray(n, i, j, bx[px], by[px], bz[px]);
+        else { bx[px] = by[px] = bz[px] = 0.f; }
+    }
+
+    float pixsum[PIX][3];
+#pragma unroll
+    for (int px = 0; px < PIX; px++) pixsum[px][0] = pixsum[px][1] = pixsum[px][2] = 0.f;
+
+    // upstream gradient per pixel (MODE_BWD known up front; MODE_FUSED after shading)
+    float gpix[PIX][3];
+#pragma unroll
+    for (int px = 0; px < PIX; px++) {
+        gpix[px][0] = gpix[px][1] = gpix[px][2] = 0.f;
+        if (MODE == MODE_BWD) {
+            int b = b0 + px;
+            if (row_ok && b < n) {
+                size_t po = (((size_t)scene * P.rows + al) * n + b) * 3;
+                float inv = 1.0f / (float)S;
+                gpix[px][0] = P.dl_dimage[po] * inv; gpix[px][1] = P.dl_dimage[po + 1] * inv; gpix[px][2] = P.dl_dimage[po + 2] * inv;
+            }
+        }
+    }
+
+    float acc[19];
+#pragma unroll
+    for (int v = 0; v < 19; v++) acc[v] = 0.f;
+    int acc_key = -1;
+    float gg[9];
+#pragma unroll
+    for (int v = 0; v < 9; v++) gg[v] = 0.f;
+    float loss_part = 0.f;
+
+    const int nchunks_s = (S + SPT - 1) / SPT;
+#pragma unroll 1
+    for (int sc0 = 0; sc0 < nchunks_s; sc0++) {
+        // ---- build the 8 rays of this sample chunk
+        float rcx[kRays], rcy[kRays], rcz[kRays];  // camera-space rays (kept for the reverse pass)
+        RayPack rp;
+        {
+            float wx[kRays], wy[kRays], wz[kRays];
+#pragma unroll
+            for (int r = 0; r < kRays; r++) {
+                const int px = r / SPT, sl = r % SPT;
+                const int s = sc0 * SPT + sl;
+                const int b = b0 + px;
+                const bool ok = row_ok && b < n && s < S;
+                float jx = 0.f, jy = 0.f;
+                if (ok) {
+                    if (sc.jitter_x) {
+                        size_t off = (size_t)scene * sc.jitter_scene_stride + ((size_t)al * n + b) * S + s;
+                        jx = __ldg(sc.jitter_x + off);
+                        jy = __ldg(sc.jitter_y + off);
+                    } else {
+                        jx = rrt_rng(sc.seed, scene, (uint32_t)(a * n + b), s, 0);
+                        jy = rrt_rng(sc.seed, scene, (uint32_t)(a * n + b), s, 1);
+                    }
+                    rcx[r] = __fadd_rn(bx[px], jitter_offset(jx, s, S, n));
+                    rcy[r] = __fadd_rn(by[px], jitter_offset(jy, s, S, n));
+                    rcz[r] = bz[px];
+                    // camera.o2w (identity in the root variant)
+                    wx[r] = dot3_canon(g.C[0], g.C[1], g.C[2], rcx[r], rcy[r], rcz[r]);
+                    wy[r] = dot3_canon(g.C[3], g.C[4], g.C[5], rcx[r], rcy[r], rcz[r]);
+                    wz[r] = dot3_canon(g.C[6], g.C[7], g.C[8], rcx[r], rcy[r], rcz[r]);
+                } else {
+                    rcx[r] = rcy[r] = rcz[r] = 0.f;
+                    wx[r] = wy[r] = wz[r] = 0.f;  // zero direction never hits (det == 0)
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < kRays / 2; p++) {
+                rp.dx[p] = pk(wx[2 * p], wx[2 * p + 1]);
+                rp.dy[p] = pk(wy[2 * p], wy[2 * p + 1]);
+                rp.dz[p] = pk(wz[2 * p], wz[2 * p + 1]);
+            }
+        }
+
+        // ---- nearest-hit sweep (or stored winners)
+        float tmin[kRays];
+        int idx[kRays];
+#pragma unroll
+        for (int r = 0; r < kRays; r++) { tmin[r] = __int_as_float(0x7f800000); idx[r] = -1; }
+
+        const bool use_stored = (MODE == MODE_BWD) && (P.hit_in != nullptr);
+        if (use_stored) {
+#pragma unroll
+            for (int r = 0; r < kRays; r++) {
+                const int px = r / SPT, s = sc0 * SPT + r % SPT, b = b0 + px;
+                if (row_ok && b < n && s < S)
+                    idx[r] = P.hit_in[(((size_t)scene * S + s) * P.rows + al) * n + b];
+            }
+        } else {
+#pragma unroll 1
+            for (int kb = 0; kb < N; kb += kObjChunk) {
+                const int cnt = min(kObjChunk, N - kb);
+                if (kb > 0 || sc0 > 0) __syncthreads();   // previous chunk fully consumed
+                if (N > kObjChunk || sc0 == 0) {
+                    int fast = 1;
+                    for (int k = tid; k < cnt; k += blockDim.x) {
+                        Obj ob;
+                        make_obj(w2o + (size_t)(kb + k) * RRT_W2O_STRIDE, sc.obj_type[kb + k], g.ct, ob);
+                        store_rec(smem_tab + 4 * k, ob);
+                        fast &= (ob.flags == 0);
+                    }
+                    if (!fast) all_fast_s = 0;
+                }
+                __syncthreads();
+                if (all_fast_s) sweep_chunk<true>(smem_tab, cnt, kb, rp, tmin, idx);
+                else sweep_chunk<false>(smem_tab, cnt, kb, rp, tmin, idx);
+            }
+        }
+
+        // ---- spill the per-ray state to (L1-resident) local arrays for the rolled loops below
+        float l_rc[kRays][3];
+        int l_idx[kRays];
+#pragma unroll
+        for (int r = 0; r < kRays; r++) {
+            l_rc[r][0] = rcx[r]; l_rc[r][1] = rcy[r]; l_rc[r][2] = rcz[r];
+            l_idx[r] = idx[r];
+        }
+
+        // ---- outputs of the sweep
+        if (MODE != MODE_BWD) {
+#pragma unroll
+            for (int r = 0; r < kRays; r++) {
+                const int px = r / SPT, s = sc0 * SPT + r % SPT, b = b0 + px;
+                if (row_ok && b < n && s < S) {
+                    size_t ro = (((size_t)scene * S + s) * P.rows + al) * n + b;
+                    if (P.hit_out) P.hit_out[ro] = idx[r];
+                    if (MODE == MODE_FWD && P.tmin_out) P.tmin_out[ro] = tmin[r];
+                }
+            }
+        }
+
+        // ---- shade the winners (forward value)
+        if (MODE != MODE_BWD) {
+#pragma unroll 1
+            for (int r = 0; r < kRays; r++) {
+                const int k = l_idx[r];
+                if (k < 0) continue;
+                Obj ob;
+                make_obj(w2o + (size_t)k * RRT_W2O_STRIDE, sc.obj_type[k], g.ct, ob);
+                const float* mat = mats + (size_t)k * RRT_MAT_STRIDE;
+                float m7[7];
+#pragma unroll
+                for (int q = 0; q < 7; q++) m7[q] = __ldg(mat + q);
+                float dwx = dot3_canon(g.C[0], g.C[1], g.C[2], l_rc[r][0], l_rc[r][1], l_rc[r][2]);
+                float dwy = dot3_canon(g.C[3], g.C[4], g.C[5], l_rc[r][0], l_rc[r][1], l_rc[r][2]);
+                float dwz = dot3_canon(g.C[6], g.C[7], g.C[8], l_rc[r][0], l_rc[r][1], l_rc[r][2]);
+                HitRec h;
+                obj_test(ob, dwx, dwy, dwz, h);
+                ShadeRec sr;
+                float rgb[3];
+                shade(sc.shader, sc.max_depth, ob, m7, g, h, sr, rgb);
+                const int px = r / SPT;
+#pragma unroll
+                for (int q = 0; q < PIX; q++)
+                    if (q == px) { pixsum[q][0] += rgb[0]; pixsum[q][1] += rgb[1]; pixsum[q][2] += rgb[2]; }
+            }
+        }
+
+        const bool last_chunk = (sc0 == nchunks_s - 1);
+        // ---- pixel value, image store, loss and upstream gradient
+        if (MODE != MODE_BWD && last_chunk) {
+#pragma unroll
+            for (int px = 0; px < PIX; px++) {
+                const int b = b0 + px;
+                if (!(row_ok && b < n)) continue;
+                size_t po = (((size_t)scene * P.rows + al) * n + b) * 3;
+                float inv = 1.0f / (float)S;
+                float v0 = pixsum[px][0] * inv, v1 = pixsum[px][1] * inv, v2 = pixsum[px][2] * inv;  // scene.py:49-50
+                if (P.image) { P.image[po] = v0; P.image[po + 1] = v1; P.image[po + 2] = v2; }
+                if (MODE == MODE_FUSED) {
+                    float d0 = v0 - P.target[po], d1 = v1 - P.target[po + 1], d2 = v2 - P.target[po + 2];
+                    loss_part += P.cw[0] * d0 * d0 + P.cw[1] * d1 * d1 + P.cw[2] * d2 * d2;
+                    gpix[px][0] = 2.0f * P.cw[0] * d0 * inv;
+                    gpix[px][1] = 2.0f * P.cw[1] * d1 * inv;
+                    gpix[px][2] = 2.0f * P.cw[2] * d2 * inv;
+                }
+            }
+        }
+
+        // ---- reverse pass over the winners
+        if (MODE != MODE_FWD) {
+#pragma unroll 1
+            for (int r = 0; r < kRays; r++) {
+                int k = l_idx[r];
+                HitRec h;
+                Obj ob;
+                float m7[7];
+                float dwx = 0.f, dwy = 0.f, dwz = 0.f;
+                if (k >= 0) {
+                    make_obj(w2o + (size_t)k * RRT_W2O_STRIDE, sc.obj_type[k], g.ct, ob);
+                    dwx = dot3_canon(g.C[0], g.C[1], g.C[2], l_rc[r][0], l_rc[r][1], l_rc[r][2]);
+                    dwy = dot3_canon(g.C[3], g.C[4], g.C[5], l_rc[r][0], l_rc[r][1], l_rc[r][2]);
+                    dwz = dot3_canon(g.C[6], g.C[7], g.C[8], l_rc[r][0], l_rc[r][1], l_rc[r][2]);
+                    obj_test(ob, dwx, dwy, dwz, h);
+                    if (!(h.t < __int_as_float(0x7f800000))) k = -1;  // stale stored winner
+                }
+                // flush the running per-object accumulator when some lane changes object
+                const bool change = (k >= 0) && (acc_key >= 0) && (k != acc_key);
+                if (__any_sync(0xffffffffu, change)) {
+                    warp_flush(acc_key, acc, slot_key, slots, gobj, lane);
+                    acc_key = -1;
+                }
+                if (k >= 0) {
+                    const float* mat = mats + (size_t)k * RRT_MAT_STRIDE;
+#pragma unroll
+                    for (int q = 0; q < 7; q++) m7[q] = __ldg(mat + q);
+                    ShadeRec sr;
+                    float rgb[3];
+                    shade(sc.shader, sc.max_depth, ob, m7, g, h, sr, rgb);
+                    const int px = r / SPT;
+                    float gc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int q = 0; q < PIX; q++)
+                        if (q == px) { gc[0] = gpix[q][0]; gc[1] = gpix[q][1]; gc[2] = gpix[q][2]; }
+                    acc_key = k;
+                    backward_ray(sc.shader, sc.max_depth, ob, m7, g, h, sr, l_rc[r], gc, acc, gg);
+                }
+            }
+        }
+    }  // sample chunks
+
+    if (MODE != MODE_FWD) {
+        // ---- warp -> CTA -> global reduction
+        warp_flush(acc_key, acc, slot_key, slots, gobj, lane);
+#pragma unroll
+        for (int v = 0; v < 9; v++) {
+            float x = warp_sum(gg[v]);
+            if (lane == 0 && x != 0.f) atomicAdd(&gglob[v], x);
+        }
+        if (MODE == MODE_FUSED) {
+            float x = warp_sum(loss_part);
+            if (lane == 0) loss_warp[warp] = x;
+        }
+        __syncthreads();
+        for (int q = tid; q < kSlots * 19; q += blockDim.x) {
+            int s = q / 19, v = q - s * 19;
+            int key = slot_key[s];
+            float x = slots[s * kSlotStride + v];
+            if (key >= 0 && x != 0.f) atomicAdd(&gobj[(size_t)key * RRT_OBJ_GRAD_STRIDE + v], x);
+        }
+        float* gglobal = gobj + (size_t)N * RRT_OBJ_GRAD_STRIDE;
+        if (tid < 9) {
+            // layout: Lhat -> slots 0..2, intensity 3..5, look_at 18..20
+            int dst = tid < 6 ? tid : 12 + tid;
+            if (gglob[tid] != 0.f) atomicAdd(&gglobal[dst], gglob[tid]);
+        }
+        if (MODE == MODE_FUSED && tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < nwarps; w++) t += (double)loss_warp[w];
+            if (t != 0.0) atomicAdd(&P.loss[scene], t);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- gradient finalisation
+// One CTA per scene.  Converts the raw per-object sums [M, g_b] into d/d w2o and
+// folds the camera and light chains (see backward_ray).
+__global__ void finalize_grads(const __grid_constant__ KParams P) {
+    const rrt_scene& sc = P.sc;
+    const int N = sc.num_objects, scene = blockIdx.x, tid = threadIdx.x;
+    float* gobj = P.grad + (size_t)scene * RRT_GRAD_SIZE(N);
+    float* gglobal = gobj + (size_t)N * RRT_OBJ_GRAD_STRIDE;
+    const float* cam = sc.camera + (size_t)scene * sc.camera_scene_stride;
+    const float* w2o = sc.w2o + (size_t)scene * sc.w2o_scene_stride;
+    __shared__ float camg[12];
+    if (tid < 12) camg[tid] = 0.f;
+    __syncthreads();
+    float C[9], ct[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        C[r * 3] = cam[r * 4]; C[r * 3 + 1] = cam[r * 4 + 1]; C[r * 3 + 2] = cam[r * 4 + 2];
+        ct[r] = cam[r * 4 + 3];
+    }
+    float cg[12];
+#pragma unroll
+    for (int q = 0; q < 12; q++) cg[q] = 0.f;
+    for (int k = tid; k < N; k += blockDim.x) {
+        float* og = gobj + (size_t)k * RRT_OBJ_GRAD_STRIDE;
+        float M[9], gb[3], A[9];
+#pragma unroll
+        for (int q = 0; q < 9; q++) M[q] = og[q];
+#pragma unroll
+        for (int q = 0; q < 3; q++) gb[q] = og[9 + q];
+        const float* w = w2o + (size_t)k * RRT_W2O_STRIDE;
+#pragma unroll
+        for (int r = 0; r < 3; r++) { A[r * 3] = w[r * 4]; A[r * 3 + 1] = w[r * 4 + 1]; A[r * 3 + 2] = w[r * 4 + 2]; }
+        // d/dA = M C^T + g_b ct^T ;  d/db = g_b        (d' = A C r, o' = A ct + b)
+        float out[12];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                out[r * 4 + c] = M[r * 3] * C[c * 3] + M[r * 3 + 1] * C[c * 3 + 1] + M[r * 3 + 2] * C[c * 3 + 2] + gb[r] * ct[c];
+            out[r * 4 + 3] = gb[r];
+        }
+#pragma unroll
+        for (int q = 0; q < 12; q++) og[q] = out[q];
+        if (sc.camera_grad) {
+            // d/dC = sum_k A_k^T M_k ; d/dct = sum_k A_k^T g_b,k
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    cg[r * 4 + c] += A[0 * 3 + r] * M[0 * 3 + c] + A[1 * 3 + r] * M[1 * 3 + c] + A[2 * 3 + r] * M[2 * 3 + c];
+                cg[r * 4 + 3] += A[0 * 3 + r] * gb[0] + A[1 * 3 + r] * gb[1] + A[2 * 3 + r] * gb[2];
+            }
+        }
+    }
+    if (sc.camera_grad) {
+#pragma unroll
+        for (int q = 0; q < 12; q++) {
+            float x = warp_sum(cg[q]);
+            if ((tid & 31) == 0 && x != 0.f) atomicAdd(&camg[q], x);
+        }
+    }
+    __syncthreads();
+    if (tid < 12) gglobal[6 + tid] = camg[tid];
+    if (tid == 0) {
+        // Lhat = L/|L|  =>  g_L = (g_Lhat - Lhat (Lhat . g_Lhat)) / |L|    scene.py:83-86
+        const float* li = sc.light + (size_t)scene * sc.light_scene_stride;
+        float L0 = li[0], L1 = li[1], L2 = li[2];
+        float ln = sqrtf(L0 * L0 + L1 * L1 + L2 * L2);
+        float h0 = L0 / ln, h1 = L1 / ln, h2 = L2 / ln;
+        float g0 = gglobal[0], g1 = gglobal[1], g2 = gglobal[2];
+        float dot = h0 * g0 + h1 * g1 + h2 * g2;
+        gglobal[0] = (g0 - h0 * dot) / ln;
+        gglobal[1] = (g1 - h1 * dot) / ln;
+        gglobal[2] = (g2 - h2 * dot) / ln;
+    }
+}
+
+// ---------------------------------------------------------------- FP32 peak micro-benchmarks
+template <int MODE>
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float seed) {
+    if (MODE == 0) {
+        float a[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) a[q] = seed + (float)(threadIdx.x + q);
+        float b = 1.0000001f, c = 1e-7f;
+#pragma unroll 1
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int rep = 0; rep < 8; rep++)
+#pragma unroll
+                for (int q = 0; q < 16; q++) a[q] = __fmaf_rn(a[q], b, c);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; q++) s += a[q];
+        if (s == 123.456f) out[0] = s;
+    } else {
+        u64 a[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) a[q] = pk(seed + (float)(threadIdx.x + q), seed - (float)q);
+        u64 b = pk(1.0000001f, 0.9999999f), c = pk(1e-7f, -1e-7f);
+#pragma unroll 1
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int rep = 0; rep < 8; rep++)
+#pragma unroll
+                for (int q = 0; q < 16; q++) a[q] = fma2(a[q], b, c);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; q++) { float lo, hi; upk(a[q], lo, hi); s += lo + hi; }
+        if (s == 123.456f) out[0] = s;
+    }
+}
+
+// ---------------------------------------------------------------- host side
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* a = "") {
+    snprintf(g_err, sizeof g_err, fmt, a);
+    return code;
+}
+
+int check_scene(const rrt_scene* sc, int* rows_out) {
+    if (!sc) return fail(RRT_ERR_INVALID, "scene is NULL");
+    if (sc->n <= 0) return fail(RRT_ERR_INVALID, "n must be > 0");
+    if (sc->samples <= 0 || sc->samples > 128) return fail(RRT_ERR_INVALID, "samples must be in 1..128");
+    if (sc->num_objects < 0) return fail(RRT_ERR_INVALID, "num_objects must be >= 0");
+    if (sc->num_scenes <= 0 || sc->num_scenes > 65535) return fail(RRT_ERR_INVALID, "num_scenes must be in 1..65535");
+    if (sc->shader < 0 || sc->shader > 2) return fail(RRT_ERR_INVALID, "unknown shader");
+    if (sc->row_begin < 0 || sc->row_begin >= sc->n) return fail(RRT_ERR_INVALID, "row_begin out of range");
+    int rows = sc->row_count > 0 ? sc->row_count : sc->n - sc->row_begin;
+    if (sc->row_begin + rows > sc->n) return fail(RRT_ERR_INVALID, "row slab exceeds the image");
+    if (sc->num_objects > 0 && (!sc->obj_type || !sc->w2o || !sc->material)) return fail(RRT_ERR_INVALID, "object tables are NULL");
+    if (!sc->light || !sc->camera) return fail(RRT_ERR_INVALID, "light/camera tables are NULL");
+    if ((sc->jitter_x == nullptr) != (sc->jitter_y == nullptr)) return fail(RRT_ERR_INVALID, "jitter_x and jitter_y must both be set or both NULL");
+    if (((uintptr_t)sc->w2o & 15) || (sc->w2o_scene_stride & 3)) return fail(RRT_ERR_INVALID, "w2o must be 16-byte aligned");
+    if (sc->shader == RRT_SHADER_DEPTH && !(sc->max_depth != 0.0f)) return fail(RRT_ERR_INVALID, "max_depth must be non-zero");
+    *rows_out = rows;
+    return RRT_OK;
+}
+
+template <int MODE>
+int launch(const KParams& P, cudaStream_t st) {
+    const rrt_scene& sc = P.sc;
+    const int S = sc.samples;
+    int pix;
+    if (S == 1) pix = 8; else if (S == 2) pix = 4; else if (S == 4) pix = 2; else pix = 1;
+    // block height: keep the grid >= ~2 waves of 148 SMs when the image is small
+    const int cols = (sc.n + 32 * pix - 1) / (32 * pix);
+    int warps = kMaxWarps;
+    while (warps > 1 && (long long)cols * ((P.rows + warps - 1) / warps) * sc.num_scenes < 2 * 148) warps >>= 1;
+    dim3 grid(cols, (P.rows + warps - 1) / warps, sc.num_scenes), block(32 * warps);
+    if (grid.y > 65535) return fail(RRT_ERR_UNSUPPORTED, "row slab too tall for one launch");
+    const int staged = sc.num_objects < kObjChunk ? sc.num_objects : kObjChunk;
+    size_t smem = (size_t)(staged > 0 ? staged : 1) * 64;
+    void (*kern)(const KParams) = nullptr;
+    if (S == 1) kern = render_kernel<8, 1, MODE>;
+    else if (S == 2) kern = render_kernel<4, 2, MODE>;
+    else if (S == 4) kern = render_kernel<2, 4, MODE>;
+    else kern = render_kernel<1, 8, MODE>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    kern<<<grid, block, smem, st>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "render kernel launch: %s", cudaGetErrorString(e));
+    return RRT_OK;
+}
+
+int launch_finalize(const KParams& P, cudaStream_t st) {
+    finalize_grads<<<P.sc.num_scenes, 128, 0, st>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "finalize launch: %s", cudaGetErrorString(e));
+    return RRT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rrt_version(void) { return RRT_VERSION; }
+
+const char* rrt_last_error(void) { return g_err; }
+
+int rrt_render_forward(const rrt_scene* scene, float* image, int32_t* hit_index, float* tmin, void* stream) {
+    KParams P;
+    memset(&P, 0, sizeof P);
+    int rc = check_scene(scene, &P.rows);
+    if (rc) return rc;
+    if (!image && !hit_index && !tmin) return fail(RRT_ERR_INVALID, "no output buffer given");
+    P.sc = *scene;
+    P.image = image;
+    P.hit_out = hit_index;
+    P.tmin_out = tmin;
+    return launch<MODE_FWD>(P, (cudaStream_t)stream);
+}
+
+int rrt_render_backward(const rrt_scene* scene, const float* dl_dimage, const int32_t* hit_index, float* grad, void* stream) {
+    KParams P;
+    memset(&P, 0, sizeof P);
+    int rc = check_scene(scene, &P.rows);
+    if (rc) return rc;
+    if (!dl_dimage || !grad) return fail(RRT_ERR_INVALID, "dl_dimage and grad are required");
+    P.sc = *scene;
+    P.dl_dimage = dl_dimage;
+    P.hit_in = hit_index;
+    P.grad = grad;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(grad, 0, sizeof(float) * RRT_GRAD_SIZE(scene->num_objects) * scene->num_scenes, st);
+    if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "memset grad: %s", cudaGetErrorString(e));
+    rc = launch<MODE_BWD>(P, st);
+    if (rc) return rc;
+    return launch_finalize(P, st);
+}
+
+int rrt_render_fused_mse(const rrt_scene* scene, const float* target, const float* channel_weight, float* image,
+                         int32_t* hit_index, double* loss, float* grad, void* stream) {
+    KParams P;
+    memset(&P, 0, sizeof P);
+    int rc = check_scene(scene, &P.rows);
+    if (rc) return rc;
+    if (!target || !loss || !grad) return fail(RRT_ERR_INVALID, "target, loss and grad are required");
+    const int S = scene->samples;
+    if (!(S == 1 || S == 2 || S == 4 || S == 8))
+        return fail(RRT_ERR_UNSUPPORTED, "fused kernel supports samples in {1,2,4,8}; use forward + backward");
+    P.sc = *scene;
+    P.target = target;
+    P.cw[0] = channel_weight ? channel_weight[0] : 1.f;
+    P.cw[1] = channel_weight ? channel_weight[1] : 1.f;
+    P.cw[2] = channel_weight ? channel_weight[2] : 1.f;
+    P.image = image;
+    P.hit_out = hit_index;
+    P.loss = loss;
+    P.grad = grad;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(grad, 0, sizeof(float) * RRT_GRAD_SIZE(scene->num_objects) * scene->num_scenes, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(loss, 0, sizeof(double) * scene->num_scenes, st);
+    if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "memset grad/loss: %s", cudaGetErrorString(e));
+    rc = launch<MODE_FUSED>(P, st);
+    if (rc) return rc;
+    return launch_finalize(P, st);
+}
+
+int rrt_measure_fp32_peak(int mode, int iters, double* tflops, double* ms, void* stream) {
+    if (!tflops || iters <= 0 || mode < 0 || mode > 1) return fail(RRT_ERR_INVALID, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* out = nullptr;
+    if (cudaMalloc(&out, 4) != cudaSuccess) return fail(RRT_ERR_CUDA, "cudaMalloc failed");
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int blocks = 148 * 8, threads = 256;
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0, st);
+        if (mode == 0) fp32_peak_kernel<0><<<blocks, threads, 0, st>>>(out, iters, 0.5f);
+        else fp32_peak_kernel<1><<<blocks, threads, 0, st>>>(out, iters, 0.5f);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, e0, e1);
+        if (rep > 0 && t < best) best = t;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "peak kernel: %s", cudaGetErrorString(e));
+    // per thread per iteration: 8*16 FMA instructions, x2 lanes when packed, 2 flops each
+    double flops = (double)blocks * threads * (double)iters * 8.0 * 16.0 * (mode == 1 ? 2.0 : 1.0) * 2.0;
+    *tflops = flops / ((double)best * 1e-3) / 1e12;
+    if (ms) *ms = best;
+    return RRT_OK;
+}
+
+}  // extern "C"

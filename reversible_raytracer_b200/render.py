@@ -1,0 +1,208 @@
+"""Functional layer over the C ABI: torch tensors in, torch tensors out.
+
+PyTorch is used for device buffers, streams and autograd plumbing only; every
+number is produced by the kernels in csrc/rrt_kernels.cu.  There is no CPU path:
+tensors that are not on a CUDA device raise.
+
+Replaces (reference paths): Scene.build + theano.function (scene.py:18-52,
+optimize_brightness.py:43-46) and T.grad over that graph (optimize.py:25,73).
+"""
+import ctypes as C
+from dataclasses import dataclass, replace
+
+import torch
+
+from . import _native as nat
+
+
+@dataclass(frozen=True)
+class RenderConfig:
+    """Static (non-differentiable) part of a scene: what Scene.build reads besides
+    the parameter tensors (scene.py:18-52)."""
+    n: int
+    samples: int = 4                    # antialias_samples, scene.py:18
+    shader: int = nat.SHADER_PHONG
+    transpose: int = 1                  # 1 = root camera variant, 0 = orbit variant
+    max_depth: float = 1.0              # DepthMapShader.maxDepth, shader.py:11
+    camera_grad: int = 0
+    seed: int = 0                       # in-kernel jitter seed when no jitter tensors are given
+    row_begin: int = 0                  # multi-GPU row slab
+    row_count: int = 0
+
+    @property
+    def rows(self):
+        return self.row_count if self.row_count > 0 else self.n - self.row_begin
+
+    def slab(self, row_begin, row_count):
+        return replace(self, row_begin=row_begin, row_count=row_count)
+
+
+def _f32(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise nat.NativeError('%s must be a CUDA tensor (there is no CPU fallback)' % name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class _Tables:
+    """Packed device tables + the rrt_scene descriptor that points at them."""
+
+    def __init__(self, cfg, obj_type, w2o, material, light, camera, jitter=None):
+        w2o = _f32(w2o, 'w2o')
+        self.batched = w2o.dim() == 3
+        if not self.batched:
+            w2o = w2o.unsqueeze(0)
+        self.B, self.N = int(w2o.shape[0]), int(w2o.shape[1])
+        assert w2o.shape[2] == nat.W2O_STRIDE
+        self.w2o = w2o
+        self.material = _f32(material, 'material').reshape(-1, self.N, nat.MAT_STRIDE)
+        self.light = _f32(light, 'light').reshape(-1, nat.LIGHT_STRIDE)
+        self.camera = _f32(camera, 'camera').reshape(-1, nat.CAMERA_STRIDE)
+        if not obj_type.is_cuda:
+            raise nat.NativeError('obj_type must be a CUDA tensor')
+        self.obj_type = obj_type.to(torch.int32).contiguous()
+        assert self.obj_type.numel() == self.N
+        self.cfg = cfg
+        self.device = w2o.device
+        self.jx = self.jy = None
+        if jitter is not None:
+            self.jx, self.jy = _f32(jitter[0], 'jitter_x'), _f32(jitter[1], 'jitter_y')
+            per = cfg.rows * cfg.n * cfg.samples
+            assert self.jx.numel() in (per, per * self.B) and self.jy.numel() == self.jx.numel(), \
+                'jitter must be [rows,n,S] (shared) or [B,rows,n,S], slab-local, image index space'
+        for t, per in ((self.material, 1), (self.light, 1), (self.camera, 1)):
+            assert t.shape[0] in (1, self.B)
+
+        d = nat.RrtScene()
+        d.n, d.samples, d.num_objects, d.num_scenes = cfg.n, cfg.samples, self.N, self.B
+        d.shader, d.transpose = cfg.shader, cfg.transpose
+        d.row_begin, d.row_count = cfg.row_begin, cfg.row_count
+        d.max_depth, d.camera_grad, d.seed = cfg.max_depth, cfg.camera_grad, cfg.seed & 0xFFFFFFFFFFFFFFFF
+        d.obj_type, d.w2o, d.material = self.obj_type.data_ptr(), self.w2o.data_ptr(), self.material.data_ptr()
+        d.light, d.camera = self.light.data_ptr(), self.camera.data_ptr()
+        d.w2o_scene_stride = 0 if self.B == 1 else self.N * nat.W2O_STRIDE
+        d.material_scene_stride = 0 if self.material.shape[0] == 1 else self.N * nat.MAT_STRIDE
+        d.light_scene_stride = 0 if self.light.shape[0] == 1 else nat.LIGHT_STRIDE
+        d.camera_scene_stride = 0 if self.camera.shape[0] == 1 else nat.CAMERA_STRIDE
+        if self.jx is not None:
+            d.jitter_x, d.jitter_y = self.jx.data_ptr(), self.jy.data_ptr()
+            per = cfg.rows * cfg.n * cfg.samples
+            d.jitter_scene_stride = 0 if self.jx.numel() == per else per
+        self.desc = d
+
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+
+def render_forward(cfg, obj_type, w2o, material, light, camera, jitter=None, want_hit=True, want_tmin=False):
+    """-> image [B,rows,n,3] (or [rows,n,3] when w2o is unbatched), hit_index, tmin."""
+    T = _Tables(cfg, obj_type, w2o, material, light, camera, jitter)
+    with torch.cuda.device(T.device):
+        image = torch.empty((T.B, cfg.rows, cfg.n, 3), dtype=torch.float32, device=T.device)
+        hit = torch.empty((T.B, cfg.samples, cfg.rows, cfg.n), dtype=torch.int32, device=T.device) if want_hit else None
+        tmin = torch.empty((T.B, cfg.samples, cfg.rows, cfg.n), dtype=torch.float32, device=T.device) if want_tmin else None
+        rc = nat.lib().rrt_render_forward(C.byref(T.desc), image.data_ptr(),
+                                          hit.data_ptr() if want_hit else None,
+                                          tmin.data_ptr() if want_tmin else None, T.stream())
+    nat.check(rc, 'rrt_render_forward')
+    if not T.batched:
+        image = image[0]
+        hit = hit[0] if hit is not None else None
+        tmin = tmin[0] if tmin is not None else None
+    return image, hit, tmin
+
+
+def render_backward(cfg, obj_type, w2o, material, light, camera, dl_dimage, hit_index=None, jitter=None):
+    """-> flat gradient [B, N*19+21] (layout: include/rrt_b200.h)."""
+    T = _Tables(cfg, obj_type, w2o, material, light, camera, jitter)
+    dl = _f32(dl_dimage, 'dl_dimage')
+    assert dl.numel() == T.B * cfg.rows * cfg.n * 3
+    with torch.cuda.device(T.device):
+        grad = torch.empty((T.B, nat.grad_size(T.N)), dtype=torch.float32, device=T.device)
+        if hit_index is not None:
+            hit_index = hit_index.to(torch.int32).contiguous()
+            assert hit_index.numel() == T.B * cfg.samples * cfg.rows * cfg.n
+        rc = nat.lib().rrt_render_backward(C.byref(T.desc), dl.data_ptr(),
+                                           hit_index.data_ptr() if hit_index is not None else None,
+                                           grad.data_ptr(), T.stream())
+    nat.check(rc, 'rrt_render_backward')
+    return grad if T.batched else grad[0]
+
+
+def render_fused_mse(cfg, obj_type, w2o, material, light, camera, target, channel_weight=None, jitter=None,
+                     want_image=False, want_hit=False):
+    """Fused forward + sum_c w_c*sum((image-target)^2) + reverse pass, one kernel.
+    -> loss float64 [B], grad float32 [B, N*19+21], image or None, hit_index or None."""
+    T = _Tables(cfg, obj_type, w2o, material, light, camera, jitter)
+    tg = _f32(target, 'target')
+    assert tg.numel() == T.B * cfg.rows * cfg.n * 3
+    cw = None
+    if channel_weight is not None:
+        cw = (C.c_float * 3)(*[float(v) for v in channel_weight])
+    with torch.cuda.device(T.device):
+        loss = torch.empty((T.B,), dtype=torch.float64, device=T.device)
+        grad = torch.empty((T.B, nat.grad_size(T.N)), dtype=torch.float32, device=T.device)
+        image = torch.empty((T.B, cfg.rows, cfg.n, 3), dtype=torch.float32, device=T.device) if want_image else None
+        hit = torch.empty((T.B, cfg.samples, cfg.rows, cfg.n), dtype=torch.int32, device=T.device) if want_hit else None
+        rc = nat.lib().rrt_render_fused_mse(C.byref(T.desc), tg.data_ptr(), cw,
+                                            image.data_ptr() if want_image else None,
+                                            hit.data_ptr() if want_hit else None,
+                                            loss.data_ptr(), grad.data_ptr(), T.stream())
+    nat.check(rc, 'rrt_render_fused_mse')
+    if not T.batched:
+        loss, grad = loss[0], grad[0]
+        image = image[0] if image is not None else None
+        hit = hit[0] if hit is not None else None
+    return loss, grad, image, hit
+
+
+def split_grad(flat, N):
+    """flat [..., N*19+21] -> (w2o [...,N,12], material [...,N,7], light [...,6], camera [...,15])."""
+    og = flat[..., :N * nat.OBJ_GRAD_STRIDE].reshape(*flat.shape[:-1], N, nat.OBJ_GRAD_STRIDE)
+    gg = flat[..., N * nat.OBJ_GRAD_STRIDE:]
+    return og[..., :12], og[..., 12:19], gg[..., 0:6], gg[..., 6:21]
+
+
+class _RenderFn(torch.autograd.Function):
+    """image = render(w2o, material, light, camera); backward = the reverse-pass kernel."""
+
+    @staticmethod
+    def forward(ctx, w2o, material, light, camera, cfg, obj_type, jitter):
+        image, hit, _ = render_forward(cfg, obj_type, w2o, material, light, camera, jitter, want_hit=True)
+        ctx.cfg, ctx.obj_type, ctx.jitter = cfg, obj_type, jitter
+        ctx.save_for_backward(w2o, material, light, camera, hit)
+        ctx.shapes = (w2o.shape, material.shape, light.shape, camera.shape)
+        return image
+
+    @staticmethod
+    def backward(ctx, dl_dimage):
+        w2o, material, light, camera, hit = ctx.saved_tensors
+        N = w2o.shape[-2]
+        flat = render_backward(ctx.cfg, ctx.obj_type, w2o, material, light, camera, dl_dimage, hit, ctx.jitter)
+        gw, gm, gl, gc = split_grad(flat, N)
+        shp = ctx.shapes
+
+        def fit(g, shape):
+            # tables shared across a batch receive the sum over scenes
+            while g.dim() > len(shape):
+                g = g.sum(0)
+            if g.shape != shape and g.dim() == len(shape) and shape[0] == 1 and g.shape[0] != 1:
+                g = g.sum(0, keepdim=True)
+            return g.reshape(shape)
+        return fit(gw, shp[0]), fit(gm, shp[1]), fit(gl, shp[2]), fit(gc, shp[3]), None, None, None
+
+
+def render(cfg, obj_type, w2o, material, light, camera, jitter=None):
+    """Differentiable render: image [B,rows,n,3] / [rows,n,3] with autograd to the
+    four parameter tables."""
+    return _RenderFn.apply(w2o, material, light, camera, cfg, obj_type, jitter)
+
+
+def measure_fp32_peak(mode=1, iters=4096):
+    """FP32 pipe micro-benchmark (TFLOP/s): mode 0 scalar FFMA, 1 packed FFMA2."""
+    tf, ms = C.c_double(0), C.c_double(0)
+    rc = nat.lib().rrt_measure_fp32_peak(mode, iters, C.byref(tf), C.byref(ms),
+                                         C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    nat.check(rc, 'rrt_measure_fp32_peak')
+    return tf.value, ms.value

@@ -1,0 +1,27 @@
+"""Shared test helpers: oracle PackedScene -> device tensors for the product API."""
+import numpy as np
+import torch
+
+from reversible_raytracer_b200.render import RenderConfig
+
+
+def to_device(ps, device, with_jitter=True):
+    """oracle.oracle_c.PackedScene -> (cfg, obj_type, w2o, material, light, camera, jitter)."""
+    cfg = RenderConfig(n=ps.n, samples=ps.samples, shader=ps.shader, transpose=ps.transpose,
+                       max_depth=ps.max_depth, camera_grad=ps.camera_grad, seed=ps.seed,
+                       row_begin=ps.row_begin, row_count=ps.row_count)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    w2o = t(ps.w2o) if ps.B > 1 else t(ps.w2o[0])
+    jitter = None
+    if with_jitter and ps.jitter_x is not None:
+        jitter = (t(ps.jitter_x), t(ps.jitter_y))
+    return cfg, t(ps.obj_type), w2o, t(ps.material), t(ps.light), t(ps.camera), jitter
+
+
+def block_rel_err(a, b):
+    """max |a-b| / max |b| over one parameter block (gradient tolerance metric)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    s = np.max(np.abs(b)) if b.size else 0.0
+    if s == 0.0:
+        return float(np.max(np.abs(a))) if a.size else 0.0
+    return float(np.max(np.abs(a - b)) / s)

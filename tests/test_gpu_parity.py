@@ -1,0 +1,159 @@
+"""GPU parity: CUDA kernels (through the C ABI) vs the canonical-order C oracle.
+
+Bars (BASELINE.json north_star): hit/object-index masks BIT-EXACT; pixels within
+rtol 1e-4 (+ atol 1e-5, images live in [0,1]); gradients within 1e-3 of each
+parameter block's max magnitude.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle_c as oc, scenes
+from reversible_raytracer_b200 import render as R
+from helpers import to_device, block_rel_err
+
+pytestmark = pytest.mark.gpu
+
+PIX_RTOL, PIX_ATOL, GRAD_TOL = 1e-4, 1e-5, 1e-3
+
+CASES = {
+    'C1_optimize_brightness': lambda: scenes.optimize_brightness(),
+    'C2_test_balls_depth': lambda: scenes.test_balls(),
+    'C3_match_mirror_square': lambda: scenes.match_mirror(),
+    'C4_orbit_view0': lambda: scenes.orbit((3.8307, -8.1441, 32), 0),
+    'C4_orbit_view1': lambda: scenes.orbit((-5.0, 7.4833, 32), 1),
+    'C5_stress_diag': lambda: scenes.stress(n=128, num_objects=100),
+    'C5g_stress_general': lambda: scenes.stress(n=96, num_objects=48, general=True),
+    'S1': lambda: scenes.stress(n=100, num_objects=20, samples=1),
+    'S2': lambda: scenes.stress(n=70, num_objects=20, samples=2),
+    'S8': lambda: scenes.stress(n=40, num_objects=20, samples=8),
+    'S3_generic': lambda: scenes.stress(n=33, num_objects=9, samples=3),
+    'S16_generic': lambda: scenes.stress(n=20, num_objects=9, samples=16),
+    'ragged_n1': lambda: scenes.optimize_brightness(n=1),
+    'ragged_n5': lambda: scenes.match_mirror(n=5),
+    'many_objects_chunked': lambda: scenes.stress(n=32, num_objects=1500),
+}
+
+
+def check_forward(ps, dev):
+    img_o, hit_o, tmin_o = oc.render_forward(ps)
+    cfg, ot, w2o, mat, light, cam, jit = to_device(ps, dev)
+    img, hit, tmin = R.render_forward(cfg, ot, w2o, mat, light, cam, jit, want_hit=True, want_tmin=True)
+    torch.cuda.synchronize()
+    img, hit, tmin = img.cpu().numpy(), hit.cpu().numpy(), tmin.cpu().numpy()
+    assert np.array_equal(hit.reshape(hit_o.shape), hit_o), 'hit masks must be bit-exact'
+    assert np.array_equal(tmin.reshape(tmin_o.shape).view(np.uint32), tmin_o.view(np.uint32)), 'tmin must be bit-exact'
+    np.testing.assert_allclose(img.reshape(img_o.shape), img_o, rtol=PIX_RTOL, atol=PIX_ATOL)
+    return img_o, hit_o
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_forward_parity(name, cuda):
+    ps = oc.PackedScene.from_spec(CASES[name](), camera_grad=1)
+    check_forward(ps, cuda)
+
+
+def compare_grads(flat, ref, N):
+    g, r = oc.split_grad(flat, N), oc.split_grad(ref, N)
+    for k in range(N):
+        assert block_rel_err(g['w2o'][k], r['w2o'][k]) <= GRAD_TOL or np.max(np.abs(r['w2o'])) * 1e-5 > np.max(np.abs(r['w2o'][k])), ('w2o', k)
+    assert block_rel_err(g['w2o'], r['w2o']) <= GRAD_TOL
+    assert block_rel_err(g['material'], r['material']) <= GRAD_TOL
+    for key in ('light_dir', 'light_int', 'cam_o2w', 'look_at'):
+        assert block_rel_err(g[key], r[key]) <= GRAD_TOL, key
+
+
+@pytest.mark.parametrize('name', [c for c in CASES if 'generic' not in c])
+def test_fused_mse_parity(name, cuda):
+    ps = oc.PackedScene.from_spec(CASES[name](), camera_grad=1)
+    img_o, _, _ = oc.render_forward(ps, want_aux=False)
+    rng = np.random.RandomState(11)
+    target = np.clip(img_o + rng.normal(0, 0.1, img_o.shape), 0, 1).astype(np.float32)
+    cw = (1.0, 0.0, 0.0) if 'depth' in name else None
+    image_o, hit_o, loss_o, grad_o = oc.render_fused_mse(ps, target, cw)
+    cfg, ot, w2o, mat, light, cam, jit = to_device(ps, cuda)
+    loss, grad, image, hit = R.render_fused_mse(cfg, ot, w2o, mat, light, cam, torch.from_numpy(target).to(cuda),
+                                                cw, jit, want_image=True, want_hit=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(hit.cpu().numpy().reshape(hit_o.shape), hit_o)
+    np.testing.assert_allclose(image.cpu().numpy().reshape(image_o.shape), image_o, rtol=PIX_RTOL, atol=PIX_ATOL)
+    np.testing.assert_allclose(float(loss), loss_o[0], rtol=1e-4)
+    compare_grads(grad.cpu().numpy().astype(np.float64), grad_o[0], ps.N)
+
+
+@pytest.mark.parametrize('name', list(CASES))
+@pytest.mark.parametrize('stored', [True, False])
+def test_backward_parity(name, stored, cuda):
+    ps = oc.PackedScene.from_spec(CASES[name](), camera_grad=1)
+    img_o, hit_o, _ = oc.render_forward(ps)
+    rng = np.random.RandomState(5)
+    dl = rng.normal(0, 1, img_o.shape).astype(np.float32)
+    grad_o = oc.render_backward(ps, dl, hit_o)
+    cfg, ot, w2o, mat, light, cam, jit = to_device(ps, cuda)
+    hit = torch.from_numpy(hit_o).to(cuda) if stored else None
+    grad = R.render_backward(cfg, ot, w2o, mat, light, cam, torch.from_numpy(dl).to(cuda), hit, jit)
+    torch.cuda.synchronize()
+    compare_grads(grad.cpu().numpy().astype(np.float64), grad_o[0], ps.N)
+
+
+def test_batched_scenes(cuda):
+    """C4 shape: a batch of scenes x 2 camera views, per-scene tables."""
+    rng = np.random.RandomState(1234)
+    specs = []
+    for q in range(6):
+        th = rng.uniform(0, 2 * np.pi)
+        specs.append(scenes.orbit((9 * np.cos(th), 9 * np.sin(th), 32), q % 2, seed=100 + q))
+    pss = [oc.PackedScene.from_spec(s, camera_grad=1) for s in specs]
+    B = len(pss)
+    ps = oc.PackedScene(64, 4, pss[0].obj_type, np.stack([p.w2o[0] for p in pss]),
+                        np.stack([p.material[0] for p in pss]), np.stack([p.light[0] for p in pss]),
+                        np.stack([p.camera[0] for p in pss]), pss[0].shader, 0,
+                        jitter_x=np.stack([p.jitter_x for p in pss]), jitter_y=np.stack([p.jitter_y for p in pss]),
+                        camera_grad=1)
+    img_o, hit_o, _ = oc.render_forward(ps)
+    target = np.clip(img_o + rng.normal(0, 0.1, img_o.shape), 0, 1).astype(np.float32)
+    image_o, hit_o, loss_o, grad_o = oc.render_fused_mse(ps, target)
+    cfg, ot, w2o, mat, light, cam, jit = to_device(ps, cuda)
+    loss, grad, image, hit = R.render_fused_mse(cfg, ot, w2o, mat, light, cam, torch.from_numpy(target).to(cuda),
+                                                None, jit, want_image=True, want_hit=True)
+    assert np.array_equal(hit.cpu().numpy(), hit_o)
+    np.testing.assert_allclose(image.cpu().numpy(), image_o, rtol=PIX_RTOL, atol=PIX_ATOL)
+    np.testing.assert_allclose(loss.cpu().numpy(), loss_o, rtol=1e-4)
+    for b in range(B):
+        compare_grads(grad[b].cpu().numpy().astype(np.float64), grad_o[b], ps.N)
+
+
+def test_row_slabs_and_rng_jitter(cuda):
+    """Multi-GPU sharding unit: row slabs reproduce the full image bit-exactly, with
+    the in-kernel counter RNG (no jitter buffers); slab gradients sum to the full one."""
+    spec = scenes.stress(n=96, num_objects=40)
+    full = oc.PackedScene.from_spec(spec, camera_grad=0, use_rng_seed=777)
+    img_o, hit_o, _ = oc.render_forward(full)
+    cfg, ot, w2o, mat, light, cam, _ = to_device(full, cuda, with_jitter=False)
+    img, hit, _ = R.render_forward(cfg, ot, w2o, mat, light, cam, None)
+    assert np.array_equal(hit.cpu().numpy().reshape(hit_o.shape), hit_o)
+    np.testing.assert_allclose(img.cpu().numpy().reshape(img_o.shape), img_o, rtol=PIX_RTOL, atol=PIX_ATOL)
+    target = torch.zeros_like(img)
+    loss_f, grad_f, _, _ = R.render_fused_mse(cfg, ot, w2o, mat, light, cam, target)
+    parts, gsum, lsum = [], 0, 0
+    for rb, rc in ((0, 40), (40, 13), (53, 43)):
+        c2 = cfg.slab(rb, rc)
+        im, _, _ = R.render_forward(c2, ot, w2o, mat, light, cam, None)
+        parts.append(im)
+        l, g, _, _ = R.render_fused_mse(c2, ot, w2o, mat, light, cam, target[rb:rb + rc])
+        gsum, lsum = gsum + g.double(), lsum + l
+    assert torch.equal(torch.cat(parts, 0), img)
+    np.testing.assert_allclose(float(lsum), float(loss_f), rtol=1e-5)
+    N = full.N
+    compare_grads(gsum.cpu().numpy(), grad_f.double().cpu().numpy(), N)
+
+
+def test_error_reporting(cuda):
+    from reversible_raytracer_b200 import _native as nat
+    ps = oc.PackedScene.from_spec(scenes.test_balls(), camera_grad=0)
+    cfg, ot, w2o, mat, light, cam, jit = to_device(ps, cuda)
+    bad = R.RenderConfig(n=32, samples=0)
+    with pytest.raises(nat.NativeError):
+        R.render_forward(bad, ot, w2o, mat, light, cam, None)
+    with pytest.raises(nat.NativeError):
+        R.render_forward(cfg, ot.cpu(), w2o.cpu(), mat.cpu(), light.cpu(), cam.cpu(), None)
