@@ -205,12 +205,24 @@ __device__ __forceinline__ float obj_test(const Obj& ob, float dwx, float dwy, f
     }
 }
 
-// out-of-line on purpose: keeps the hot loop's register and code footprint small
-__device__ __noinline__ float rare_hit_t(const float4* rec, float dwx, float dwy, float dwz) {
-    Obj ob;
-    load_rec(rec, ob);
-    HitRec h;
-    return obj_test(ob, dwx, dwy, dwz, h);
+// Rare path of the sweep, out of line on purpose (keeps the hot loop's register and
+// code footprint small): scalar canonical-order test of `cnt` staged objects
+// (chunk-local indices k0..k0+cnt-1, global index kbase+k) against the thread's 8
+// rays, which live in local memory here.  List order + strict '<' == scene.py:46-47
+// (the earlier shape wins ties).
+__device__ __noinline__ void rare_group(const float4* __restrict__ tab, int k0, int cnt, int kbase,
+                                        const float* dw, float* tmin, int* idx) {
+#pragma unroll 1
+    for (int j = 0; j < cnt; j++) {
+        Obj ob;
+        load_rec(tab + 4 * (k0 + j), ob);
+#pragma unroll 1
+        for (int r = 0; r < kRays; r++) {
+            HitRec h;
+            float t = obj_test(ob, dw[r], dw[kRays + r], dw[2 * kRays + r], h);
+            if (t < tmin[r]) { tmin[r] = t; idx[r] = kbase + k0 + j; }
+        }
+    }
 }
 
 // ---------------------------------------------------------------- packed sweep
@@ -236,52 +248,54 @@ struct RayPack {
     u64 dx[kRays / 2], dy[kRays / 2], dz[kRays / 2];
 };
 
-#define RRT_RARE(r, detv)                                                      \
-    if ((detv) > 0.0f) {                                                       \
-        float lo_, hi_, x_, y_, z_;                                            \
-        upk(rp.dx[(r) >> 1], lo_, hi_); x_ = ((r) & 1) ? hi_ : lo_;            \
-        upk(rp.dy[(r) >> 1], lo_, hi_); y_ = ((r) & 1) ? hi_ : lo_;            \
-        upk(rp.dz[(r) >> 1], lo_, hi_); z_ = ((r) & 1) ? hi_ : lo_;            \
-        float t_ = rare_hit_t(rec, x_, y_, z_);                                \
-        if (t_ < tmin[(r)]) { tmin[(r)] = t_; idx[(r)] = kbase + k; }          \
-    }
+constexpr int kGroup = 4;  // objects per branch in the hot loop
 
-// Sweep `count` staged objects (global indices kbase..kbase+count-1) over the 8 rays.
-// list order + strict '<' == scene.py:46-47 (earlier shape wins ties).
-template <bool FAST>
-__device__ __forceinline__ void sweep_chunk(const float4* __restrict__ tab, int count, int kbase, const RayPack& rp,
-                                            float (&tmin)[kRays], int (&idx)[kRays]) {
-#pragma unroll 2
+// max over the 8 dets of one object, folded into the running group max (FMNMX3 chain;
+// fmaxf drops NaN, and NaN is a miss: shape.py:124-125)
+template <bool GENERAL>
+__device__ __forceinline__ float object_max_det(const float4* __restrict__ rec, const RayPack& rp, float gmax) {
+    float4 q0 = rec[0], q1 = rec[1];
+    float4 q2 = q0, q3 = q0;
+    if (GENERAL) { q2 = rec[2]; q3 = rec[3]; }
+#pragma unroll
+    for (int p = 0; p < kRays / 2; p++) {
+        float lo, hi;
+        upk(pair_det<GENERAL>(q0, q1, q2, q3, rp.dx[p], rp.dy[p], rp.dz[p]), lo, hi);
+        gmax = fmaxf(gmax, fmaxf(lo, hi));
+    }
+    return gmax;
+}
+
+// Sweep `count` staged SPHERES over the thread's 8 rays.  The hot loop is branch-free
+// over groups of kGroup objects: packed FFMA2 discriminants, a running max, ONE
+// compare-and-branch per group; a group with any det > 0 (rare: ~1e-3 per object and
+// warp) is re-evaluated by the scalar canonical routine.  GENERAL=false is the
+// diagonal fast path (translate*scale objects): exact-zero off-diagonals make it
+// bit-identical to the general form.
+template <bool GENERAL>
+__device__ __forceinline__ void sweep_spheres(const float4* __restrict__ tab, int count, int kbase, const RayPack& rp,
+                                              const float* dw, float* tmin, int* idx) {
+    int k = 0;
+#pragma unroll 1
+    for (; k + kGroup <= count; k += kGroup) {
+        float gmax = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kGroup; j++) gmax = object_max_det<GENERAL>(tab + 4 * (k + j), rp, gmax);
+        if (__builtin_expect(gmax > 0.0f, 0)) rare_group(tab, k, kGroup, kbase, dw, tmin, idx);
+    }
+    if (k < count) rare_group(tab, k, count - k, kbase, dw, tmin, idx);
+}
+
+// Chunks that contain squares: spheres get the packed pre-test one by one, squares
+// always take the scalar routine.
+__device__ __forceinline__ void sweep_mixed(const float4* __restrict__ tab, int count, int kbase, const RayPack& rp,
+                                            const float* dw, float* tmin, int* idx) {
+#pragma unroll 1
     for (int k = 0; k < count; k++) {
-        const float4* rec = tab + 4 * k;
-        float4 q0 = rec[0], q1 = rec[1];
-        float4 q2, q3;
-        int flags = FAST ? 0 : __float_as_int(q1.w);
-        u64 det[kRays / 2];
-        if (FAST || flags == 0) {
-#pragma unroll
-            for (int p = 0; p < kRays / 2; p++) det[p] = pair_det<false>(q0, q1, q0, q0, rp.dx[p], rp.dy[p], rp.dz[p]);
-        } else if (flags == 2) {
-            q2 = rec[2];
-            q3 = rec[3];
-#pragma unroll
-            for (int p = 0; p < kRays / 2; p++) det[p] = pair_det<true>(q0, q1, q2, q3, rp.dx[p], rp.dy[p], rp.dz[p]);
-        } else {
-            // squares: every ray takes the scalar canonical routine
-            const float one = 1.0f;
-#pragma unroll
-            for (int p = 0; p < kRays / 2; p++) det[p] = pk(one, one);
-        }
-        float dl[kRays];
-#pragma unroll
-        for (int p = 0; p < kRays / 2; p++) upk(det[p], dl[2 * p], dl[2 * p + 1]);
-        bool any = false;
-#pragma unroll
-        for (int r = 0; r < kRays; r++) any |= (dl[r] > 0.0f);
-        if (__builtin_expect(any, 0)) {
-            RRT_RARE(0, dl[0]) RRT_RARE(1, dl[1]) RRT_RARE(2, dl[2]) RRT_RARE(3, dl[3])
-            RRT_RARE(4, dl[4]) RRT_RARE(5, dl[5]) RRT_RARE(6, dl[6]) RRT_RARE(7, dl[7])
-        }
+        const int flags = __float_as_int(tab[4 * k + 1].w);
+        float gmax = 1.0f;
+        if (!(flags & 1)) gmax = object_max_det<true>(tab + 4 * k, rp, 0.0f);
+        if (gmax > 0.0f) rare_group(tab, k, 1, kbase, dw, tmin, idx);
     }
 }
 
@@ -467,7 +481,7 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const __grid_constant__ 
     __shared__ float slots[kSlots * kSlotStride];
     __shared__ float gglob[9];
     __shared__ float loss_warp[kMaxWarps];
-    __shared__ int all_fast_s;
+    __shared__ int chunk_class;  // sticky per CTA: bit0 squares, bit1 general spheres seen
 
     const rrt_scene& sc = P.sc;
     const int n = sc.n, S = sc.samples, N = sc.num_objects;
@@ -496,7 +510,7 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const __grid_constant__ 
             float ln = sqrtf(g.L[0] * g.L[0] + g.L[1] * g.L[1] + g.L[2] * g.L[2]);  // scene.py:83-86
             g.Ln = ln;
             g.Lh[0] = g.L[0] / ln; g.Lh[1] = g.L[1] / ln; g.Lh[2] = g.L[2] / ln;
-            all_fast_s = 1;
+            chunk_class = 0;
         }
         if (tid < kSlots) slot_key[tid] = -1;
         if (tid < 9) gglob[tid] = 0.f;
@@ -549,8 +563,11 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const __grid_constant__ 
     const int nchunks_s = (S + SPT - 1) / SPT;
 #pragma unroll 1
     for (int sc0 = 0; sc0 < nchunks_s; sc0++) {
-        // ---- build the 8 rays of this sample chunk
-        float rcx[kRays], rcy[kRays], rcz[kRays];  // camera-space rays (kept for the reverse pass)
+        // ---- build the 8 rays of this sample chunk.  Per-ray state lives in (L1-resident)
+        // local memory: it is read by the rare path of the sweep and by the rolled shading /
+        // reverse-pass loops below; only the packed world directions stay in registers.
+        float l_rc[3 * kRays], l_dw[3 * kRays], l_tmin[kRays];  // SoA: [x0..x7 | y0..y7 | z0..z7]
+        int l_idx[kRays];
         RayPack rp;
         {
             float wx[kRays], wy[kRays], wz[kRays];
@@ -561,6 +578,8 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const __grid_constant__ 
                 const int b = b0 + px;
                 const bool ok = row_ok && b < n && s < S;
                 float jx = 0.f, jy = 0.f;
+                float rcx = 0.f, rcy = 0.f, rcz = 0.f;
+                wx[r] = wy[r] = wz[r] = 0.f;  // zero direction never hits (det == 0)
                 if (ok) {
                     if (sc.jitter_x) {
                         size_t off = (size_t)scene * sc.jitter_scene_stride + ((size_t)al * n + b) * S + s;
@@ -570,17 +589,18 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const __grid_constant__ 
                         jx = rrt_rng(sc.seed, scene, (uint32_t)(a * n + b), s, 0);
                         jy = rrt_rng(sc.seed, scene, (uint32_t)(a * n + b), s, 1);
                     }
-                    rcx[r] = __fadd_rn(bx[px], jitter_offset(jx, s, S, n));
-                    rcy[r] = __fadd_rn(by[px], jitter_offset(jy, s, S, n));
-                    rcz[r] = bz[px];
+                    rcx = __fadd_rn(bx[px], jitter_offset(jx, s, S, n));
+                    rcy = __fadd_rn(by[px], jitter_offset(jy, s, S, n));
+                    rcz = bz[px];
                     // camera.o2w (identity in the root variant)
-                    wx[r] = dot3_canon(g.C[0], g.C[1], g.C[2], rcx[r], rcy[r], rcz[r]);
-                    wy[r] = dot3_canon(g.C[3], g.C[4], g.C[5], rcx[r], rcy[r], rcz[r]);
-                    wz[r] = dot3_canon(g.C[6], g.C[7], g.C[8], rcx[r], rcy[r], rcz[r]);
-                } else {
-                    rcx[r] = rcy[r] = rcz[r] = 0.f;
-                    wx[r] = wy[r] = wz[r] = 0.f;  // zero direction never hits (det == 0)
+                    wx[r] = dot3_canon(g.C[0], g.C[1], g.C[2], rcx, rcy, rcz);
+                    wy[r] = dot3_canon(g.C[3], g.C[4], g.C[5], rcx, rcy, rcz);
+                    wz[r] = dot3_canon(g.C[6], g.C[7], g.C[8], rcx, rcy, rcz);
                 }
+                l_rc[r] = rcx; l_rc[kRays + r] = rcy; l_rc[2 * kRays + r] = rcz;
+                l_dw[r] = wx[r]; l_dw[kRays + r] = wy[r]; l_dw[2 * kRays + r] = wz[r];
+                l_tmin[r] = __int_as_float(0x7f800000);
+                l_idx[r] = -1;
             }
 #pragma unroll
             for (int p = 0; p < kRays / 2; p++) {
@@ -591,18 +611,13 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const __grid_constant__ 
         }
 
         // ---- nearest-hit sweep (or stored winners)
-        float tmin[kRays];
-        int idx[kRays];
-#pragma unroll
-        for (int r = 0; r < kRays; r++) { tmin[r] = __int_as_float(0x7f800000); idx[r] = -1; }
-
         const bool use_stored = (MODE == MODE_BWD) && (P.hit_in != nullptr);
         if (use_stored) {
 #pragma unroll
             for (int r = 0; r < kRays; r++) {
                 const int px = r / SPT, s = sc0 * SPT + r % SPT, b = b0 + px;
                 if (row_ok && b < n && s < S)
-                    idx[r] = P.hit_in[(((size_t)scene * S + s) * P.rows + al) * n + b];
+                    l_idx[r] = P.hit_in[(((size_t)scene * S + s) * P.rows + al) * n + b];
             }
         } else {
 #pragma unroll 1
@@ -610,28 +625,21 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const __grid_constant__ 
                 const int cnt = min(kObjChunk, N - kb);
                 if (kb > 0 || sc0 > 0) __syncthreads();   // previous chunk fully consumed
                 if (N > kObjChunk || sc0 == 0) {
-                    int fast = 1;
+                    int cls = 0;                           // bit0: squares present, bit1: general spheres present
                     for (int k = tid; k < cnt; k += blockDim.x) {
                         Obj ob;
                         make_obj(w2o + (size_t)(kb + k) * RRT_W2O_STRIDE, sc.obj_type[kb + k], g.ct, ob);
                         store_rec(smem_tab + 4 * k, ob);
-                        fast &= (ob.flags == 0);
+                        cls |= ob.flags;
                     }
-                    if (!fast) all_fast_s = 0;
+                    if (cls) atomicOr(&chunk_class, cls);
                 }
                 __syncthreads();
-                if (all_fast_s) sweep_chunk<true>(smem_tab, cnt, kb, rp, tmin, idx);
-                else sweep_chunk<false>(smem_tab, cnt, kb, rp, tmin, idx);
+                const int cls = chunk_class;
+                if (cls == 0) sweep_spheres<false>(smem_tab, cnt, kb, rp, l_dw, l_tmin, l_idx);
+                else if (!(cls & 1)) sweep_spheres<true>(smem_tab, cnt, kb, rp, l_dw, l_tmin, l_idx);
+                else sweep_mixed(smem_tab, cnt, kb, rp, l_dw, l_tmin, l_idx);
             }
-        }
-
-        // ---- spill the per-ray state to (L1-resident) local arrays for the rolled loops below
-        float l_rc[kRays][3];
-        int l_idx[kRays];
-#pragma unroll
-        for (int r = 0; r < kRays; r++) {
-            l_rc[r][0] = rcx[r]; l_rc[r][1] = rcy[r]; l_rc[r][2] = rcz[r];
-            l_idx[r] = idx[r];
         }
 
         // ---- outputs of the sweep
@@ -641,8 +649,8 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const __grid_constant__ 
                 const int px = r / SPT, s = sc0 * SPT + r % SPT, b = b0 + px;
                 if (row_ok && b < n && s < S) {
                     size_t ro = (((size_t)scene * S + s) * P.rows + al) * n + b;
-                    if (P.hit_out) P.hit_out[ro] = idx[r];
-                    if (MODE == MODE_FWD && P.tmin_out) P.tmin_out[ro] = tmin[r];
+                    if (P.hit_out) P.hit_out[ro] = l_idx[r];
+                    if (MODE == MODE_FWD && P.tmin_out) P.tmin_out[ro] = l_tmin[r];
                 }
             }
         }
@@ -659,9 +667,9 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const __grid_constant__ 
                 float m7[7];
 #pragma unroll
                 for (int q = 0; q < 7; q++) m7[q] = __ldg(mat + q);
-                float dwx = dot3_canon(g.C[0], g.C[1], g.C[2], l_rc[r][0], l_rc[r][1], l_rc[r][2]);
-                float dwy = dot3_canon(g.C[3], g.C[4], g.C[5], l_rc[r][0], l_rc[r][1], l_rc[r][2]);
-                float dwz = dot3_canon(g.C[6], g.C[7], g.C[8], l_rc[r][0], l_rc[r][1], l_rc[r][2]);
+                float dwx = dot3_canon(g.C[0], g.C[1], g.C[2], l_rc[r], l_rc[kRays + r], l_rc[2 * kRays + r]);
+                float dwy = dot3_canon(g.C[3], g.C[4], g.C[5], l_rc[r], l_rc[kRays + r], l_rc[2 * kRays + r]);
+                float dwz = dot3_canon(g.C[6], g.C[7], g.C[8], l_rc[r], l_rc[kRays + r], l_rc[2 * kRays + r]);
                 HitRec h;
                 obj_test(ob, dwx, dwy, dwz, h);
                 ShadeRec sr;
@@ -706,9 +714,9 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const __grid_constant__ 
                 float dwx = 0.f, dwy = 0.f, dwz = 0.f;
                 if (k >= 0) {
                     make_obj(w2o + (size_t)k * RRT_W2O_STRIDE, sc.obj_type[k], g.ct, ob);
-                    dwx = dot3_canon(g.C[0], g.C[1], g.C[2], l_rc[r][0], l_rc[r][1], l_rc[r][2]);
-                    dwy = dot3_canon(g.C[3], g.C[4], g.C[5], l_rc[r][0], l_rc[r][1], l_rc[r][2]);
-                    dwz = dot3_canon(g.C[6], g.C[7], g.C[8], l_rc[r][0], l_rc[r][1], l_rc[r][2]);
+                    dwx = dot3_canon(g.C[0], g.C[1], g.C[2], l_rc[r], l_rc[kRays + r], l_rc[2 * kRays + r]);
+                    dwy = dot3_canon(g.C[3], g.C[4], g.C[5], l_rc[r], l_rc[kRays + r], l_rc[2 * kRays + r]);
+                    dwz = dot3_canon(g.C[6], g.C[7], g.C[8], l_rc[r], l_rc[kRays + r], l_rc[2 * kRays + r]);
                     obj_test(ob, dwx, dwy, dwz, h);
                     if (!(h.t < __int_as_float(0x7f800000))) k = -1;  // stale stored winner
                 }
@@ -731,7 +739,10 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const __grid_constant__ 
                     for (int q = 0; q < PIX; q++)
                         if (q == px) { gc[0] = gpix[q][0]; gc[1] = gpix[q][1]; gc[2] = gpix[q][2]; }
                     acc_key = k;
-                    backward_ray(sc.shader, sc.max_depth, ob, m7, g, h, sr, l_rc[r], gc, acc, gg);
+                    {
+                        const float rc3[3] = {l_rc[r], l_rc[kRays + r], l_rc[2 * kRays + r]};
+                        backward_ray(sc.shader, sc.max_depth, ob, m7, g, h, sr, rc3, gc, acc, gg);
+                    }
                 }
             }
         }

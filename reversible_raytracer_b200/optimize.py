@@ -1,0 +1,84 @@
+"""Optimiser loops -- thin PyTorch re-host of the reference's optimize.py, the
+direct CALLER of the hot path (it owns T.grad + the SGD update, optimize.py:19-29).
+
+The reference compiles `loss` (a symbolic expression) into one Theano function;
+here `loss` is a CLOSURE that re-renders with the current parameter values and
+returns a scalar tensor, e.g.
+
+    train = GDOptimizer().optimize([center1, center2],
+                                   lambda: -scene.build()[90, 85].sum() - scene.build()[50, 90].sum())
+    for i in range(90): print(train(0.0008))
+
+Both call shapes found in the reference are accepted:
+    optimize(tVars, loss, momentum=0) -> fn(lr)            optimize.py:19-29 (HEAD)
+    optimize(tVars, loss, lr, momentum) -> fn()            optimize_brightness.py:50-52,
+                                                           match_mirror.py:48 (stale form)
+"""
+import torch
+
+from .util import get_epsilon  # noqa: F401
+
+
+class GDOptimizer(object):
+    """Gradient descent: var <- var - lr * dloss/dvar (optimize.py:11-29)."""
+
+    def __init__(self):
+        pass
+
+    def optimize(self, tVars, loss, lr=None, momentum=0):
+        if not callable(loss):
+            raise TypeError('loss must be a callable returning a scalar tensor (eager re-host of the '
+                            'symbolic loss expression of optimize.py:19)')
+        tVars = list(tVars)
+        for v in tVars:
+            v.requires_grad_(True)
+        default_lr = lr
+
+        def train(step_lr=None):
+            step_lr = default_lr if step_lr is None else step_lr
+            if step_lr is None:
+                raise TypeError('learning rate missing: call train(lr)')
+            value = loss()
+            grads = torch.autograd.grad(value, tVars, allow_unused=True)
+            with torch.no_grad():
+                for var, g in zip(tVars, grads):
+                    if g is not None:
+                        var.sub_(step_lr * g.to(var.device))
+            return float(value.detach())
+
+        return train
+
+
+class MGDAutoOptimizer(object):
+    """Autoencoder trainer (optimize.py:63-84; orbit_experiments/optimize.py:68-97).
+
+    `ae` must expose `params` (list of tensors) and `cost(X)` (root) or
+    `cost(Xl, Xr)` (orbit: left/right camera views)."""
+
+    def __init__(self, ae):
+        self.ae = ae
+
+    def optimize(self, train_data, lam=None, fixed_length=3):
+        ae = self.ae
+        for p in ae.params:
+            p.requires_grad_(True)
+        orbit = lam is not None or (hasattr(train_data, 'dim') and train_data.dim() >= 3)
+
+        def step(cost, lr, bias_scale):
+            grads = torch.autograd.grad(cost, ae.params, allow_unused=True)
+            with torch.no_grad():
+                for var, g in zip(ae.params, grads):
+                    if g is None:
+                        continue
+                    # orbit variant: 1-D parameters (biases) move at 0.1 * lr
+                    # (orbit_experiments/optimize.py:80-81)
+                    var.sub_((bias_scale if var.dim() == 1 else 1.0) * lr * g)
+            return float(cost.detach())
+
+        if orbit:
+            def opt(i, lr):
+                return step(ae.cost(train_data[i, 0], train_data[i, 1]), lr, 0.1)
+        else:
+            def opt(lr):
+                return step(ae.cost(train_data[0]), lr, 1.0)
+        return opt

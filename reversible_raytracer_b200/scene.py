@@ -1,0 +1,213 @@
+"""Scene / Camera / Light / Material -- host-side mirror of the reference's
+scene.py (root variant) and orbit_experiments/scene.py (camera with a transform).
+
+    Scene(shapes, lights, camera, shader).build(antialias_samples=4)   scene.py:11-52
+    Camera(x_dims, y_dims)                       root variant          scene.py:55-75
+    Camera(x_dims, y_dims, o2w, camera_dir)      orbit variant         orbit_experiments/scene.py:55-80
+    Light(direction, intensity).normed_dir()                           scene.py:78-86
+    Material(color, ks, kd, ka, shininess)                             scene.py:89-101
+
+Execution-model bridge: the reference's build() returns a SYMBOLIC
+image that is compiled once and re-evaluated after its theano.shared parameters
+change.  Here parameters are torch tensors (requires_grad=True for the ones being
+optimised) and build() renders EAGERLY with the CUDA kernels, returning an image
+tensor wired into torch autograd.  Call build() again after updating parameters.
+Like the reference's compiled graph, a Scene reuses the SAME anti-alias jitter on
+every build() (scene.py:24-25 bakes it into the graph as constants); it is drawn
+from NumPy's global RNG on first use unless `jitter=`/`seed=` is given.
+
+There is no CPU fallback: build() raises if CUDA or the extension is missing.
+"""
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import render as R
+from .transform import RayField, Transform, as_tensor, default_device, identity  # noqa: F401
+from .shape import *  # noqa: F401,F403  (the reference's scene.py re-exports these)
+from .util import *  # noqa: F401,F403
+from .transform import *  # noqa: F401,F403
+
+
+class Material(object):
+    """scene.py:89-101"""
+
+    def __init__(self, color, ks, kd, ka, shininess):
+        self.ks = as_tensor(ks)
+        self.kd = as_tensor(kd)
+        self.ka = as_tensor(ka)
+        self.color = as_tensor(color)
+        self.shininess = as_tensor(shininess)
+
+    def packed(self, device):
+        """-> float32[7] (ka, kd, ks, shininess, r, g, b), differentiable."""
+        parts = [self.ka.reshape(1), self.kd.reshape(1), self.ks.reshape(1), self.shininess.reshape(1),
+                 self.color.reshape(3)]
+        return torch.cat([p.to(device) for p in parts])
+
+
+class Light(object):
+    """Directional light, scene.py:78-86."""
+
+    def __init__(self, direction, intensity):
+        self.direction = as_tensor(direction)
+        self.intensity = as_tensor(intensity)
+
+    def normed_dir(self):
+        d = self.direction
+        norm = torch.sqrt(d[0] ** 2 + d[1] ** 2 + d[2] ** 2)
+        return d / norm
+
+    def packed(self, device):
+        return torch.cat([self.direction.reshape(3).to(device), self.intensity.reshape(3).to(device)])
+
+
+class Camera(object):
+    """Pin-hole camera.  Two constructors, like the reference's two copies."""
+
+    def __init__(self, x_dims, y_dims, o2w=None, camera_dir=None):
+        self.x_dims = int(x_dims)
+        self.y_dims = int(y_dims)
+        self.has_transform = o2w is not None
+        self.o2w = o2w if o2w is not None else identity()
+        self.w2o = self.o2w.inverse()
+        self.look_at = as_tensor(np.asarray([0, 0, 1.], dtype='float32') if camera_dir is None else camera_dir)
+        self.rays = None
+
+    def make_rays(self, x_dims, y_dims, sampleDist_x=None, sampleDist_y=None):
+        """scene.py:61-75 (dense helper; the kernels generate rays in registers with
+        the same float64 -> float32 arithmetic).  Orbit variant applies camera.o2w
+        (orbit_experiments/scene.py:80)."""
+        rays = np.dstack(np.meshgrid(np.linspace(0.5, -0.5, y_dims),
+                                     np.linspace(-0.5, 0.5, x_dims), indexing='ij'))
+        rays = np.dstack([rays, np.ones([y_dims, x_dims], dtype='float32')])
+        rays = np.divide(rays, np.linalg.norm(rays, axis=2).reshape(y_dims, x_dims, 1).repeat(3, 2))
+        rays = np.asarray(rays, dtype=np.float32)
+        if sampleDist_x is not None:
+            rays[:, :, 0] = rays[:, :, 0] + np.asarray(sampleDist_x, dtype=np.float32) / np.float32(x_dims)
+        if sampleDist_y is not None:
+            rays[:, :, 1] = rays[:, :, 1] + np.asarray(sampleDist_y, dtype=np.float32) / np.float32(y_dims)
+        rf = RayField([0., 0., 0.], rays)
+        return self.o2w(rf) if self.has_transform else rf
+
+    def packed(self, device):
+        """-> float32[15]: camera.o2w rows 0..2 (3x4) then look_at."""
+        return torch.cat([self.o2w.m[:3, :].reshape(12).to(device), self.look_at.reshape(3).to(device)])
+
+
+class Scene(object):
+    """scene.py:11-52"""
+
+    def __init__(self, shapes, lights, camera, shader):
+        self.shapes = shapes
+        self.lights = lights
+        self.camera = camera
+        self.shader = shader
+        self._jitter = {}
+        self.last_hit_index = None
+
+    # -- jitter ---------------------------------------------------------------
+    def _jitter_for(self, n, S, jitter, seed, device):
+        """Anti-alias offsets in IMAGE index space (include/rrt_b200.h).  The reference
+        draws x then y as (x_dims, y_dims, S) arrays from the global RNG
+        (scene.py:24-25) in RAY index space; the root variant shades pixel (a,b) with
+        ray [b,a], hence the transpose."""
+        key = (n, S)
+        if jitter is not None:
+            jx, jy = (np.asarray(j, dtype=np.float32) for j in jitter)
+        elif seed is not None:
+            rng = np.random.RandomState(seed)
+            jx = np.asarray(rng.random_sample((n, n, S)), dtype=np.float32)
+            jy = np.asarray(rng.random_sample((n, n, S)), dtype=np.float32)
+        elif key in self._jitter:
+            return self._jitter[key]
+        else:
+            jx = np.asarray(np.random.random((n, n, S)), dtype=np.float32)
+            jy = np.asarray(np.random.random((n, n, S)), dtype=np.float32)
+        if not self.camera.has_transform:
+            jx, jy = jx.transpose(1, 0, 2), jy.transpose(1, 0, 2)
+        out = (torch.from_numpy(np.ascontiguousarray(jx)).to(device),
+               torch.from_numpy(np.ascontiguousarray(jy)).to(device))
+        self._jitter[key] = out
+        return out
+
+    def reset_jitter(self):
+        self._jitter = {}
+
+    # -- packing ----------------------------------------------------------------
+    def device(self):
+        for s in self.shapes:
+            if s.w2o.m.is_cuda:
+                return s.w2o.m.device
+        return default_device()
+
+    def pack(self, device=None):
+        """-> (obj_type int32[N], w2o [N,12], material [N,7], light [6], camera [15]),
+        all on `device`, differentiable w.r.t. whatever the user's tensors require."""
+        device = device or self.device()
+        if len(self.shapes) == 0:
+            w2o = torch.zeros((0, 12), dtype=torch.float32, device=device)
+            mat = torch.zeros((0, 7), dtype=torch.float32, device=device)
+        else:
+            w2o = torch.stack([s.w2o.m[:3, :].reshape(12).to(device) for s in self.shapes])
+            mat = torch.stack([s.material.packed(device) for s in self.shapes])
+        obj_type = torch.tensor([s.kind for s in self.shapes], dtype=torch.int32, device=device)
+        return obj_type, w2o, mat, self.lights[0].packed(device), self.camera.packed(device)
+
+    def config(self, antialias_samples=4):
+        cam = self.camera
+        if cam.x_dims != cam.y_dims:
+            raise ValueError('the reference renderer only works for x_dims == y_dims '
+                             '(rays are (y,x,3), image and jitter are (x,y,.): scene.py:21,24)')
+        return R.RenderConfig(n=cam.x_dims, samples=int(antialias_samples), shader=self.shader.shader_id,
+                              transpose=0 if cam.has_transform else 1,
+                              max_depth=float(getattr(self.shader, 'maxDepth', 1.0)),
+                              camera_grad=1 if cam.has_transform else 0)
+
+    # -- rendering ------------------------------------------------------------------
+    def build(self, antialias_samples=4, jitter=None, seed=None):
+        """Render the scene (scene.py:18-52) -> image (x_dims, y_dims, 3) float32 on the
+        GPU, differentiable w.r.t. shape transforms, materials, the light and (orbit
+        variant) the camera transform."""
+        if not torch.cuda.is_available():
+            raise nat.NativeError('Scene.build needs a CUDA device (B200); there is no CPU fallback')
+        device = self.device()
+        if device.type != 'cuda':
+            device = torch.device('cuda', torch.cuda.current_device())
+        cfg = self.config(antialias_samples)
+        obj_type, w2o, mat, light, cam = self.pack(device)
+        jit = self._jitter_for(cfg.n, cfg.samples, jitter, seed, device)
+        return R.render(cfg, obj_type, w2o, mat, light, cam, jit)
+
+    def build_mse(self, target, antialias_samples=4, channel_weight=None, jitter=None, seed=None,
+                  want_image=False):
+        """Fused forward + sum((image-target)^2) + reverse pass in ONE kernel (the cost of
+        match_mirror.py:45 and of every autoencoder, autoencoder.py:76).  Returns a
+        differentiable scalar loss (float32) -- call .backward() on it -- and, if asked,
+        the detached image."""
+        device = self.device()
+        cfg = self.config(antialias_samples)
+        obj_type, w2o, mat, light, cam = self.pack(device)
+        jit = self._jitter_for(cfg.n, cfg.samples, jitter, seed, device)
+        loss, image = _FusedMSE.apply(w2o, mat, light, cam, cfg, obj_type, jit,
+                                      as_tensor(target).to(device), channel_weight, want_image)
+        return (loss, image) if want_image else loss
+
+
+class _FusedMSE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w2o, mat, light, cam, cfg, obj_type, jit, target, channel_weight, want_image):
+        loss, grad, image, _ = R.render_fused_mse(cfg, obj_type, w2o, mat, light, cam, target, channel_weight, jit,
+                                                  want_image=want_image)
+        ctx.N = w2o.shape[-2]
+        ctx.save_for_backward(grad)
+        if image is None:
+            image = torch.empty(0, device=w2o.device)
+        ctx.mark_non_differentiable(image)
+        return loss.float(), image
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_image):
+        (grad,) = ctx.saved_tensors
+        gw, gm, gl, gc = R.split_grad(grad * g_loss, ctx.N)
+        return gw, gm, gl, gc, None, None, None, None, None, None
