@@ -56,12 +56,13 @@ typedef struct {
 
 /* ---- jitter RNG shared (by specification) with the CUDA kernels ------------- */
 static inline float orc_rng(uint64_t seed, uint32_t scene, uint32_t pix, uint32_t s, uint32_t axis) {
-    uint64_t key = ((uint64_t)scene << 40) ^ ((uint64_t)pix << 8) ^ ((uint64_t)s << 1) ^ (uint64_t)axis;
-    uint64_t z = seed + (key + 1) * 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    return (float)(z >> 40) * 5.9604644775390625e-08f; /* 2^-24 */
+    /* counter-based 32-bit hash (lowbias32 finaliser) -> 24-bit uniform in [0,1) */
+    uint32_t x = (pix * 0x9E3779B1u) ^ (scene * 0x85EBCA77u) ^ ((s * 2u + axis) * 0xC2B2AE3Du) ^
+                 (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x27D4EB2Fu);
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return (float)(x >> 8) * 5.9604644775390625e-08f; /* 2^-24 */
 }
 
 /* np.linspace(start, stop, n)[i] : fl(fl(i*step)+start), last element = stop */

@@ -9,7 +9,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
-LIB_PATH = os.path.join(HERE, 'librrt_b200.so')
+LIB_PATH = os.environ.get('RRT_B200_LIB') or os.path.join(HERE, 'librrt_b200.so')   # env override: A/B kernel variants
 SRC = os.path.join(HERE, 'csrc', 'rrt_kernels.cu')
 INCLUDE = os.path.join(REPO, 'include')
 

@@ -38,10 +38,22 @@ namespace {
 typedef unsigned long long u64;
 
 constexpr int kRays = 8;          // rays per thread (4 packed pairs)
-constexpr int kObjChunk = 1024;   // objects staged in shared memory at a time (64 KB)
+#ifndef RRT_OBJ_CHUNK
+#define RRT_OBJ_CHUNK 512
+#endif
+#ifndef RRT_GROUP
+#define RRT_GROUP 4
+#endif
+#ifndef RRT_MIN_BLOCKS
+#define RRT_MIN_BLOCKS 5
+#endif
+#ifndef RRT_MAX_WARPS
+#define RRT_MAX_WARPS 4
+#endif
+constexpr int kObjChunk = RRT_OBJ_CHUNK;   // objects staged in shared memory at a time (64 B each)
 constexpr int kSlots = 32;        // per-CTA gradient slots (object -> 19 floats)
 constexpr int kSlotStride = 20;
-constexpr int kMaxWarps = 8;
+constexpr int kMaxWarps = RRT_MAX_WARPS;
 
 enum { MODE_FWD = 0, MODE_BWD = 1, MODE_FUSED = 2 };
 
@@ -81,14 +93,15 @@ __device__ __forceinline__ u64 mul2(u64 a, u64 b) {
 }
 
 // ---------------------------------------------------------------- jitter RNG
+// Counter-based 32-bit hash (lowbias32 finaliser) -> 24-bit uniform in [0,1).
 // Same function (by specification) as orc_rng in oracle/oracle_c.c.
 __device__ __forceinline__ float rrt_rng(u64 seed, uint32_t scene, uint32_t pix, uint32_t s, uint32_t axis) {
-    u64 key = ((u64)scene << 40) ^ ((u64)pix << 8) ^ ((u64)s << 1) ^ (u64)axis;
-    u64 z = seed + (key + 1ull) * 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    return (float)(uint32_t)(z >> 40) * 5.9604644775390625e-08f;
+    uint32_t x = (pix * 0x9E3779B1u) ^ (scene * 0x85EBCA77u) ^ ((s * 2u + axis) * 0xC2B2AE3Du) ^
+                 (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x27D4EB2Fu);
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return (float)(x >> 8) * 5.9604644775390625e-08f;
 }
 
 // ---------------------------------------------------------------- primary rays
@@ -205,26 +218,6 @@ __device__ __forceinline__ float obj_test(const Obj& ob, float dwx, float dwy, f
     }
 }
 
-// Rare path of the sweep, out of line on purpose (keeps the hot loop's register and
-// code footprint small): scalar canonical-order test of `cnt` staged objects
-// (chunk-local indices k0..k0+cnt-1, global index kbase+k) against the thread's 8
-// rays, which live in local memory here.  List order + strict '<' == scene.py:46-47
-// (the earlier shape wins ties).
-__device__ __noinline__ void rare_group(const float4* __restrict__ tab, int k0, int cnt, int kbase,
-                                        const float* dw, float* tmin, int* idx) {
-#pragma unroll 1
-    for (int j = 0; j < cnt; j++) {
-        Obj ob;
-        load_rec(tab + 4 * (k0 + j), ob);
-#pragma unroll 1
-        for (int r = 0; r < kRays; r++) {
-            HitRec h;
-            float t = obj_test(ob, dw[r], dw[kRays + r], dw[2 * kRays + r], h);
-            if (t < tmin[r]) { tmin[r] = t; idx[r] = kbase + k0 + j; }
-        }
-    }
-}
-
 // ---------------------------------------------------------------- packed sweep
 template <bool GENERAL>
 __device__ __forceinline__ u64 pair_det(const float4& q0, const float4& q1, const float4& q2, const float4& q3,
@@ -248,7 +241,44 @@ struct RayPack {
     u64 dx[kRays / 2], dy[kRays / 2], dz[kRays / 2];
 };
 
-constexpr int kGroup = 4;  // objects per branch in the hot loop
+// Rare path of the sweep, out of line on purpose (keeps the hot loop's register and
+// code footprint small).  Re-tests `cnt` staged objects (chunk-local k0..k0+cnt-1,
+// global index kbase+k) against the thread's 8 rays, re-read from local memory
+// (SoA [x0..x7|y0..y7|z0..z7], 16-byte aligned): packed discriminants first, then
+// the scalar canonical-order routine only for the (ray, object) pairs with det > 0.
+// List order + strict '<' == scene.py:46-47 (the earlier shape wins ties).
+__device__ __noinline__ void rare_group(const float4* __restrict__ tab, int k0, int cnt, int kbase,
+                                        const float* dw, float* tmin, int* idx) {
+    const u64* dp = reinterpret_cast<const u64*>(dw);
+    u64 dx[kRays / 2], dy[kRays / 2], dz[kRays / 2];
+#pragma unroll
+    for (int p = 0; p < kRays / 2; p++) { dx[p] = dp[p]; dy[p] = dp[kRays / 2 + p]; dz[p] = dp[kRays + p]; }
+#pragma unroll 1
+    for (int j = 0; j < cnt; j++) {
+        const float4* rec = tab + 4 * (k0 + j);
+        const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2], q3 = rec[3];
+        const bool square = __float_as_int(q1.w) & 1;
+        float det[kRays];
+#pragma unroll
+        for (int p = 0; p < kRays / 2; p++) upk(pair_det<true>(q0, q1, q2, q3, dx[p], dy[p], dz[p]), det[2 * p], det[2 * p + 1]);
+        unsigned hits = 0;
+#pragma unroll
+        for (int r = 0; r < kRays; r++) hits |= ((square || det[r] > 0.0f) ? 1u : 0u) << r;
+        if (!hits) continue;
+        Obj ob;
+        load_rec(rec, ob);
+#pragma unroll 1
+        while (hits) {
+            const int r = __ffs(hits) - 1;
+            hits &= hits - 1;
+            HitRec h;
+            const float t = obj_test(ob, dw[r], dw[kRays + r], dw[2 * kRays + r], h);
+            if (t < tmin[r]) { tmin[r] = t; idx[r] = kbase + k0 + j; }
+        }
+    }
+}
+
+constexpr int kGroup = RRT_GROUP;  // objects per branch in the hot loop
 
 // max over the 8 dets of one object, folded into the running group max (FMNMX3 chain;
 // fmaxf drops NaN, and NaN is a miss: shape.py:124-125)
@@ -300,6 +330,26 @@ __device__ __forceinline__ void sweep_mixed(const float4* __restrict__ tab, int 
 }
 
 // ---------------------------------------------------------------- shading (float32)
+// x ** y like C pow() (Theano's T.pow, shader.py:45): integer-valued exponents up to
+// 1024 (shininess = 50 in every reference script) take square-and-multiply -- a
+// negative base is fine there, as in pow(); everything else goes to powf.
+__device__ __forceinline__ float pow_shininess(float x, float y) {
+    const int e = (int)y;
+    if ((float)e == y && e >= 0 && e <= 1024) {
+        float r = 1.0f, b = x;
+        int k = e;
+#pragma unroll 1
+        while (k) {
+            if (k & 1) r *= b;
+            b *= b;
+            k >>= 1;
+        }
+        return r;
+    }
+    return powf(x, y);
+}
+
+
 struct ShadeRec {
     float t, d[3], o[3], pn, nrm[3], ndl, rm[3], rv, pw, ph;
     bool inside[3];
@@ -317,8 +367,9 @@ __device__ __forceinline__ void shade(int shader, float max_depth, const Obj& ob
     }
     if (!(ob.flags & 1)) {  // Sphere.normals shape.py:134-137 (object-space normal)
         float p0 = fmaf(r.t, r.d[0], r.o[0]), p1 = fmaf(r.t, r.d[1], r.o[1]), p2 = fmaf(r.t, r.d[2], r.o[2]);
-        r.pn = sqrtf(p0 * p0 + p1 * p1 + p2 * p2);
-        float inv = 1.0f / r.pn;
+        const float pn2 = p0 * p0 + p1 * p1 + p2 * p2;
+        const float inv = rsqrtf(pn2);
+        r.pn = pn2 * inv;
         r.nrm[0] = p0 * inv; r.nrm[1] = p1 * inv; r.nrm[2] = p2 * inv;
     } else {                // Square.normals shape.py:55-68
         r.nrm[0] = r.nrm[1] = 0.f;
@@ -332,7 +383,7 @@ __device__ __forceinline__ void shade(int shader, float max_depth, const Obj& ob
 #pragma unroll
         for (int c = 0; c < 3; c++) r.rm[c] = 2.0f * r.ndl * r.nrm[c] + g.Lh[c];
         r.rv = r.rm[0] * g.look[0] + r.rm[1] * g.look[1] + r.rm[2] * g.look[2];
-        r.pw = powf(r.rv, mat[3]);
+        r.pw = pow_shininess(r.rv, mat[3]);
         r.ph += mat[2] * r.pw;
     }
 #pragma unroll
@@ -371,8 +422,8 @@ __device__ __forceinline__ void backward_ray(int shader, float max_depth, const 
         float g_n[3] = {0.f, 0.f, 0.f}, g_Lh[3] = {0.f, 0.f, 0.f};
         if (shader == RRT_SHADER_PHONG) {
             og[14] += g_ph * r.pw;
-            if (r.rv > 0.0f) og[15] += g_ph * mat[2] * r.pw * logf(r.rv);
-            float dpw = (r.rv != 0.0f) ? r.pw / r.rv : powf(r.rv, mat[3] - 1.0f);  // rv^(sh-1)
+            if (r.rv > 0.0f) og[15] += g_ph * mat[2] * r.pw * __logf(r.rv);
+            float dpw = (r.rv != 0.0f) ? __fdividef(r.pw, r.rv) : pow_shininess(r.rv, mat[3] - 1.0f);  // rv^(sh-1)
             float g_rv = g_ph * mat[2] * mat[3] * dpw;
             float g_rm[3];
 #pragma unroll
@@ -390,7 +441,7 @@ __device__ __forceinline__ void backward_ray(int shader, float max_depth, const 
         for (int c = 0; c < 3; c++) gg[c] += g_Lh[c];
         if (sphere) {
             float ndg = r.nrm[0] * g_n[0] + r.nrm[1] * g_n[1] + r.nrm[2] * g_n[2];
-            float inv = 1.0f / r.pn;
+            float inv = __frcp_rn(r.pn);
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 float gp = (g_n[c] - r.nrm[c] * ndg) * inv;
@@ -401,9 +452,9 @@ __device__ __forceinline__ void backward_ray(int shader, float max_depth, const 
         }
     }
     if (sphere) {
-        float ivn = 1.0f / h.vn;
+        float ivn = __frcp_rn(h.vn);
         float g_pd = -g_t * ivn, g_s = -g_t * ivn, g_vn = -g_t * r.t * ivn;
-        float g_det = g_s / (2.0f * sqrtf(h.det));
+        float g_det = g_s * 0.5f * rsqrtf(h.det);
         g_pd += 2.0f * h.pd * g_det;
         g_vn += ob.ncc * g_det;            // -cc * g_det
         float g_cc = -h.vn * g_det;
@@ -474,7 +525,7 @@ __device__ __forceinline__ void warp_flush(int key, float (&acc)[19], int* slot_
 // each with SPT samples: PIX*SPT = 8 rays.  S > SPT (generic path, PIX = 1) loops
 // over chunks of SPT samples.
 template <int PIX, int SPT, int MODE>
-__global__ void __launch_bounds__(256, 2) render_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_kernel(const __grid_constant__ KParams P) {
     extern __shared__ float4 smem_tab[];  // kObjChunk (or N) sweep records
     __shared__ Globals g;
     __shared__ int slot_key[kSlots];
@@ -566,7 +617,7 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const __grid_constant__ 
         // ---- build the 8 rays of this sample chunk.  Per-ray state lives in (L1-resident)
         // local memory: it is read by the rare path of the sweep and by the rolled shading /
         // reverse-pass loops below; only the packed world directions stay in registers.
-        float l_rc[3 * kRays], l_dw[3 * kRays], l_tmin[kRays];  // SoA: [x0..x7 | y0..y7 | z0..z7]
+        __align__(16) float l_rc[3 * kRays], l_dw[3 * kRays], l_tmin[kRays];  // SoA: [x0..x7 | y0..y7 | z0..z7]
         int l_idx[kRays];
         RayPack rp;
         {
