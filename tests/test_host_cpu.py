@@ -1,0 +1,273 @@
+"""CPU tests of the host side: the mirror of the reference's Python API, the packed
+tables Scene.build hands to the kernels, the C-ABI library's symbols, the
+fail-loudly behaviour without a GPU, and the multi-process sharding logic (gloo)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle_c as oc, oracle_numpy as on, scenes
+from reversible_raytracer_b200 import _native as nat, render as R, sharding, workloads as W
+from reversible_raytracer_b200 import transform as T
+from reversible_raytracer_b200.scene import Camera, Light, Material, Scene
+from reversible_raytracer_b200.shape import Sphere, Square
+from reversible_raytracer_b200.shader import DepthMapShader, PhongShader
+from reversible_raytracer_b200.optimize import GDOptimizer, MGDAutoOptimizer, get_epsilon
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(autouse=True)
+def cpu_default():
+    T.set_default_device('cpu')
+    yield
+
+
+# ---- the reference's own unit tests (test/test_transform.py:9-41) on the product's algebra
+def test_rotate_kat():
+    m = T.rotate(20, (0, 0, 1)).m.numpy()
+    assert np.all(np.isclose(m, [[0.93969262, -0.34202015, 0., 0.], [0.34202015, 0.93969262, 0., 0.],
+                                 [0., 0., 1., 0.], [0., 0., 0., 1.]]))
+
+
+def test_composition_kat():
+    m = (T.translate((4, 5, 6)) * T.rotate(20, (0, 0, 1))).m.numpy()
+    assert np.all(np.isclose(m, [[0.93969262, -0.34202015, 0., 4.], [0.34202015, 0.93969262, 0., 5.],
+                                 [0., 0., 1., 6.], [0., 0., 0., 1.]]))
+
+
+def test_apply_kat():
+    r = T.RayField((1, 0, 0), np.tile([0, 1, 0], (10, 10, 1)))
+    t = T.translate((4, 5, 6)) * T.rotate(90, (0, 0, 1))
+    out = t(r)
+    assert np.all(np.isclose(out.origin.numpy(), [4, 6, 6]))
+    assert np.all(np.isclose(out.rays.numpy(), np.tile([-1, 0, 0], (10, 10, 1)), atol=1e-6))
+
+
+def test_apply_spatial_transpose_matches_oracle():
+    rays = np.random.RandomState(0).normal(size=(6, 6, 3)).astype(np.float32)
+    t = T.translate((1, 2, 3)) * T.rotate(30, (0, 1, 0)) * T.scale((1, 2, 3))
+    out = t(T.RayField((0.5, 0, 1), rays))
+    o2, r2 = on.apply_rayfield(t.m.numpy(), (0.5, 0, 1), rays)
+    np.testing.assert_allclose(out.rays.numpy(), r2, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out.origin.numpy(), o2, rtol=1e-6)
+
+
+def test_inverse_and_exact_zeros():
+    t = T.translate((1., -2., 3.)) * T.scale((0.5, 0.25, 2.0))
+    w = t.inverse().m
+    np.testing.assert_allclose((w @ t.m).numpy(), np.eye(4), atol=1e-6)
+    off = w[:3, :3] - torch.diag(torch.diag(w[:3, :3]))
+    assert torch.count_nonzero(off) == 0          # diagonal fast path keys on exact zeros
+
+
+def test_lazy_transform_tracks_inplace_updates_and_autograd():
+    c = torch.tensor([1., 2., 3.], requires_grad=True)
+    s = Sphere(T.translate(c) * T.scale((2, 2, 2)), Material((1, 1, 1), .3, .7, .5, 50.))
+    w = s.w2o.m
+    np.testing.assert_allclose(w[:3, 3].detach().numpy(), [-0.5, -1.0, -1.5])
+    w[:3, 3].sum().backward()
+    np.testing.assert_allclose(c.grad.numpy(), [-0.5, -0.5, -0.5])
+    with torch.no_grad():
+        c.sub_(1.0)
+    np.testing.assert_allclose(s.w2o.m[:3, 3].detach().numpy(), [0.0, -0.5, -1.0])   # re-evaluated
+
+
+# ---- packed tables == the oracle's scene specs
+def _scene_c3():
+    m1 = Material((0.2, 0.9, 0.4), 0.3, 0.7, 0.5, 50.)
+    m2 = Material((0.87, 0.1, 0.507), 0.3, 0.9, 0.4, 50.)
+    objs = [Sphere(T.translate((-.5, -.5, 4)), m1), Sphere(T.translate((.5, .5, 4)), m2),
+            Square(T.translate((0, 0, 3)) * T.rotate(50, [0., 1., 0.]), m2)]
+    return Scene(objs, [Light((-1., -1., 2.), (1., 0.87, 0.961))], Camera(128, 128), PhongShader())
+
+
+def test_pack_matches_oracle_spec_match_mirror():
+    sc = _scene_c3()
+    obj_type, w2o, mat, light, cam = sc.pack(torch.device('cpu'))
+    ps = oc.PackedScene.from_spec(scenes.match_mirror())
+    assert obj_type.tolist() == ps.obj_type.tolist()
+    np.testing.assert_allclose(w2o.numpy(), ps.w2o[0], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(mat.numpy(), ps.material[0], rtol=1e-7)
+    np.testing.assert_allclose(light.numpy(), ps.light[0], rtol=1e-7)
+    np.testing.assert_allclose(cam.numpy(), ps.camera[0], rtol=1e-7)
+    cfg = sc.config(4)
+    assert (cfg.n, cfg.samples, cfg.shader, cfg.transpose, cfg.camera_grad) == (128, 4, nat.SHADER_PHONG, 1, 0)
+
+
+def test_pack_orbit_variant_and_depth_shader():
+    m1 = Material((0.0, 0.9, 0.0), 0.3, 0.7, 0.5, 50.)
+    m2 = Material((0.9, 0.0, 0.0), 0.3, 0.9, 0.4, 50.)
+    centre = (3.83, -8.14, 32.)
+    shapes = [Sphere(T.translate(centre) * T.scale((4., 4., 4.)), m1), Sphere(T.translate((0, 0, 48)) * T.scale((6, 6, 6)), m2)]
+    cam = Camera(64, 64, T.translate((0, 2.5, 0)), np.asarray([0, 0, 1], dtype='float32'))
+    sc = Scene(shapes, [Light((0., 0., 1.), (1., 1., 1.))], cam, PhongShader(specular=False))
+    _, w2o, mat, light, camera = sc.pack(torch.device('cpu'))
+    ps = oc.PackedScene.from_spec(scenes.orbit(centre, 0))
+    np.testing.assert_allclose(w2o.numpy(), ps.w2o[0], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(camera.numpy(), ps.camera[0], rtol=1e-7)
+    cfg = sc.config()
+    assert (cfg.shader, cfg.transpose, cfg.camera_grad) == (nat.SHADER_PHONG_NOSPEC, 0, 1)
+    sc2 = Scene(shapes, sc.lights, Camera(32, 32), DepthMapShader(6.1))
+    assert sc2.config().shader == nat.SHADER_DEPTH and abs(sc2.config().max_depth - 6.1) < 1e-6
+    with pytest.raises(ValueError):
+        Scene(shapes, sc.lights, Camera(32, 16), PhongShader()).config()
+
+
+def test_jitter_is_baked_and_transposed_for_root_variant():
+    sc = _scene_c3()
+    jx, jy = sc._jitter_for(8, 4, None, 11, torch.device('cpu'))
+    rng = np.random.RandomState(11)
+    ex = np.asarray(rng.random_sample((8, 8, 4)), dtype=np.float32)        # x drawn first (scene.py:24-25)
+    ey = np.asarray(rng.random_sample((8, 8, 4)), dtype=np.float32)
+    np.testing.assert_array_equal(jx.numpy(), ex.transpose(1, 0, 2))        # image index space
+    np.testing.assert_array_equal(jy.numpy(), ey.transpose(1, 0, 2))
+    again = sc._jitter_for(8, 4, None, None, torch.device('cpu'))           # same jitter on every build
+    assert again[0] is jx
+
+
+def test_workloads_match_oracle_scenes():
+    for general in (False, True):
+        tb = W.stress_tables(40, general=general)
+        ps = oc.PackedScene.from_spec(scenes.stress(n=16, num_objects=40, general=general))
+        np.testing.assert_allclose(tb['w2o'], ps.w2o[0], rtol=2e-6, atol=2e-6)
+        np.testing.assert_allclose(tb['material'], ps.material[0], rtol=1e-6)
+        if not general:
+            A = tb['w2o'].reshape(-1, 3, 4)[:, :, :3]
+            assert np.count_nonzero(A - A * np.eye(3)) == 0
+    ob = W.orbit_tables(4)
+    assert ob['w2o'].shape == (8, 2, 12) and ob['camera'].shape == (8, 15)
+    ps = oc.PackedScene.from_spec(scenes.orbit(ob['centres'][1], 1))
+    np.testing.assert_allclose(ob['w2o'][3], ps.w2o[0], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(ob['camera'][3], ps.camera[0], rtol=1e-7)
+    assert W.algorithmic_flops(100, 10, 50) == 100 * 10 * 16 + 50 * 320
+
+
+# ---- C ABI: the library loads and exports everything include/rrt_b200.h declares
+def test_cabi_exports_and_struct_layout(tmp_path):
+    hdr = open(os.path.join(ROOT, 'include', 'rrt_b200.h')).read()
+    declared = sorted(set(re.findall(r'\b(rrt_[a-z0-9_]+)\s*\(', hdr)))
+    assert set(declared) == set(nat.EXPORTS), declared
+    L = nat.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.rrt_version() == 100
+    # struct layout: ctypes mirror == what the C compiler sees
+    src = tmp_path / 'sz.c'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rrt_b200.h"\nint main(){printf("%zu %zu %zu %zu", sizeof(rrt_scene), '
+                   'offsetof(rrt_scene, seed), offsetof(rrt_scene, obj_type), offsetof(rrt_scene, jitter_scene_stride));return 0;}')
+    exe = tmp_path / 'sz'
+    subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), '-o', str(exe), str(src)])
+    size, o_seed, o_obj, o_js = map(int, subprocess.check_output([str(exe)]).split())
+    for S in (nat.RrtScene, oc.RrtScene):
+        assert ctypes.sizeof(S) == size
+        assert (S.seed.offset, S.obj_type.offset, S.jitter_scene_stride.offset) == (o_seed, o_obj, o_js)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'reversible_raytracer_b200')
+    for fn in os.listdir(pkg):
+        if fn.endswith('.py'):
+            txt = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r'^\s*(from|import)\s+oracle', txt, re.M), fn
+
+
+def test_no_cpu_fallback():
+    ps = oc.PackedScene.from_spec(scenes.test_balls())
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    cfg = R.RenderConfig(n=32, samples=4, shader=nat.SHADER_DEPTH, max_depth=6.1)
+    with pytest.raises(nat.NativeError):
+        R.render_forward(cfg, t(ps.obj_type), t(ps.w2o[0]), t(ps.material), t(ps.light), t(ps.camera), None)
+    if not torch.cuda.is_available():
+        with pytest.raises(nat.NativeError):
+            _scene_c3().build()
+
+
+# ---- optimiser re-host
+def test_gdoptimizer_both_call_shapes():
+    x = torch.tensor([3.0, -2.0])
+    loss = lambda: (x ** 2).sum()
+    train = GDOptimizer().optimize([x], loss)                 # optimize.py:19-29 (HEAD): fn(lr)
+    v0 = train(0.1)
+    assert abs(v0 - 13.0) < 1e-6
+    np.testing.assert_allclose(x.detach().numpy(), [2.4, -1.6], rtol=1e-6)
+    train2 = GDOptimizer().optimize([x], loss, 0.5, 0.1)      # stale 4-arg form: fn()
+    train2()
+    np.testing.assert_allclose(x.detach().numpy(), [0.0, 0.0], atol=1e-6)
+    with pytest.raises(TypeError):
+        GDOptimizer().optimize([x], loss)()
+    assert abs(get_epsilon(1e-4, 200, 100) - 1e-4 / 1.5) < 1e-12
+
+
+def test_mgd_auto_optimizer():
+    class AE:
+        def __init__(self):
+            self.params = [torch.tensor([[1.0, 2.0]]), torch.tensor([0.5])]
+        def cost(self, Xl, Xr=None):
+            y = (self.params[0] * Xl).sum() + self.params[1].sum()
+            return y * y if Xr is None else y * y + (Xr.sum() - self.params[1].sum()) ** 2
+    ae = AE()
+    c0 = MGDAutoOptimizer(ae).optimize(torch.tensor([[1.0, 1.0]]))(0.01)
+    c1 = MGDAutoOptimizer(ae).optimize(torch.tensor([[1.0, 1.0]]))(0.01)
+    assert c1 < c0
+    ae2 = AE()
+    data = torch.ones(2, 2, 2)
+    opt = MGDAutoOptimizer(ae2).optimize(data, lam=0.0)
+    b0 = ae2.params[1].clone()
+    opt(1, 0.01)
+    assert not torch.equal(ae2.params[1], b0)
+
+
+# ---- sharding
+def test_row_slabs_partition():
+    for n, world in ((4096, 8), (4096, 3), (7, 8), (64, 1), (33, 4)):
+        rows = [sharding.row_slab(n, world, r) for r in range(world)]
+        assert sum(c for _, c in rows) == n
+        pos = 0
+        for b, c in rows:
+            assert b == pos and c >= 0
+            pos += c
+        assert max(c for _, c in rows) - min(c for _, c in rows) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        # each rank owns a row slab of an oracle render and contributes its slab's loss + gradient
+        ps = oc.PackedScene.from_spec(scenes.optimize_brightness(n=40))
+        img, _, _ = oc.render_forward(ps, want_aux=False)
+        target = np.ascontiguousarray(img[0][:, ::-1, :])
+        rb, rc = sharding.row_slab(ps.n, world, rank)
+        _, _, loss, grad = oc.render_fused_mse(ps.slab(rb, rc), target[rb:rb + rc])
+        l, g = sharding.allreduce_loss_grad(torch.from_numpy(loss), torch.from_numpy(grad[0]).float())
+        q.put((rank, float(l[0]), g.double().numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_gradient_sum_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ps = oc.PackedScene.from_spec(scenes.optimize_brightness(n=40))
+    img, _, _ = oc.render_forward(ps, want_aux=False)
+    _, _, loss, grad = oc.render_fused_mse(ps, np.ascontiguousarray(img[0][:, ::-1, :]))
+    for rank, l, g in res:
+        assert abs(l - loss[0]) <= 1e-9 * abs(loss[0])
+        np.testing.assert_allclose(g, grad[0], rtol=1e-5, atol=1e-5 * np.abs(grad[0]).max())
