@@ -41,6 +41,7 @@ def parse():
     ap.add_argument('--samples', type=int, default=4)
     ap.add_argument('--general', action='store_true', help='C5g: rotated, non-uniformly scaled spheres')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--miss', action='store_true', help='diagnostic: move every sphere out of view (pure sweep, no hits)')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     return ap.parse_args()
 
@@ -167,6 +168,9 @@ def run_b200(args):
 
     tb = W.stress_tables(N, general=args.general)
     tt = W.stress_tables(N, general=args.general, centre_noise=0.05)
+    if args.miss:
+        for t_ in (tb, tt):
+            t_['w2o'].reshape(-1, 3, 4)[:, 0, 3] -= 1.0e4   # b_x = -c_x/r: shifts every centre far off-axis
     host = {k: torch.from_numpy(tb[k]).pin_memory() for k in ('w2o', 'material', 'light', 'camera')}
     d = {k: v.to(dev) for k, v in host.items()}
     obj_type = torch.from_numpy(tb['obj_type']).to(dev)

@@ -69,6 +69,10 @@ struct KParams {
     float cw[3];
     double* loss;
     float* grad;
+    // host-precomputed prologue constants
+    double lin_step;   // 1/(n-1): np.linspace step magnitude (0 when n == 1)
+    float inv_s, inv_n; // exact reciprocals when S and n are powers of two
+    int pow2;          // 1: (u+s)/S/n may be evaluated as exact multiplications
 };
 
 // ---------------------------------------------------------------- packed f32x2
@@ -105,18 +109,18 @@ __device__ __forceinline__ float rrt_rng(u64 seed, uint32_t scene, uint32_t pix,
 }
 
 // ---------------------------------------------------------------- primary rays
-// np.linspace(start, stop, n)[i] = fl(fl(i*step) + start), last element = stop.
-__device__ __forceinline__ double lin(int i, int n, double start, double stop) {
+// np.linspace(start, stop, n)[i] = fl(fl(i*step) + start), last element = stop; the
+// step (stop-start)/(n-1) = +-1/(n-1) is computed once on the host in IEEE double.
+__device__ __forceinline__ double lin(int i, int n, double start, double stop, double step) {
     if (n == 1) return start;
     if (i == n - 1) return stop;
-    double step = __ddiv_rn(stop - start, (double)(n - 1));
     return __dadd_rn(__dmul_rn((double)i, step), start);
 }
 
 // Camera.make_rays scene.py:66-72: float64 grid, normalise, cast to float32.
-__device__ __forceinline__ void base_ray(int n, int i, int j, float& rx, float& ry, float& rz) {
-    double x = lin(i, n, 0.5, -0.5);
-    double y = lin(j, n, -0.5, 0.5);
+__device__ __forceinline__ void base_ray(int n, double step, int i, int j, float& rx, float& ry, float& rz) {
+    double x = lin(i, n, 0.5, -0.5, -step);
+    double y = lin(j, n, -0.5, 0.5, step);
     double s = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), 1.0);
     double nrm = __dsqrt_rn(s);
     rx = __double2float_rn(__ddiv_rn(x, nrm));
@@ -127,6 +131,10 @@ __device__ __forceinline__ void base_ray(int n, int i, int j, float& rx, float& 
 // scene.py:31-32 then :73-74, all float32 round-to-nearest.
 __device__ __forceinline__ float jitter_offset(float u, int s, int S, int n) {
     return __fdiv_rn(__fdiv_rn(__fadd_rn(u, (float)s), (float)S), (float)n);
+}
+// same value when S and n are powers of two (division by 2^k == multiplication by 2^-k, exact)
+__device__ __forceinline__ float jitter_offset_pow2(float u, int s, float inv_s, float inv_n) {
+    return __fmul_rn(__fmul_rn(__fadd_rn(u, (float)s), inv_s), inv_n);
 }
 
 __device__ __forceinline__ float dot3_canon(float a0, float a1, float a2, float v0, float v1, float v2) {
@@ -532,10 +540,15 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
     __shared__ float slots[kSlots * kSlotStride];
     __shared__ float gglob[9];
     __shared__ float loss_warp[kMaxWarps];
+    __shared__ int cam_identity_s;
     __shared__ int chunk_class;  // sticky per CTA: bit0 squares, bit1 general spheres seen
 
     const rrt_scene& sc = P.sc;
-    const int n = sc.n, S = sc.samples, N = sc.num_objects;
+    // S is a compile-time constant except in the generic (PIX=1, SPT=8) instantiation, so the
+    // sample-chunk loop below has exactly one trip and nothing reverse-pass related is live
+    // across the sweep.
+    const int n = sc.n, N = sc.num_objects;
+    const int S = (PIX == 1) ? sc.samples : SPT;
     const int scene = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int al = blockIdx.y * nwarps + warp;      // slab-local row
@@ -562,6 +575,8 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
             g.Ln = ln;
             g.Lh[0] = g.L[0] / ln; g.Lh[1] = g.L[1] / ln; g.Lh[2] = g.L[2] / ln;
             chunk_class = 0;
+            cam_identity_s = (g.C[0] == 1.f && g.C[4] == 1.f && g.C[8] == 1.f && g.C[1] == 0.f && g.C[2] == 0.f &&
+                              g.C[3] == 0.f && g.C[5] == 0.f && g.C[6] == 0.f && g.C[7] == 0.f);
         }
         if (tid < kSlots) slot_key[tid] = -1;
         if (tid < 9) gglob[tid] = 0.f;
@@ -569,6 +584,7 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
     for (int q = tid; q < kSlots * kSlotStride; q += blockDim.x) slots[q] = 0.f;
     __syncthreads();
 
+    const bool cam_identity = cam_identity_s != 0;
     const float* w2o = sc.w2o + (size_t)scene * sc.w2o_scene_stride;
     const float* mats = sc.material + (size_t)scene * sc.material_scene_stride;
     float* gobj = (MODE != MODE_FWD) ? P.grad + (size_t)scene * RRT_GRAD_SIZE(N) : nullptr;
@@ -579,7 +595,7 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
     for (int px = 0; px < PIX; px++) {
         int b = b0 + px;
         int i = sc.transpose ? b : a, j = sc.transpose ? a : b;
-        if (row_ok && b < n) base_ray(n, i, j, bx[px], by[px], bz[px]);
+        if (row_ok && b < n) base_ray(n, P.lin_step, i, j, bx[px], by[px], bz[px]);
         else { bx[px] = by[px] = bz[px] = 0.f; }
     }
 
@@ -640,13 +656,18 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                         jx = rrt_rng(sc.seed, scene, (uint32_t)(a * n + b), s, 0);
                         jy = rrt_rng(sc.seed, scene, (uint32_t)(a * n + b), s, 1);
                     }
-                    rcx = __fadd_rn(bx[px], jitter_offset(jx, s, S, n));
-                    rcy = __fadd_rn(by[px], jitter_offset(jy, s, S, n));
+                    const float ox = P.pow2 ? jitter_offset_pow2(jx, s, P.inv_s, P.inv_n) : jitter_offset(jx, s, S, n);
+                    const float oy = P.pow2 ? jitter_offset_pow2(jy, s, P.inv_s, P.inv_n) : jitter_offset(jy, s, S, n);
+                    rcx = __fadd_rn(bx[px], ox);
+                    rcy = __fadd_rn(by[px], oy);
                     rcz = bz[px];
-                    // camera.o2w (identity in the root variant)
-                    wx[r] = dot3_canon(g.C[0], g.C[1], g.C[2], rcx, rcy, rcz);
-                    wy[r] = dot3_canon(g.C[3], g.C[4], g.C[5], rcx, rcy, rcz);
-                    wz[r] = dot3_canon(g.C[6], g.C[7], g.C[8], rcx, rcy, rcz);
+                    if (cam_identity) {     // root variant: C = I, the fma chain returns its input
+                        wx[r] = rcx; wy[r] = rcy; wz[r] = rcz;
+                    } else {                // camera.o2w, orbit_experiments/scene.py:80
+                        wx[r] = dot3_canon(g.C[0], g.C[1], g.C[2], rcx, rcy, rcz);
+                        wy[r] = dot3_canon(g.C[3], g.C[4], g.C[5], rcx, rcy, rcz);
+                        wz[r] = dot3_canon(g.C[6], g.C[7], g.C[8], rcx, rcy, rcz);
+                    }
                 }
                 l_rc[r] = rcx; l_rc[kRays + r] = rcy; l_rc[2 * kRays + r] = rcz;
                 l_dw[r] = wx[r]; l_dw[kRays + r] = wy[r]; l_dw[2 * kRays + r] = wz[r];
@@ -700,8 +721,8 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                 const int px = r / SPT, s = sc0 * SPT + r % SPT, b = b0 + px;
                 if (row_ok && b < n && s < S) {
                     size_t ro = (((size_t)scene * S + s) * P.rows + al) * n + b;
-                    if (P.hit_out) P.hit_out[ro] = l_idx[r];
-                    if (MODE == MODE_FWD && P.tmin_out) P.tmin_out[ro] = l_tmin[r];
+                    if (P.hit_out) __stcs(P.hit_out + ro, l_idx[r]);
+                    if (MODE == MODE_FWD && P.tmin_out) __stcs(P.tmin_out + ro, l_tmin[r]);
                 }
             }
         }
@@ -718,9 +739,7 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                 float m7[7];
 #pragma unroll
                 for (int q = 0; q < 7; q++) m7[q] = __ldg(mat + q);
-                float dwx = dot3_canon(g.C[0], g.C[1], g.C[2], l_rc[r], l_rc[kRays + r], l_rc[2 * kRays + r]);
-                float dwy = dot3_canon(g.C[3], g.C[4], g.C[5], l_rc[r], l_rc[kRays + r], l_rc[2 * kRays + r]);
-                float dwz = dot3_canon(g.C[6], g.C[7], g.C[8], l_rc[r], l_rc[kRays + r], l_rc[2 * kRays + r]);
+                const float dwx = l_dw[r], dwy = l_dw[kRays + r], dwz = l_dw[2 * kRays + r];
                 HitRec h;
                 obj_test(ob, dwx, dwy, dwz, h);
                 ShadeRec sr;
@@ -743,9 +762,9 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                 size_t po = (((size_t)scene * P.rows + al) * n + b) * 3;
                 float inv = 1.0f / (float)S;
                 float v0 = pixsum[px][0] * inv, v1 = pixsum[px][1] * inv, v2 = pixsum[px][2] * inv;  // scene.py:49-50
-                if (P.image) { P.image[po] = v0; P.image[po + 1] = v1; P.image[po + 2] = v2; }
+                if (P.image) { __stcs(P.image + po, v0); __stcs(P.image + po + 1, v1); __stcs(P.image + po + 2, v2); }
                 if (MODE == MODE_FUSED) {
-                    float d0 = v0 - P.target[po], d1 = v1 - P.target[po + 1], d2 = v2 - P.target[po + 2];
+                    float d0 = v0 - __ldcs(P.target + po), d1 = v1 - __ldcs(P.target + po + 1), d2 = v2 - __ldcs(P.target + po + 2);
                     loss_part += P.cw[0] * d0 * d0 + P.cw[1] * d1 * d1 + P.cw[2] * d2 * d2;
                     gpix[px][0] = 2.0f * P.cw[0] * d0 * inv;
                     gpix[px][1] = 2.0f * P.cw[1] * d1 * inv;
@@ -765,9 +784,7 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                 float dwx = 0.f, dwy = 0.f, dwz = 0.f;
                 if (k >= 0) {
                     make_obj(w2o + (size_t)k * RRT_W2O_STRIDE, sc.obj_type[k], g.ct, ob);
-                    dwx = dot3_canon(g.C[0], g.C[1], g.C[2], l_rc[r], l_rc[kRays + r], l_rc[2 * kRays + r]);
-                    dwy = dot3_canon(g.C[3], g.C[4], g.C[5], l_rc[r], l_rc[kRays + r], l_rc[2 * kRays + r]);
-                    dwz = dot3_canon(g.C[6], g.C[7], g.C[8], l_rc[r], l_rc[kRays + r], l_rc[2 * kRays + r]);
+                    dwx = l_dw[r]; dwy = l_dw[kRays + r]; dwz = l_dw[2 * kRays + r];
                     obj_test(ob, dwx, dwy, dwz, h);
                     if (!(h.t < __int_as_float(0x7f800000))) k = -1;  // stale stored winner
                 }
@@ -975,8 +992,12 @@ int check_scene(const rrt_scene* sc, int* rows_out) {
 }
 
 template <int MODE>
-int launch(const KParams& P, cudaStream_t st) {
+int launch(KParams& P, cudaStream_t st) {
     const rrt_scene& sc = P.sc;
+    P.lin_step = sc.n > 1 ? 1.0 / (double)(sc.n - 1) : 0.0;
+    P.inv_s = 1.0f / (float)sc.samples;
+    P.inv_n = 1.0f / (float)sc.n;
+    P.pow2 = ((sc.samples & (sc.samples - 1)) == 0) && ((sc.n & (sc.n - 1)) == 0);
     const int S = sc.samples;
     int pix;
     if (S == 1) pix = 8; else if (S == 2) pix = 4; else if (S == 4) pix = 2; else pix = 1;
