@@ -152,8 +152,34 @@ int rrt_render_fused_mse(const rrt_scene* scene, const float* target,
                          double* loss, float* grad, void* stream);
 
 /*
+ * Parameter -> matrix chain.  Replaces the symbolic transform algebra that feeds the
+ * renderer: translate / scale / rotate (transform.py:60-122), Transform.__mul__ and
+ * .inverse (transform.py:32-38) and, in rrt_chain_backward, T.grad through them.
+ * One thread evaluates one chain = product of up to RRT_CHAIN_MAX_OPS primitive
+ * matrices, e.g. shape.w2o = (translate(c) * rotate(a, axis) * scale(s)).inverse()
+ * is the chain [scale^-1, rotate^-1, translate^-1].
+ *   ops        [num_ops][4] int32 (device): kind | RRT_CHAIN_INVERT, arg0, arg1, unused
+ *                kind RRT_CHAIN_TRANSLATE / _SCALE: 3 floats at values[arg0]
+ *                kind RRT_CHAIN_ROTATE: angle (degrees) at values[arg0], axis[3] at values[arg1]
+ *   chain_begin [num_chains+1] int32 (device): ops of chain k are [chain_begin[k], chain_begin[k+1])
+ *   values     [num_values] float32 (device): constants and live parameters, gathered by the host
+ *   out        [num_chains][12] float32: rows 0..2 of each product (row-major 3x4)
+ *   g_out      [num_chains][12] float32: dL/d out;  g_values [num_values] float32, zeroed by the callee
+ */
+#define RRT_CHAIN_TRANSLATE 1
+#define RRT_CHAIN_SCALE 2
+#define RRT_CHAIN_ROTATE 3
+#define RRT_CHAIN_INVERT 0x100
+#define RRT_CHAIN_MAX_OPS 8
+int rrt_chain_forward(const int32_t* ops, const int32_t* chain_begin, int num_chains, const float* values,
+                      float* out, void* stream);
+int rrt_chain_backward(const int32_t* ops, const int32_t* chain_begin, int num_chains, const float* values,
+                       const float* g_out, float* g_values, int num_values, void* stream);
+
+/*
  * FP32 pipe micro-benchmark used as the roofline denominator (MEASURED_PEAKS.json
- * has no FP32 entry).  mode 0 = scalar FFMA, 1 = packed FFMA2 (fma.rn.f32x2).
+ * has no FP32 entry).  mode 0 = scalar FFMA, 1 = packed FFMA2 (fma.rn.f32x2),
+ * 2 = FFMA2 + one ALU-pipe FMNMX3 per 4 (diagnostic: shows FFMA2 does not dual-issue).
  * Synchronises the stream.  tflops is a HOST pointer.
  */
 int rrt_measure_fp32_peak(int mode, int iters, double* tflops, double* ms, void* stream);

@@ -20,12 +20,19 @@ from .util import get_epsilon  # noqa: F401
 
 
 class GDOptimizer(object):
-    """Gradient descent: var <- var - lr * dloss/dvar (optimize.py:11-29)."""
+    """Gradient descent: var <- var - lr * dloss/dvar (optimize.py:11-29).
+
+    The reference compiles forward + T.grad + update into ONE Theano function; the
+    equivalent here is a CUDA graph: after two eager warm-up calls the whole step (loss
+    closure, torch.autograd.grad, in-place update) is captured once and every later
+    train() is a single graph replay (graph='auto', the default; falls back to eager
+    stepping if the closure cannot be captured, e.g. it synchronises).  graph=False keeps
+    eager stepping."""
 
     def __init__(self):
         pass
 
-    def optimize(self, tVars, loss, lr=None, momentum=0):
+    def optimize(self, tVars, loss, lr=None, momentum=0, graph='auto'):
         if not callable(loss):
             raise TypeError('loss must be a callable returning a scalar tensor (eager re-host of the '
                             'symbolic loss expression of optimize.py:19)')
@@ -33,19 +40,54 @@ class GDOptimizer(object):
         for v in tVars:
             v.requires_grad_(True)
         default_lr = lr
+        use_graph = bool(graph) and all(v.is_cuda for v in tVars)
+        st = dict(calls=0, graph=None, value=None, lr=None, failed=False)
 
-        def train(step_lr=None):
-            step_lr = default_lr if step_lr is None else step_lr
-            if step_lr is None:
-                raise TypeError('learning rate missing: call train(lr)')
+        def step(step_lr):
             value = loss()
             grads = torch.autograd.grad(value, tVars, allow_unused=True)
             with torch.no_grad():
                 for var, g in zip(tVars, grads):
                     if g is not None:
                         var.sub_(step_lr * g.to(var.device))
-            return float(value.detach())
+            return value
 
+        def capture():
+            dev = tVars[0].device
+            st['lr'] = torch.zeros((), dtype=torch.float32, device=dev)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            saved = [v.detach().clone() for v in tVars]
+            with torch.cuda.stream(side):          # warm-up on a side stream (PyTorch capture recipe)
+                step(st['lr'])
+            torch.cuda.current_stream(dev).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st['value'] = step(st['lr'])
+            with torch.no_grad():                  # lr was 0 during warm-up/capture; restore exactly anyway
+                for v, s0 in zip(tVars, saved):
+                    v.copy_(s0)
+            st['graph'] = g
+
+        def train(step_lr=None):
+            step_lr = default_lr if step_lr is None else step_lr
+            if step_lr is None:
+                raise TypeError('learning rate missing: call train(lr)')
+            st['calls'] += 1
+            if use_graph and st['graph'] is None and not st['failed'] and st['calls'] > 2:
+                try:
+                    capture()
+                except Exception:                  # closure not capturable: keep stepping eagerly
+                    st['failed'] = True
+                    st['graph'] = None
+                    torch.cuda.synchronize()
+            if st['graph'] is not None:
+                st['lr'].fill_(float(step_lr))
+                st['graph'].replay()
+                return float(st['value'].detach())
+            return float(step(step_lr).detach())
+
+        train.state = st
         return train
 
 

@@ -33,6 +33,8 @@ class Material(object):
     """scene.py:89-101"""
 
     def __init__(self, color, ks, kd, ka, shininess):
+        # live parameters (torch tensors) are re-read on every build; constants are packed once
+        self.dynamic = any(isinstance(v, torch.Tensor) for v in (color, ks, kd, ka, shininess))
         self.ks = as_tensor(ks)
         self.kd = as_tensor(kd)
         self.ka = as_tensor(ka)
@@ -50,6 +52,7 @@ class Light(object):
     """Directional light, scene.py:78-86."""
 
     def __init__(self, direction, intensity):
+        self.dynamic = isinstance(direction, torch.Tensor) or isinstance(intensity, torch.Tensor)
         self.direction = as_tensor(direction)
         self.intensity = as_tensor(intensity)
 
@@ -72,6 +75,7 @@ class Camera(object):
         self.o2w = o2w if o2w is not None else identity()
         self.w2o = self.o2w.inverse()
         self.look_at = as_tensor(np.asarray([0, 0, 1.], dtype='float32') if camera_dir is None else camera_dir)
+        self.dynamic_look_at = isinstance(camera_dir, torch.Tensor)
         self.rays = None
 
     def make_rays(self, x_dims, y_dims, sampleDist_x=None, sampleDist_y=None):
@@ -104,6 +108,7 @@ class Scene(object):
         self.camera = camera
         self.shader = shader
         self._jitter = {}
+        self._cache = None
         self.last_hit_index = None
 
     # -- jitter ---------------------------------------------------------------
@@ -136,23 +141,62 @@ class Scene(object):
 
     # -- packing ----------------------------------------------------------------
     def device(self):
+        if self._cache is not None:
+            return self._cache['device']
+        d = default_device()
+        if d.type == 'cuda':
+            return d
         for s in self.shapes:
             if s.w2o.m.is_cuda:
                 return s.w2o.m.device
-        return default_device()
+        return d
+
+    def _static(self, device):
+        """Structure-dependent state cached across builds: the compiled transform chain
+        (chain.py), obj_type, and the packed tables of constant materials / light / camera."""
+        st = self._cache
+        shapes = list(self.shapes)
+        if (st is not None and st['device'] == device and len(st['shapes']) == len(shapes)
+                and all(a is b for a, b in zip(st['shapes'], shapes))
+                and all(a is b.w2o for a, b in zip(st['w2o'], shapes))
+                and st['camera'] is self.camera and st['light'] is self.lights[0]):
+            return st
+        from .chain import ChainProgram
+        st = dict(device=device, shapes=shapes, w2o=[s.w2o for s in shapes], camera=self.camera, light=self.lights[0])
+        st['obj_type'] = torch.tensor([s.kind for s in shapes], dtype=torch.int32, device=device)
+        try:
+            st['prog'] = ChainProgram([s.w2o for s in shapes] + [self.camera.o2w], device) if device.type == 'cuda' else None
+        except ValueError:
+            st['prog'] = None                      # explicit-matrix transforms: torch path
+        st['mat'] = None
+        if shapes and not any(s.material.dynamic for s in shapes):
+            st['mat'] = torch.stack([s.material.packed(device) for s in shapes]).detach()
+        st['light_t'] = None if self.lights[0].dynamic else self.lights[0].packed(device).detach()
+        self._cache = st
+        return st
 
     def pack(self, device=None):
         """-> (obj_type int32[N], w2o [N,12], material [N,7], light [6], camera [15]),
         all on `device`, differentiable w.r.t. whatever the user's tensors require."""
         device = device or self.device()
-        if len(self.shapes) == 0:
-            w2o = torch.zeros((0, 12), dtype=torch.float32, device=device)
-            mat = torch.zeros((0, 7), dtype=torch.float32, device=device)
+        st = self._static(device)
+        N = len(self.shapes)
+        if st['prog'] is not None:
+            rows = st['prog'].evaluate()           # one kernel: every w2o + the camera matrix
+            w2o, cam_rows = rows[:N], rows[N]
         else:
-            w2o = torch.stack([s.w2o.m[:3, :].reshape(12).to(device) for s in self.shapes])
+            w2o = torch.stack([s.w2o.m[:3, :].reshape(12).to(device) for s in self.shapes]) if N else \
+                torch.zeros((0, 12), dtype=torch.float32, device=device)
+            cam_rows = self.camera.o2w.m[:3, :].reshape(12).to(device)
+        if st['mat'] is not None:
+            mat = st['mat']
+        elif N:
             mat = torch.stack([s.material.packed(device) for s in self.shapes])
-        obj_type = torch.tensor([s.kind for s in self.shapes], dtype=torch.int32, device=device)
-        return obj_type, w2o, mat, self.lights[0].packed(device), self.camera.packed(device)
+        else:
+            mat = torch.zeros((0, 7), dtype=torch.float32, device=device)
+        light = st['light_t'] if st['light_t'] is not None else self.lights[0].packed(device)
+        cam = torch.cat([cam_rows, self.camera.look_at.reshape(3).to(device)])
+        return st['obj_type'], w2o, mat, light, cam
 
     def config(self, antialias_samples=4):
         cam = self.camera

@@ -61,10 +61,14 @@ class Transform(object):
     evaluated once and cached.
     """
 
-    def __init__(self, m=None, mInv=None, _fm=None, _fmInv=None, _dynamic=False):
+    def __init__(self, m=None, mInv=None, _fm=None, _fmInv=None, _dynamic=False, _expr=None):
         self._m, self._mInv = m, mInv
         self._fm, self._fmInv = _fm, _fmInv
         self._dynamic = _dynamic
+        # structure of the expression, for the native parameter->matrix chain (chain.py):
+        #   ('T'|'S', tensor, is_parameter) | ('R', angle, axis, is_parameter) | ('mul', A, B) | ('inv', A)
+        #   | ('I',) | None (explicit matrices: not expressible, torch path only)
+        self._expr = _expr
 
     @property
     def m(self):
@@ -87,7 +91,8 @@ class Transform(object):
         return self._mInv
 
     def inverse(self):
-        return Transform(self._mInv, self._m, self._fmInv, self._fm, self._dynamic)
+        return Transform(self._mInv, self._m, self._fmInv, self._fm, self._dynamic,
+                         _expr=None if self._expr is None else ('inv', self))
 
     def __mul__(self, other):
         # transform.py:35-38: m = A.m . B.m ; mInv = B.mInv . A.mInv.  Explicit
@@ -96,7 +101,8 @@ class Transform(object):
         a, b = self, other
         return Transform(_fm=lambda: _mm4(a.m, b.m.to(a.m.device)),
                          _fmInv=lambda: _mm4(b.mInv, a.mInv.to(b.mInv.device)),
-                         _dynamic=a._dynamic or b._dynamic)
+                         _dynamic=a._dynamic or b._dynamic,
+                         _expr=None if (a._expr is None or b._expr is None) else ('mul', a, b))
 
     def __call__(self, x):
         """Apply to a RayField.  Like the reference (transform.py:44-46) the `.T` on the
@@ -124,7 +130,7 @@ def _eye(device):
 
 def identity():
     """transform.py:56-58"""
-    return Transform(_eye(default_device()), _eye(default_device()))
+    return Transform(_eye(default_device()), _eye(default_device()), _expr=('I',))
 
 
 def _place(device, entries):
@@ -145,7 +151,7 @@ def translate(x):
     x = as_tensor(x)
     return Transform(_fm=lambda: _place(x.device, {(0, 3): x[0], (1, 3): x[1], (2, 3): x[2]}),
                      _fmInv=lambda: _place(x.device, {(0, 3): -x[0], (1, 3): -x[1], (2, 3): -x[2]}),
-                     _dynamic=dyn)
+                     _dynamic=dyn, _expr=('T', x, dyn))
 
 
 def scale(x):
@@ -154,7 +160,7 @@ def scale(x):
     x = as_tensor(x)
     return Transform(_fm=lambda: _place(x.device, {(0, 0): x[0], (1, 1): x[1], (2, 2): x[2]}),
                      _fmInv=lambda: _place(x.device, {(0, 0): 1. / x[0], (1, 1): 1. / x[1], (2, 2): 1. / x[2]}),
-                     _dynamic=dyn)
+                     _dynamic=dyn, _expr=('S', x, dyn))
 
 
 def rotate(angle, axis):
@@ -164,7 +170,7 @@ def rotate(angle, axis):
     axis_t = as_tensor(axis)
     angle_t = as_tensor(angle, device=axis_t.device)
     return Transform(_fm=lambda: _rotation(angle_t, axis_t), _fmInv=lambda: _rotation(angle_t, axis_t).t(),
-                     _dynamic=dyn)
+                     _dynamic=dyn, _expr=('R', angle_t, axis_t, dyn))
 
 
 def _rotation(angle, a):

@@ -179,3 +179,55 @@ def test_fit_golden_orbit_renders(cuda):
                 sc.shapes = [Sphere(translate(c) * scale((4., 4., 4.)), m1), Sphere(translate((0, 0, 48)) * scale((6, 6, 6)), m2)]
                 u8 = (sc.build(seed=7 + v) * 255).to(torch.uint8).cpu().numpy().astype(int)
                 assert np.abs(u8 - views[i, v].astype(int)).mean() < 0.5, (i, v)
+
+
+def test_chain_program_matches_torch_path(cuda):
+    """Native parameter->matrix chain (rrt_chain_forward/backward) == the torch-op
+    evaluation of the same Transform expressions, values and gradients."""
+    from reversible_raytracer_b200.chain import ChainProgram
+    rng = np.random.RandomState(0)
+    c = torch.tensor(rng.normal(size=3), dtype=torch.float32, device=cuda, requires_grad=True)
+    sc_ = torch.tensor(rng.uniform(0.5, 2, 3), dtype=torch.float32, device=cuda, requires_grad=True)
+    ang = torch.tensor(37.0, device=cuda, requires_grad=True)
+    axis = torch.tensor([0.6, 0.0, 0.8], device=cuda, requires_grad=True)
+    p6 = torch.tensor([0.1, -0.2, 3.0, 0.5, 0.6, 0.7], device=cuda, requires_grad=True)
+    ts = [
+        (translate(c) * rotate(ang, axis) * scale(sc_)).inverse(),
+        (translate(p6[:3]) * scale(p6[3:])).inverse(),
+        translate((1, 2, 3)) * rotate(90, (0, 0, 1)),
+        (translate(c) * scale((4., 4., 4.))).inverse(),
+        T.identity(),
+        (rotate(ang, (0, 1, 0)) * translate(c)).inverse().inverse(),
+    ]
+    prog = ChainProgram(ts, cuda)
+    out = prog.evaluate()
+    ref = torch.stack([t.m[:3, :].reshape(12) for t in ts])
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().cpu().numpy(), rtol=1e-5, atol=1e-6)
+    w = torch.tensor(rng.normal(size=(len(ts), 12)), dtype=torch.float32, device=cuda)
+    leaves = [c, sc_, ang, axis, p6]
+    g1 = torch.autograd.grad((out * w).sum(), leaves)
+    g2 = torch.autograd.grad((ref * w).sum(), leaves)
+    for a, b in zip(g1, g2):
+        assert block_rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-4
+    # exact zeros survive (diagonal fast path keys on them)
+    A = out[3].reshape(3, 4)[:, :3]
+    assert torch.count_nonzero(A - torch.diag(torch.diag(A))) == 0
+
+
+def test_graph_captured_optimizer_matches_eager(cuda):
+    def run(graph):
+        sc, c1, c2 = _c1(cuda)
+        sc._jitter_for(128, 4, None, 21, cuda)
+
+        def loss():
+            im = sc.build()
+            return -im[90, 85].sum() - im[50, 90].sum()
+        train = GDOptimizer().optimize([c1, c2], loss, graph=graph)
+        vals = [train(0.0008) for _ in range(6)]
+        return vals, c1.detach().cpu().numpy(), c2.detach().cpu().numpy(), train.state
+    v_e, a_e, b_e, _ = run(False)
+    v_g, a_g, b_g, st = run('auto')
+    assert st['graph'] is not None and not st['failed']      # steps 3.. are graph replays
+    np.testing.assert_allclose(v_g, v_e, rtol=1e-5)
+    np.testing.assert_allclose(a_g, a_e, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(b_g, b_e, rtol=1e-5, atol=1e-6)

@@ -1,0 +1,75 @@
+"""Optimise-step latency of the small reference configs (C1, C3) and throughput of the
+batched autoencoder decoder workload (C4) -- exploration / reporting helper."""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from reversible_raytracer_b200 import render as R, workloads as W  # noqa: E402
+from reversible_raytracer_b200.optimize import GDOptimizer  # noqa: E402
+from reversible_raytracer_b200.scene import *  # noqa: E402,F401,F403
+from reversible_raytracer_b200.shader import *  # noqa: E402,F401,F403
+
+
+def timeit(fn, warm=5, iters=50):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / iters * 1e6
+
+
+def c1():
+    c1 = torch.tensor([-.5, -.5, 4.], device='cuda')
+    c2 = torch.tensor([.5, .5, 4.], device='cuda')
+    m1 = Material((0.2, 0.9, 0.4), 0.3, 0.7, 0.5, 50.)
+    m2 = Material((0.87, 0.1, 0.507), 0.3, 0.9, 0.4, 50.)
+    shapes = [Sphere(translate(c1), m1), Sphere(translate(c2) * rotate(90, (0, 0, 1)) * scale((1, 2, 1.5)), m2)]
+    sc = Scene(shapes, [Light((-1., -1., 2.), (0.961, 1., 0.87))], Camera(128, 128), PhongShader())
+
+    def loss():
+        im = sc.build()
+        return -im[90, 85].sum() - im[50, 90].sum()
+    train = GDOptimizer().optimize([c1, c2], loss, 0.0008, 0.1)
+    return train, sc
+
+
+def c3(fused):
+    c1 = torch.tensor([-.5, -.5, 4.], device='cuda')
+    c2 = torch.tensor([.5, .5, 4.], device='cuda')
+    m1 = Material((0.2, 0.9, 0.4), 0.3, 0.7, 0.5, 50.)
+    m2 = Material((0.87, 0.1, 0.507), 0.3, 0.9, 0.4, 50.)
+    objs = [Sphere(translate(c1), m1), Sphere(translate(c2), m2), Square(translate((0, 0, 3)) * rotate(50, [0., 1., 0.]), m2)]
+    sc = Scene(objs, [Light((-1., -1., 2.), (1., 0.87, 0.961))], Camera(128, 128), PhongShader())
+    flipped = torch.flip(sc.build().detach(), dims=[1])
+    cost = (lambda: sc.build_mse(flipped)) if fused else (lambda: ((sc.build() - flipped) ** 2).sum())
+    return GDOptimizer().optimize([c1, c2], cost, 0.000008, 0.1), sc
+
+
+def c4(num_scenes=256):
+    tb = W.orbit_tables(num_scenes)
+    tt = W.orbit_tables(num_scenes, centre_noise=0.5)
+    dev = torch.device('cuda')
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    cfg = R.RenderConfig(n=64, samples=4, shader=tb['shader'], transpose=0, seed=7, camera_grad=0)
+    args = (t(tb['obj_type']), t(tb['w2o']), t(tb['material']), t(tb['light']), t(tb['camera']))
+    target, _, _ = R.render_forward(cfg, args[0], t(tt['w2o']), *args[2:], None, want_hit=False)
+    return lambda: R.render_fused_mse(cfg, *args, target), 2 * num_scenes * 64 * 64 * 4
+
+
+if __name__ == '__main__':
+    train, sc = c1()
+    print('C1 optimize_brightness step: %.1f us' % timeit(train))
+    print('C1 render only (scene.build): %.1f us' % timeit(lambda: sc.build()))
+    for fused in (False, True):
+        train, sc = c3(fused)
+        print('C3 match_mirror step (fused=%s): %.1f us' % (fused, timeit(train)))
+    fn, rays = c4()
+    us = timeit(fn, iters=100)
+    print('C4 orbit batch 256x2 fused fwd+mse+bwd: %.1f us  -> %.0f Mrays/s' % (us, rays / us))
