@@ -41,6 +41,7 @@ def parse():
     ap.add_argument('--samples', type=int, default=4)
     ap.add_argument('--general', action='store_true', help='C5g: rotated, non-uniformly scaled spheres')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the other BASELINE configs (C1/C3 step latency, C4, C5g)')
     ap.add_argument('--miss', action='store_true', help='diagnostic: move every sphere out of view (pure sweep, no hits)')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     return ap.parse_args()
@@ -141,6 +142,45 @@ class ClockSampler(threading.Thread):
     def summary(self):
         med = float(np.median(self.samples)) if self.samples else None
         return dict(sm_mhz=med, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons))
+
+
+# ------------------------------------------------------------------ the other BASELINE configs
+def other_configs(dev):
+    """Optimise-step latency of the reference's own small configs (C1 optimize_brightness.py,
+    C3 match_mirror.py: 128x128, S=4) through the drop-in API + GDOptimizer (CUDA-graph
+    replayed step incl. the device->host read of the loss), throughput of the batched
+    autoencoder decoder workload C4 (256 scenes x 2 views, 64x64, S=4, fused fwd+mse+bwd),
+    and C5g (general affine spheres) / C5 forward-only for the record."""
+    import torch
+    from reversible_raytracer_b200 import render as R, workloads as W, _native as nat
+    from tools import latency as L
+    out = {}
+    train, _ = L.c1()
+    out['C1_optimize_brightness_step_us'] = round(L.timeit(train, warm=6, iters=100), 1)
+    train, _ = L.c3(False)
+    out['C3_match_mirror_step_us'] = round(L.timeit(train, warm=6, iters=100), 1)
+    train, _ = L.c3(True)
+    out['C3_match_mirror_fused_step_us'] = round(L.timeit(train, warm=6, iters=100), 1)
+    fn, rays = L.c4(256)
+    us = L.timeit(fn, warm=5, iters=100)
+    out['C4_orbit_256x2_fused'] = dict(us_per_batch=round(us, 1), Mrays_s=round(rays / us, 1))
+
+    def stress(general, fwd_only, samples=4, n=4096, N=1024, iters=3):
+        tb = W.stress_tables(N, general=general)
+        t = lambda a: torch.from_numpy(a).to(dev)
+        cfg = R.RenderConfig(n=n, samples=samples, shader=nat.SHADER_PHONG, transpose=1, seed=4321)
+        args = (t(tb['obj_type']), t(tb['w2o']), t(tb['material']), t(tb['light']), t(tb['camera']))
+        target, _, _ = R.render_forward(cfg, *args, None, want_hit=False)
+        fn = (lambda: R.render_forward(cfg, *args, None, want_hit=False)) if fwd_only else \
+             (lambda: R.render_fused_mse(cfg, *args, target, want_image=True))
+        us = L.timeit(fn, warm=2, iters=iters)
+        return dict(ms=round(us / 1e3, 3), Mrays_s=round(n * n * samples / us, 1))
+    out['C5_forward_only'] = stress(False, True)
+    out['C5_S1_fused'] = stress(False, False, samples=1)
+    g = stress(True, False)
+    g['frac_fp32_peak_28flop_per_test'] = None
+    out['C5g_general_affine_fused'] = g
+    return out
 
 
 # ------------------------------------------------------------------ GPU leg
@@ -294,6 +334,16 @@ def run_b200(args):
                    gpu_launches=2 * args.steps, clocks=sampler.summary())
         if roof is not None:
             out['roofline'] = roof
+        if world == 1 and not args.no_extras:
+            try:
+                oc_ = other_configs(dev)
+                g_ = oc_.get('C5g_general_affine_fused')
+                if g_ and roof is not None:
+                    g_['frac_fp32_peak_28flop_per_test'] = round(
+                        (rays * N * 28) / (g_['ms'] * 1e-3) / 1e12 / roof['peak'], 4)
+                out['other_configs'] = oc_
+            except Exception as e:          # extras must never take the headline down
+                out['other_configs'] = {'error': repr(e)}
         if cpu is not None:
             out['cpu_baseline'] = cpu
         print(json.dumps(out))

@@ -1,0 +1,64 @@
+"""Batched B200 port of the orbit autoencoder experiment
+(orbit_experiments/autoencoder_2ly.py + test_optimization.py): a small MLP encoder
+maps each camera view to a sphere centre; the DECODER is the differentiable ray
+tracer; cost = sum of squared errors of both views (autoencoder_2ly.py:87-91).
+
+The reference trains one scene pair per compiled call ("TODO remake it for batch",
+autoencoder_2ly.py:116); here a whole batch of scene pairs is one fused
+forward + loss + reverse-pass kernel launch, and the encoder is stock PyTorch.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from reversible_raytracer_b200 import render as R, workloads as W  # noqa: E402
+
+
+class Encoder(torch.nn.Module):
+    """autoencoder_2ly.py:62-80: tanh(X W0 + b) -> tanh(. W1 + b) -> centre = h2 Cw + cbias, relu on z."""
+
+    def __init__(self, n_visible, h1=600, h2=30):
+        super().__init__()
+        self.l1, self.l2, self.cap = torch.nn.Linear(n_visible, h1), torch.nn.Linear(h1, h2), torch.nn.Linear(h2, 3)
+        with torch.no_grad():
+            self.cap.weight.mul_(0.05)
+            self.cap.bias.copy_(torch.tensor([0., 0., 32.]))
+
+    def forward(self, x):
+        c = self.cap(torch.tanh(self.l2(torch.tanh(self.l1(x)))))
+        return torch.cat([c[..., :2], torch.relu(c[..., 2:])], dim=-1)
+
+
+def main(num_scenes=256, steps=30, lr=2e-8, n=64, seed=1234, verbose=True):
+    dev = torch.device('cuda')
+    tb = W.orbit_tables(num_scenes, seed=seed)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    cfg = R.RenderConfig(n=n, samples=4, shader=tb['shader'], transpose=0, seed=11)
+    obj_type, material, light, camera = t(tb['obj_type']), t(tb['material']), t(tb['light']), t(tb['camera'])
+    B = 2 * num_scenes
+    # data: the scenes rendered at their true centres (planet_orbit.py), as uint8 like the dataset
+    X, _, _ = R.render_forward(cfg, obj_type, t(tb['w2o']), material, light, camera, None, want_hit=False)
+    X = (X * 255).to(torch.uint8).float() / 255.0                                        # [B,n,n,3]
+    enc = Encoder(n * n * 3).to(dev)
+    opt = torch.optim.SGD(enc.parameters(), lr=lr)
+    fixed = torch.tensor([0., 0., 48.], device=dev).expand(B, 3)
+    scales = torch.tensor([[4., 4., 4.], [6., 6., 6.]], device=dev).expand(B, 2, 3)
+    losses = []
+    for step in range(steps):
+        centres = enc(X.reshape(B, -1))                                                  # [B,3] (one per view)
+        w2o = R.w2o_translate_scale(torch.stack([centres, fixed], dim=1), scales)        # [B,2,12]
+        loss = R.render_fused_mse_loss(cfg, obj_type, w2o, material, light, camera, X).sum()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+        if verbose:
+            print('step %d cost %.3f' % (step, losses[-1]))
+    return losses
+
+
+if __name__ == '__main__':
+    main()

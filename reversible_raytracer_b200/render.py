@@ -199,6 +199,48 @@ def render(cfg, obj_type, w2o, material, light, camera, jitter=None):
     return _RenderFn.apply(w2o, material, light, camera, cfg, obj_type, jitter)
 
 
+def w2o_translate_scale(centres, scales):
+    """Batched, differentiable w2o rows of (translate(c) * scale(s)).inverse()
+    = scale(1/s) * translate(-c)  (transform.py:35-38, 60-93): [..., 3], [..., 3] -> [..., 12].
+    Off-diagonals are exact zeros (diagonal fast path of the kernels)."""
+    inv = 1.0 / scales
+    z = torch.zeros_like(inv[..., 0])
+    b = -centres * inv
+    rows = [inv[..., 0], z, z, b[..., 0], z, inv[..., 1], z, b[..., 1], z, z, inv[..., 2], b[..., 2]]
+    return torch.stack(rows, dim=-1)
+
+
+def render_fused_mse_loss(cfg, obj_type, w2o, material, light, camera, target, channel_weight=None, jitter=None):
+    """Differentiable scalar (or [B]) squared-error loss through the fused single-kernel
+    path: forward + loss + reverse pass run once; autograd just scales the stored gradient."""
+    return _FusedLossFn.apply(w2o, material, light, camera, cfg, obj_type, jitter, target, channel_weight)
+
+
+class _FusedLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w2o, material, light, camera, cfg, obj_type, jitter, target, channel_weight):
+        loss, grad, _, _ = render_fused_mse(cfg, obj_type, w2o, material, light, camera, target, channel_weight, jitter)
+        ctx.save_for_backward(grad)
+        ctx.N = w2o.shape[-2]
+        ctx.shapes = (w2o.shape, material.shape, light.shape, camera.shape)
+        return loss.float()
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        (grad,) = ctx.saved_tensors
+        g = grad * (g_loss.unsqueeze(-1) if g_loss.dim() > 0 else g_loss)
+        gw, gm, gl, gc = split_grad(g, ctx.N)
+        shp = ctx.shapes
+
+        def fit(t, shape):
+            while t.dim() > len(shape):
+                t = t.sum(0)
+            if t.shape != shape and t.dim() == len(shape) and shape[0] == 1 and t.shape[0] != 1:
+                t = t.sum(0, keepdim=True)
+            return t.reshape(shape)
+        return fit(gw, shp[0]), fit(gm, shp[1]), fit(gl, shp[2]), fit(gc, shp[3]), None, None, None, None, None
+
+
 def measure_fp32_peak(mode=1, iters=4096):
     """FP32 pipe micro-benchmark (TFLOP/s): mode 0 scalar FFMA, 1 packed FFMA2."""
     tf, ms = C.c_double(0), C.c_double(0)
