@@ -43,7 +43,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip the other BASELINE configs (C1/C3 step latency, C4, C5g)')
     ap.add_argument('--miss', action='store_true', help='diagnostic: move every sphere out of view (pure sweep, no hits)')
-    ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    ap.add_argument('--cpu-seconds', type=float, default=20.0)
     return ap.parse_args()
 
 
@@ -53,6 +53,7 @@ def cpu_fused_sample(args, rows, row_begin=None):
     threads).  The ONLY place bench.py executes anything under oracle/."""
     from oracle import oracle_c as oc
     from reversible_raytracer_b200 import workloads as W
+    oc.use_all_cores()                      # torchrun sets OMP_NUM_THREADS=1
     tb = W.stress_tables(args.objects, general=args.general)
     n, S = args.n, args.samples
     rb = (n // 2 - rows // 2) if row_begin is None else row_begin

@@ -523,6 +523,14 @@ float orc_rng_value(uint64_t seed, uint32_t scene, uint32_t pix, uint32_t s, uin
     return orc_rng(seed, scene, pix, s, axis);
 }
 
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

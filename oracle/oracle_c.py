@@ -56,6 +56,14 @@ def num_threads():
     return int(lib().orc_num_threads())
 
 
+def use_all_cores():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline legs want every core this
+    process may run on."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 

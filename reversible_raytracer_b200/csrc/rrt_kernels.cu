@@ -73,6 +73,7 @@ struct KParams {
     double lin_step;   // 1/(n-1): np.linspace step magnitude (0 when n == 1)
     float inv_s, inv_n; // exact reciprocals when S and n are powers of two
     int pow2;          // 1: (u+s)/S/n may be evaluated as exact multiplications
+    int vec_ok;        // 1: image/target rows are 16-byte aligned (n % 4 == 0, aligned base pointers)
 };
 
 // ---------------------------------------------------------------- packed f32x2
@@ -540,6 +541,7 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
     __shared__ float slots[kSlots * kSlotStride];
     __shared__ float gglob[9];
     __shared__ float loss_warp[kMaxWarps];
+    __shared__ __align__(16) float stage[kMaxWarps][32 * PIX * 3];   // per-warp tile-row staging (vector I/O)
     __shared__ int cam_identity_s;
     __shared__ int chunk_class;  // sticky per CTA: bit0 squares, bit1 general spheres seen
 
@@ -753,22 +755,71 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
         }
 
         const bool last_chunk = (sc0 == nchunks_s - 1);
-        // ---- pixel value, image store, loss and upstream gradient
+        // ---- pixel value, image store, loss and upstream gradient.  A full, aligned tile row
+        // (32*PIX pixels = 96*PIX contiguous floats per warp) moves through a per-warp
+        // shared-memory stage so that global traffic is coalesced 16-byte vectors
+        // (LDG.128 / STG.128, streaming); ragged tiles use scalar accesses.
         if (MODE != MODE_BWD && last_chunk) {
+            const float inv = 1.0f / (float)S;
+            const bool vec = P.vec_ok && row_ok && (blockIdx.x * 32 + 32) * PIX <= n;   // warp-uniform
+            const size_t row_off = (((size_t)scene * P.rows + al) * n + (size_t)blockIdx.x * 32 * PIX) * 3;
+            float* st = stage[warp];
+            constexpr int kVec = 32 * PIX * 3 / 4;
+            float tg[PIX][3];
+            if (MODE == MODE_FUSED) {
+                if (vec) {
+                    const float4* g4 = reinterpret_cast<const float4*>(P.target + row_off);
+                    for (int j = lane; j < kVec; j += 32) reinterpret_cast<float4*>(st)[j] = __ldcs(g4 + j);
+                    __syncwarp();
+#pragma unroll
+                    for (int px = 0; px < PIX; px++)
+#pragma unroll
+                        for (int c = 0; c < 3; c++) tg[px][c] = st[(lane * PIX + px) * 3 + c];
+                    __syncwarp();
+                } else {
+#pragma unroll
+                    for (int px = 0; px < PIX; px++) {
+                        const int b = b0 + px;
+                        const bool ok = row_ok && b < n;
+                        const size_t po = (((size_t)scene * P.rows + al) * n + b) * 3;
+#pragma unroll
+                        for (int c = 0; c < 3; c++) tg[px][c] = ok ? __ldcs(P.target + po + c) : 0.f;
+                    }
+                }
+            }
+            float v[PIX][3];
 #pragma unroll
             for (int px = 0; px < PIX; px++) {
                 const int b = b0 + px;
-                if (!(row_ok && b < n)) continue;
-                size_t po = (((size_t)scene * P.rows + al) * n + b) * 3;
-                float inv = 1.0f / (float)S;
-                float v0 = pixsum[px][0] * inv, v1 = pixsum[px][1] * inv, v2 = pixsum[px][2] * inv;  // scene.py:49-50
-                if (P.image) { __stcs(P.image + po, v0); __stcs(P.image + po + 1, v1); __stcs(P.image + po + 2, v2); }
-                if (MODE == MODE_FUSED) {
-                    float d0 = v0 - __ldcs(P.target + po), d1 = v1 - __ldcs(P.target + po + 1), d2 = v2 - __ldcs(P.target + po + 2);
+                const bool ok = row_ok && b < n;
+#pragma unroll
+                for (int c = 0; c < 3; c++) v[px][c] = pixsum[px][c] * inv;             // scene.py:49-50
+                if (MODE == MODE_FUSED && ok) {
+                    const float d0 = v[px][0] - tg[px][0], d1 = v[px][1] - tg[px][1], d2 = v[px][2] - tg[px][2];
                     loss_part += P.cw[0] * d0 * d0 + P.cw[1] * d1 * d1 + P.cw[2] * d2 * d2;
                     gpix[px][0] = 2.0f * P.cw[0] * d0 * inv;
                     gpix[px][1] = 2.0f * P.cw[1] * d1 * inv;
                     gpix[px][2] = 2.0f * P.cw[2] * d2 * inv;
+                }
+            }
+            if (P.image) {
+                if (vec) {
+#pragma unroll
+                    for (int px = 0; px < PIX; px++)
+#pragma unroll
+                        for (int c = 0; c < 3; c++) st[(lane * PIX + px) * 3 + c] = v[px][c];
+                    __syncwarp();
+                    float4* g4 = reinterpret_cast<float4*>(P.image + row_off);
+                    for (int j = lane; j < kVec; j += 32) __stcs(g4 + j, reinterpret_cast<const float4*>(st)[j]);
+                    __syncwarp();
+                } else {
+#pragma unroll
+                    for (int px = 0; px < PIX; px++) {
+                        const int b = b0 + px;
+                        if (!(row_ok && b < n)) continue;
+                        const size_t po = (((size_t)scene * P.rows + al) * n + b) * 3;
+                        __stcs(P.image + po, v[px][0]); __stcs(P.image + po + 1, v[px][1]); __stcs(P.image + po + 2, v[px][2]);
+                    }
                 }
             }
         }
@@ -1166,6 +1217,7 @@ int launch(KParams& P, cudaStream_t st) {
     P.inv_s = 1.0f / (float)sc.samples;
     P.inv_n = 1.0f / (float)sc.n;
     P.pow2 = ((sc.samples & (sc.samples - 1)) == 0) && ((sc.n & (sc.n - 1)) == 0);
+    P.vec_ok = (sc.n % 4 == 0) && (((uintptr_t)P.image & 15) == 0) && (((uintptr_t)P.target & 15) == 0);
     const int S = sc.samples;
     int pix;
     if (S == 1) pix = 8; else if (S == 2) pix = 4; else if (S == 4) pix = 2; else pix = 1;
