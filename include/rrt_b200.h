@@ -109,6 +109,13 @@ typedef struct rrt_scene {
     int64_t light_scene_stride;
     int64_t camera_scene_stride;
     int64_t jitter_scene_stride;
+
+    /* Optional [n][n][3] float32 table of the camera-space ray grid BEFORE jitter, in
+     * the reference's ray index space (value of Camera.make_rays without sampleDist,
+     * scene.py:66-72), as filled by rrt_primary_rays().  NULL => the kernels evaluate
+     * the float64 grid themselves.  Same bits either way; the table only saves the
+     * float64 divide/sqrt chains per pixel (small images, batches of scenes).          */
+    const float* base_rays;
 } rrt_scene;
 
 int rrt_version(void);
@@ -150,6 +157,13 @@ int rrt_render_backward(const rrt_scene* scene, const float* dl_dimage,
 int rrt_render_fused_mse(const rrt_scene* scene, const float* target,
                          const float* channel_weight, float* image, int32_t* hit_index,
                          double* loss, float* grad, void* stream);
+
+/*
+ * Camera.make_rays grid (scene.py:66-72: float64 linspace / normalise, cast to float32),
+ * without jitter: out[i][j][0..2] for the reference's ray indices (i, j).  Fills the
+ * optional rrt_scene.base_rays table.
+ */
+int rrt_primary_rays(int n, float* out, void* stream);
 
 /*
  * Parameter -> matrix chain.  Replaces the symbolic transform algebra that feeds the

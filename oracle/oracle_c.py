@@ -27,7 +27,7 @@ class RrtScene(C.Structure):
         ('jitter_x', C.c_void_p), ('jitter_y', C.c_void_p),
         ('w2o_scene_stride', C.c_int64), ('material_scene_stride', C.c_int64),
         ('light_scene_stride', C.c_int64), ('camera_scene_stride', C.c_int64),
-        ('jitter_scene_stride', C.c_int64),
+        ('jitter_scene_stride', C.c_int64), ('base_rays', C.c_void_p),
     ]
 
 

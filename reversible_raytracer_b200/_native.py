@@ -38,7 +38,7 @@ class RrtScene(C.Structure):
         ('jitter_x', C.c_void_p), ('jitter_y', C.c_void_p),
         ('w2o_scene_stride', C.c_int64), ('material_scene_stride', C.c_int64),
         ('light_scene_stride', C.c_int64), ('camera_scene_stride', C.c_int64),
-        ('jitter_scene_stride', C.c_int64),
+        ('jitter_scene_stride', C.c_int64), ('base_rays', C.c_void_p),
     ]
 
 
@@ -76,18 +76,19 @@ def lib():
         L.rrt_render_forward.argtypes = [C.POINTER(RrtScene), P, P, P, P]
         L.rrt_render_backward.argtypes = [C.POINTER(RrtScene), P, P, P, P]
         L.rrt_render_fused_mse.argtypes = [C.POINTER(RrtScene), P, C.POINTER(C.c_float), P, P, P, P, P]
+        L.rrt_primary_rays.argtypes = [C.c_int, P, P]
         L.rrt_chain_forward.argtypes = [P, P, C.c_int, P, P, P]
         L.rrt_chain_backward.argtypes = [P, P, C.c_int, P, P, P, C.c_int, P]
         L.rrt_measure_fp32_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), P]
         for f in (L.rrt_render_forward, L.rrt_render_backward, L.rrt_render_fused_mse, L.rrt_measure_fp32_peak,
-                  L.rrt_chain_forward, L.rrt_chain_backward):
+                  L.rrt_chain_forward, L.rrt_chain_backward, L.rrt_primary_rays):
             f.restype = C.c_int
         _lib = L
     return _lib
 
 
 EXPORTS = ['rrt_version', 'rrt_last_error', 'rrt_render_forward', 'rrt_render_backward',
-           'rrt_render_fused_mse', 'rrt_measure_fp32_peak', 'rrt_chain_forward', 'rrt_chain_backward']
+           'rrt_render_fused_mse', 'rrt_measure_fp32_peak', 'rrt_chain_forward', 'rrt_chain_backward', 'rrt_primary_rays']
 
 CHAIN_TRANSLATE, CHAIN_SCALE, CHAIN_ROTATE, CHAIN_INVERT, CHAIN_MAX_OPS = 1, 2, 3, 0x100, 8
 

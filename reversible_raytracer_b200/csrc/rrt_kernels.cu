@@ -291,11 +291,19 @@ constexpr int kGroup = RRT_GROUP;  // objects per branch in the hot loop
 
 // max over the 8 dets of one object, folded into the running group max (FMNMX3 chain;
 // fmaxf drops NaN, and NaN is a miss: shape.py:124-125)
+// LDS.128 from a 32-bit shared-window address: keeps the hot loop free of the
+// generic->shared address arithmetic (S2UR/ULEA per iteration) a float4* would cost.
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+
 template <bool GENERAL>
-__device__ __forceinline__ float object_max_det(const float4* __restrict__ rec, const RayPack& rp, float gmax) {
-    float4 q0 = rec[0], q1 = rec[1];
+__device__ __forceinline__ float object_max_det(uint32_t rec, const RayPack& rp, float gmax) {
+    float4 q0 = lds128(rec), q1 = lds128(rec + 16);
     float4 q2 = q0, q3 = q0;
-    if (GENERAL) { q2 = rec[2]; q3 = rec[3]; }
+    if (GENERAL) { q2 = lds128(rec + 32); q3 = lds128(rec + 48); }
 #pragma unroll
     for (int p = 0; p < kRays / 2; p++) {
         float lo, hi;
@@ -315,11 +323,12 @@ template <bool GENERAL>
 __device__ __forceinline__ void sweep_spheres(const float4* __restrict__ tab, int count, int kbase, const RayPack& rp,
                                               const float* dw, float* tmin, int* idx) {
     int k = 0;
+    uint32_t rec = (uint32_t)__cvta_generic_to_shared(tab);
 #pragma unroll 1
-    for (; k + kGroup <= count; k += kGroup) {
+    for (; k + kGroup <= count; k += kGroup, rec += 64 * kGroup) {
         float gmax = 0.0f;
 #pragma unroll
-        for (int j = 0; j < kGroup; j++) gmax = object_max_det<GENERAL>(tab + 4 * (k + j), rp, gmax);
+        for (int j = 0; j < kGroup; j++) gmax = object_max_det<GENERAL>(rec + 64 * j, rp, gmax);
         if (__builtin_expect(gmax > 0.0f, 0)) rare_group(tab, k, kGroup, kbase, dw, tmin, idx);
     }
     if (k < count) rare_group(tab, k, count - k, kbase, dw, tmin, idx);
@@ -333,7 +342,7 @@ __device__ __forceinline__ void sweep_mixed(const float4* __restrict__ tab, int 
     for (int k = 0; k < count; k++) {
         const int flags = __float_as_int(tab[4 * k + 1].w);
         float gmax = 1.0f;
-        if (!(flags & 1)) gmax = object_max_det<true>(tab + 4 * k, rp, 0.0f);
+        if (!(flags & 1)) gmax = object_max_det<true>((uint32_t)__cvta_generic_to_shared(tab + 4 * k), rp, 0.0f);
         if (gmax > 0.0f) rare_group(tab, k, 1, kbase, dw, tmin, idx);
     }
 }
@@ -342,6 +351,8 @@ __device__ __forceinline__ void sweep_mixed(const float4* __restrict__ tab, int 
 // x ** y like C pow() (Theano's T.pow, shader.py:45): integer-valued exponents up to
 // 1024 (shininess = 50 in every reference script) take square-and-multiply -- a
 // negative base is fine there, as in pow(); everything else goes to powf.
+__device__ __noinline__ float powf_general(float x, float y) { return powf(x, y); }
+
 __device__ __forceinline__ float pow_shininess(float x, float y) {
     const int e = (int)y;
     if ((float)e == y && e >= 0 && e <= 1024) {
@@ -355,7 +366,7 @@ __device__ __forceinline__ float pow_shininess(float x, float y) {
         }
         return r;
     }
-    return powf(x, y);
+    return powf_general(x, y);
 }
 
 
@@ -597,7 +608,14 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
     for (int px = 0; px < PIX; px++) {
         int b = b0 + px;
         int i = sc.transpose ? b : a, j = sc.transpose ? a : b;
-        if (row_ok && b < n) base_ray(n, P.lin_step, i, j, bx[px], by[px], bz[px]);
+        if (row_ok && b < n) {
+            if (sc.base_rays) {       // precomputed grid (rrt_primary_rays): same bits, no float64 chain
+                const float* br = sc.base_rays + ((size_t)i * n + j) * 3;
+                bx[px] = __ldg(br); by[px] = __ldg(br + 1); bz[px] = __ldg(br + 2);
+            } else {
+                base_ray(n, P.lin_step, i, j, bx[px], by[px], bz[px]);
+            }
+        }
         else { bx[px] = by[px] = bz[px] = 0.f; }
     }
 
@@ -638,56 +656,58 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
         __align__(16) float l_rc[3 * kRays], l_dw[3 * kRays], l_tmin[kRays];  // SoA: [x0..x7 | y0..y7 | z0..z7]
         int l_idx[kRays];
         RayPack rp;
-        {
-            float wx[kRays], wy[kRays], wz[kRays];
-#pragma unroll
-            for (int r = 0; r < kRays; r++) {
-                const int px = r / SPT, sl = r % SPT;
-                const int s = sc0 * SPT + sl;
-                const int b = b0 + px;
-                const bool ok = row_ok && b < n && s < S;
-                float jx = 0.f, jy = 0.f;
-                float rcx = 0.f, rcy = 0.f, rcz = 0.f;
-                wx[r] = wy[r] = wz[r] = 0.f;  // zero direction never hits (det == 0)
-                if (ok) {
-                    if (sc.jitter_x) {
-                        size_t off = (size_t)scene * sc.jitter_scene_stride + ((size_t)al * n + b) * S + s;
-                        jx = __ldg(sc.jitter_x + off);
-                        jy = __ldg(sc.jitter_y + off);
-                    } else {
-                        jx = rrt_rng(sc.seed, scene, (uint32_t)(a * n + b), s, 0);
-                        jy = rrt_rng(sc.seed, scene, (uint32_t)(a * n + b), s, 1);
-                    }
-                    const float ox = P.pow2 ? jitter_offset_pow2(jx, s, P.inv_s, P.inv_n) : jitter_offset(jx, s, S, n);
-                    const float oy = P.pow2 ? jitter_offset_pow2(jy, s, P.inv_s, P.inv_n) : jitter_offset(jy, s, S, n);
-                    rcx = __fadd_rn(bx[px], ox);
-                    rcy = __fadd_rn(by[px], oy);
-                    rcz = bz[px];
-                    if (cam_identity) {     // root variant: C = I, the fma chain returns its input
-                        wx[r] = rcx; wy[r] = rcy; wz[r] = rcz;
-                    } else {                // camera.o2w, orbit_experiments/scene.py:80
-                        wx[r] = dot3_canon(g.C[0], g.C[1], g.C[2], rcx, rcy, rcz);
-                        wy[r] = dot3_canon(g.C[3], g.C[4], g.C[5], rcx, rcy, rcz);
-                        wz[r] = dot3_canon(g.C[6], g.C[7], g.C[8], rcx, rcy, rcz);
-                    }
+        // rolled on purpose (code size: this runs once per thread; instruction-cache misses
+        // dominate small-scene workloads otherwise)
+#pragma unroll 1
+        for (int r = 0; r < kRays; r++) {
+            const int px = r / SPT, sl = r % SPT;
+            const int s = sc0 * SPT + sl;
+            const int b = b0 + px;
+            const bool ok = row_ok && b < n && s < S;
+            float rcx = 0.f, rcy = 0.f, rcz = 0.f;
+            float wx = 0.f, wy = 0.f, wz = 0.f;   // zero direction never hits (det == 0)
+            if (ok) {
+                float jx, jy;
+                if (sc.jitter_x) {
+                    size_t off = (size_t)scene * sc.jitter_scene_stride + ((size_t)al * n + b) * S + s;
+                    jx = __ldg(sc.jitter_x + off);
+                    jy = __ldg(sc.jitter_y + off);
+                } else {
+                    jx = rrt_rng(sc.seed, scene, (uint32_t)(a * n + b), s, 0);
+                    jy = rrt_rng(sc.seed, scene, (uint32_t)(a * n + b), s, 1);
                 }
-                l_rc[r] = rcx; l_rc[kRays + r] = rcy; l_rc[2 * kRays + r] = rcz;
-                l_dw[r] = wx[r]; l_dw[kRays + r] = wy[r]; l_dw[2 * kRays + r] = wz[r];
-                l_tmin[r] = __int_as_float(0x7f800000);
-                l_idx[r] = -1;
-            }
+                const float ox = P.pow2 ? jitter_offset_pow2(jx, s, P.inv_s, P.inv_n) : jitter_offset(jx, s, S, n);
+                const float oy = P.pow2 ? jitter_offset_pow2(jy, s, P.inv_s, P.inv_n) : jitter_offset(jy, s, S, n);
+                float bxv = 0.f, byv = 0.f, bzv = 0.f;
 #pragma unroll
-            for (int p = 0; p < kRays / 2; p++) {
-                rp.dx[p] = pk(wx[2 * p], wx[2 * p + 1]);
-                rp.dy[p] = pk(wy[2 * p], wy[2 * p + 1]);
-                rp.dz[p] = pk(wz[2 * p], wz[2 * p + 1]);
+                for (int q = 0; q < PIX; q++)
+                    if (q == px) { bxv = bx[q]; byv = by[q]; bzv = bz[q]; }
+                rcx = __fadd_rn(bxv, ox);
+                rcy = __fadd_rn(byv, oy);
+                rcz = bzv;
+                if (cam_identity) {     // root variant: C = I, the fma chain returns its input
+                    wx = rcx; wy = rcy; wz = rcz;
+                } else {                // camera.o2w, orbit_experiments/scene.py:80
+                    wx = dot3_canon(g.C[0], g.C[1], g.C[2], rcx, rcy, rcz);
+                    wy = dot3_canon(g.C[3], g.C[4], g.C[5], rcx, rcy, rcz);
+                    wz = dot3_canon(g.C[6], g.C[7], g.C[8], rcx, rcy, rcz);
+                }
             }
+            l_rc[r] = rcx; l_rc[kRays + r] = rcy; l_rc[2 * kRays + r] = rcz;
+            l_dw[r] = wx; l_dw[kRays + r] = wy; l_dw[2 * kRays + r] = wz;
+            l_tmin[r] = __int_as_float(0x7f800000);
+            l_idx[r] = -1;
+        }
+        {
+            const u64* dp = reinterpret_cast<const u64*>(l_dw);   // (x0,x1) (x2,x3) ... pairs
+#pragma unroll
+            for (int p = 0; p < kRays / 2; p++) { rp.dx[p] = dp[p]; rp.dy[p] = dp[kRays / 2 + p]; rp.dz[p] = dp[kRays + p]; }
         }
 
         // ---- nearest-hit sweep (or stored winners)
         const bool use_stored = (MODE == MODE_BWD) && (P.hit_in != nullptr);
         if (use_stored) {
-#pragma unroll
+#pragma unroll 1
             for (int r = 0; r < kRays; r++) {
                 const int px = r / SPT, s = sc0 * SPT + r % SPT, b = b0 + px;
                 if (row_ok && b < n && s < S)
@@ -717,8 +737,8 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
         }
 
         // ---- outputs of the sweep
-        if (MODE != MODE_BWD) {
-#pragma unroll
+        if (MODE != MODE_BWD && (P.hit_out || P.tmin_out)) {
+#pragma unroll 1
             for (int r = 0; r < kRays; r++) {
                 const int px = r / SPT, s = sc0 * SPT + r % SPT, b = b0 + px;
                 if (row_ok && b < n && s < S) {
@@ -826,15 +846,19 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
 
         // ---- reverse pass over the winners
         if (MODE != MODE_FWD) {
+            // one extra (sentinel) trip after the last ray of the last sample chunk flushes the
+            // running accumulator, so the warp-level flush code exists exactly once
 #pragma unroll 1
-            for (int r = 0; r < kRays; r++) {
-                int k = l_idx[r];
+            for (int r = 0; r <= kRays; r++) {
+                const bool fin = (r == kRays);
+                if (fin && !last_chunk) break;
+                int k = fin ? -1 : l_idx[r];
                 HitRec h;
                 Obj ob;
                 float m7[7];
                 float dwx = 0.f, dwy = 0.f, dwz = 0.f;
                 float gc[3] = {0.f, 0.f, 0.f};
-                {
+                if (!fin) {
                     const int px = r / SPT;
 #pragma unroll
                     for (int q = 0; q < PIX; q++)
@@ -850,7 +874,7 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                     if (!(h.t < __int_as_float(0x7f800000))) k = -1;  // stale stored winner
                 }
                 // flush the running per-object accumulator when some lane changes object
-                const bool change = (k >= 0) && (acc_key >= 0) && (k != acc_key);
+                const bool change = fin ? (acc_key >= 0) : ((k >= 0) && (acc_key >= 0) && (k != acc_key));
                 if (__any_sync(0xffffffffu, change)) {
                     warp_flush(acc_key, acc, slot_key, slots, gobj, lane);
                     acc_key = -1;
@@ -873,8 +897,7 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
     }  // sample chunks
 
     if (MODE != MODE_FWD) {
-        // ---- warp -> CTA -> global reduction
-        warp_flush(acc_key, acc, slot_key, slots, gobj, lane);
+        // ---- warp -> CTA -> global reduction (per-object sums were flushed by the sentinel trip)
 #pragma unroll
         for (int v = 0; v < 9; v++) {
             float x = warp_sum(gg[v]);
@@ -903,6 +926,16 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
             if (t != 0.0) atomicAdd(&P.loss[scene], t);
         }
     }
+}
+
+// ---------------------------------------------------------------- primary-ray grid table
+__global__ void primary_rays_kernel(int n, double step, float* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= n) return;
+    float x, y, z;
+    base_ray(n, step, i, j, x, y, z);
+    float* o = out + ((size_t)i * n + j) * 3;
+    o[0] = x; o[1] = y; o[2] = z;
 }
 
 // ---------------------------------------------------------------- gradient finalisation
@@ -1316,6 +1349,14 @@ int rrt_render_fused_mse(const rrt_scene* scene, const float* target, const floa
     rc = launch<MODE_FUSED>(P, st);
     if (rc) return rc;
     return launch_finalize(P, st);
+}
+
+int rrt_primary_rays(int n, float* out, void* stream) {
+    if (n <= 0 || n > 65535 || !out) return fail(RRT_ERR_INVALID, "rrt_primary_rays: bad arguments");
+    primary_rays_kernel<<<dim3((n + 127) / 128, n), 128, 0, (cudaStream_t)stream>>>(n, n > 1 ? 1.0 / (double)(n - 1) : 0.0, out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "primary rays launch: %s", cudaGetErrorString(e));
+    return RRT_OK;
 }
 
 int rrt_chain_forward(const int32_t* ops, const int32_t* chain_begin, int num_chains, const float* values, float* out,

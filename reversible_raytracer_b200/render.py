@@ -45,6 +45,24 @@ def _f32(t, name):
     return t.contiguous()
 
 
+_BASE_RAYS = {}
+BASE_RAYS_MAX_N = 1024       # table = 12*n*n bytes; above this the kernels evaluate the grid themselves
+
+
+def base_rays(n, device):
+    """Cached [n,n,3] table of Camera.make_rays' grid (scene.py:66-72) for small images,
+    filled once per (n, device) by rrt_primary_rays."""
+    key = (int(n), str(device))
+    t = _BASE_RAYS.get(key)
+    if t is None:
+        with torch.cuda.device(device):
+            t = torch.empty((n, n, 3), dtype=torch.float32, device=device)
+            rc = nat.lib().rrt_primary_rays(int(n), t.data_ptr(), C.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+        nat.check(rc, 'rrt_primary_rays')
+        _BASE_RAYS[key] = t
+    return t
+
+
 class _Tables:
     """Packed device tables + the rrt_scene descriptor that points at them."""
 
@@ -56,7 +74,7 @@ class _Tables:
         self.B, self.N = int(w2o.shape[0]), int(w2o.shape[1])
         assert w2o.shape[2] == nat.W2O_STRIDE
         self.w2o = w2o
-        self.material = _f32(material, 'material').reshape(-1, self.N, nat.MAT_STRIDE)
+        self.material = _f32(material, 'material').reshape(-1 if self.N else 1, self.N, nat.MAT_STRIDE)
         self.light = _f32(light, 'light').reshape(-1, nat.LIGHT_STRIDE)
         self.camera = _f32(camera, 'camera').reshape(-1, nat.CAMERA_STRIDE)
         if not obj_type.is_cuda:
@@ -89,6 +107,10 @@ class _Tables:
             d.jitter_x, d.jitter_y = self.jx.data_ptr(), self.jy.data_ptr()
             per = cfg.rows * cfg.n * cfg.samples
             d.jitter_scene_stride = 0 if self.jx.numel() == per else per
+        self.base = None
+        if cfg.n <= BASE_RAYS_MAX_N:
+            self.base = base_rays(cfg.n, self.device)
+            d.base_rays = self.base.data_ptr()
         self.desc = d
 
     def stream(self):

@@ -157,3 +157,51 @@ def test_error_reporting(cuda):
         R.render_forward(bad, ot, w2o, mat, light, cam, None)
     with pytest.raises(nat.NativeError):
         R.render_forward(cfg, ot.cpu(), w2o.cpu(), mat.cpu(), light.cpu(), cam.cpu(), None)
+
+
+def test_ray_table_and_in_kernel_grid_agree_bitwise(cuda, monkeypatch):
+    """rrt_scene.base_rays (precomputed by rrt_primary_rays, used for n <= 1024) and the
+    in-kernel float64 grid give identical bits; both equal the oracle's rays."""
+    ps = oc.PackedScene.from_spec(scenes.stress(n=96, num_objects=30), camera_grad=0)
+    cfg, ot, w2o, mat, light, cam, jit = to_device(ps, cuda)
+    a = R.render_forward(cfg, ot, w2o, mat, light, cam, jit, want_hit=True, want_tmin=True)
+    monkeypatch.setattr(R, 'BASE_RAYS_MAX_N', 0)
+    b = R.render_forward(cfg, ot, w2o, mat, light, cam, jit, want_hit=True, want_tmin=True)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    tab = R.base_rays(96, cuda).cpu().numpy()
+    from oracle import oracle_numpy as on
+    _, ref = on.make_rays(96, 96)
+    assert np.array_equal(tab.view(np.uint32), ref.view(np.uint32))
+
+
+def test_full_resolution_row_slab(cuda):
+    """BASELINE's full image side (n = 4096, in-kernel ray grid, counter RNG) on a thin
+    row slab: masks bit-exact, pixels and gradients within tolerance."""
+    spec = scenes.stress(n=8, num_objects=64)        # tables only; n is overridden below
+    ps0 = oc.PackedScene.from_spec(spec, camera_grad=0, use_rng_seed=4321)
+    ps = oc.PackedScene(4096, 4, ps0.obj_type, ps0.w2o, ps0.material, ps0.light, ps0.camera, ps0.shader, 1,
+                        seed=4321, row_begin=2045, row_count=6)
+    img_o, hit_o, tmin_o = oc.render_forward(ps)
+    cfg, ot, w2o, mat, light, cam, _ = to_device(ps, cuda, with_jitter=False)
+    img, hit, tmin = R.render_forward(cfg, ot, w2o, mat, light, cam, None, want_hit=True, want_tmin=True)
+    assert np.array_equal(hit.cpu().numpy().reshape(hit_o.shape), hit_o)
+    assert np.array_equal(tmin.cpu().numpy().reshape(tmin_o.shape).view(np.uint32), tmin_o.view(np.uint32))
+    np.testing.assert_allclose(img.cpu().numpy().reshape(img_o.shape), img_o, rtol=PIX_RTOL, atol=PIX_ATOL)
+    target = np.zeros_like(img_o)
+    _, _, loss_o, grad_o = oc.render_fused_mse(ps, target)
+    loss, grad, _, _ = R.render_fused_mse(cfg, ot, w2o, mat, light, cam, torch.from_numpy(target[0]).to(cuda))
+    np.testing.assert_allclose(float(loss), loss_o[0], rtol=1e-4)
+    compare_grads(grad.cpu().numpy().astype(np.float64), grad_o[0], ps.N)
+
+
+def test_empty_scene(cuda):
+    cfg = R.RenderConfig(n=16, samples=4)
+    z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=cuda)
+    light = torch.tensor([-1., -1., 2., 1., 1., 1.], device=cuda)
+    cam = torch.tensor([1., 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 1], device=cuda)
+    img, hit, _ = R.render_forward(cfg, torch.zeros(0, dtype=torch.int32, device=cuda), z(0, 12), z(0, 7), light, cam, None)
+    assert float(img.abs().max()) == 0.0 and int((hit >= 0).sum()) == 0
+    loss, grad, _, _ = R.render_fused_mse(cfg, torch.zeros(0, dtype=torch.int32, device=cuda), z(0, 12), z(0, 7), light, cam,
+                                          torch.ones(16, 16, 3, device=cuda))
+    assert abs(float(loss) - 16 * 16 * 3) < 1e-3 and float(grad.abs().max()) == 0.0

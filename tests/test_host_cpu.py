@@ -160,13 +160,13 @@ def test_cabi_exports_and_struct_layout(tmp_path):
     # struct layout: ctypes mirror == what the C compiler sees
     src = tmp_path / 'sz.c'
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rrt_b200.h"\nint main(){printf("%zu %zu %zu %zu", sizeof(rrt_scene), '
-                   'offsetof(rrt_scene, seed), offsetof(rrt_scene, obj_type), offsetof(rrt_scene, jitter_scene_stride));return 0;}')
+                   'offsetof(rrt_scene, seed), offsetof(rrt_scene, obj_type), offsetof(rrt_scene, base_rays));return 0;}')
     exe = tmp_path / 'sz'
     subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), '-o', str(exe), str(src)])
     size, o_seed, o_obj, o_js = map(int, subprocess.check_output([str(exe)]).split())
     for S in (nat.RrtScene, oc.RrtScene):
         assert ctypes.sizeof(S) == size
-        assert (S.seed.offset, S.obj_type.offset, S.jitter_scene_stride.offset) == (o_seed, o_obj, o_js)
+        assert (S.seed.offset, S.obj_type.offset, S.base_rays.offset) == (o_seed, o_obj, o_js)
 
 
 def test_product_never_imports_oracle():
