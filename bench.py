@@ -313,7 +313,16 @@ def run_b200(args):
         if world == 1:
             peak_tf, _ = R.measure_fp32_peak(1, 4096)
             ach = flops / (ms_step * 1e-3) / 1e12
-            roof = dict(bound='fp32', achieved=ach, peak=peak_tf, unit='TFLOP/s', frac=ach / peak_tf, traffic=None,
+            traffic, traffic_src = None, None
+            try:
+                tj = json.load(open(os.path.join(ROOT, 'profiles', 'traffic_fused_c5.json')))
+                if (n, S, N, args.general) == (4096, 4, 1024, False):
+                    traffic = tj['dram_bytes_read'] + tj['dram_bytes_write']
+                    traffic_src = tj['source']
+            except Exception:
+                pass
+            roof = dict(bound='fp32', achieved=ach, peak=peak_tf, unit='TFLOP/s', frac=ach / peak_tf, traffic=traffic,
+                        traffic_unit='bytes per launch (dram read+write)', traffic_source=traffic_src,
                         kernel='render_kernel<2,4,FUSED>', algorithmic_flops=flops,
                         peak_source='measured in this run: packed FFMA2 micro-benchmark (rrt_measure_fp32_peak); '
                                     'MEASURED_PEAKS.json has no FP32 entry; theoretical 148*128*2*1.965 GHz = 74.45',
