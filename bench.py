@@ -226,10 +226,17 @@ def run_b200(args):
     G = nat.grad_size(N)
     red = torch.zeros(G + 2, dtype=torch.float64, device=dev)
 
+    kev = []
+
     def step():
+        if world > 1:
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
         loss, grad, _, _ = R.render_fused_mse(cfg, obj_type, d['w2o'], d['material'], d['light'], d['camera'], target,
                                                want_image=True)
         if world > 1:
+            k1.record()
+            kev.append((k0, k1))
             red[:G] = grad
             red[G] = loss
             dist.all_reduce(red)            # one NCCL allreduce: gradient vector + loss
@@ -239,12 +246,15 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.all_reduce(hit_rays)
-        dist.barrier()
+    # everything with host-side start-up cost (NVML init, event creation) happens BEFORE the
+    # barrier, so that all ranks enter the timed region together
     sampler = ClockSampler(local)
     sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        dist.all_reduce(hit_rays)
+        torch.cuda.synchronize()
+        dist.barrier()
     torch.cuda.synchronize()
     for k in range(args.steps):
         flush.fill_(k & 0xff)               # L2 flush between timed iterations (outside the timed intervals)
@@ -256,6 +266,12 @@ def run_b200(args):
         dist.barrier()
     sampler.stop_flag = True
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    kernel_ms = None
+    if world > 1:
+        km = torch.tensor([sum(a.elapsed_time(b) for a, b in kev[-args.steps:]) / args.steps], dtype=torch.float64, device=dev)
+        gathered = [torch.zeros_like(km) for _ in range(world)]
+        dist.all_gather(gathered, km)
+        kernel_ms = [round(float(x), 3) for x in gathered]
     tms = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -342,6 +358,9 @@ def run_b200(args):
                             note='scene-parameter tables uploaded from pinned host memory each step, loss + gradient '
                                  'vector read back; the target image stays resident like the reference\'s compiled-in constant'),
                    gpu_launches=2 * args.steps, clocks=sampler.summary())
+        if kernel_ms is not None:
+            out['rank0_step_ms'] = [round(a.elapsed_time(b), 3) for a, b in evs]
+            out['per_rank_render_ms'] = kernel_ms     # fused kernel + finalize per rank, before the allreduce
         if roof is not None:
             out['roofline'] = roof
         if world == 1 and not args.no_extras:

@@ -711,7 +711,10 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
             for (int r = 0; r < kRays; r++) {
                 const int px = r / SPT, s = sc0 * SPT + r % SPT, b = b0 + px;
                 if (row_ok && b < n && s < S)
-                    l_idx[r] = P.hit_in[(((size_t)scene * S + s) * P.rows + al) * n + b];
+{
+                    const int kk = P.hit_in[(((size_t)scene * S + s) * P.rows + al) * n + b];
+                    l_idx[r] = (kk >= 0 && kk < N) ? kk : -1;      // never trust an index buffer blindly
+                }
             }
         } else {
 #pragma unroll 1
