@@ -76,7 +76,27 @@ class Camera(object):
         self.w2o = self.o2w.inverse()
         self.look_at = as_tensor(np.asarray([0, 0, 1.], dtype='float32') if camera_dir is None else camera_dir)
         self.dynamic_look_at = isinstance(camera_dir, torch.Tensor)
-        self.rays = None
+        self._rays = None
+        self._last_sample = None     # (sampleDist_x, sampleDist_y) of the last build's last sample
+
+    @property
+    def rays(self):
+        """The reference leaves the LAST anti-alias sample's RayField on the camera after
+        build() (scene.py:30-32); some scripts read it (e.g. autoencoder_2ly.py:139).  The
+        kernels never materialise rays, so this dense field is rebuilt on demand."""
+        if self._rays is None and self._last_sample is not None:
+            _, jit, S, transposed = self._last_sample
+            jx, jy = (j[:, :, S - 1].detach().cpu().numpy() for j in jit)      # image index space
+            if transposed:
+                jx, jy = jx.T, jy.T                                            # back to ray index space
+            sx = (jx + np.float32(S - 1)) / np.float32(S)                      # scene.py:31-32
+            sy = (jy + np.float32(S - 1)) / np.float32(S)
+            self._rays = self.make_rays(self.x_dims, self.y_dims, sx, sy)
+        return self._rays
+
+    @rays.setter
+    def rays(self, value):
+        self._rays = value
 
     def make_rays(self, x_dims, y_dims, sampleDist_x=None, sampleDist_y=None):
         """scene.py:61-75 (dense helper; the kernels generate rays in registers with
@@ -221,6 +241,7 @@ class Scene(object):
         cfg = self.config(antialias_samples)
         obj_type, w2o, mat, light, cam = self.pack(device)
         jit = self._jitter_for(cfg.n, cfg.samples, jitter, seed, device)
+        self.camera._rays, self.camera._last_sample = None, ('lazy', jit, cfg.samples, not self.camera.has_transform)
         return R.render(cfg, obj_type, w2o, mat, light, cam, jit)
 
     def build_mse(self, target, antialias_samples=4, channel_weight=None, jitter=None, seed=None,
