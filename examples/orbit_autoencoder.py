@@ -33,15 +33,32 @@ class Encoder(torch.nn.Module):
 
 
 def main(num_scenes=256, steps=30, lr=2e-8, n=64, seed=1234, verbose=True):
-    dev = torch.device('cuda')
+    """Single GPU, or `torchrun --nproc-per-node G examples/orbit_autoencoder.py`: the scene
+    batch is sharded across ranks (sharding.scene_range), every rank renders and
+    back-propagates its own scenes, and ONE flat allreduce sums the encoder-weight
+    gradients."""
+    import torch.distributed as dist
+    from reversible_raytracer_b200 import sharding
+    world, rank = int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group('nccl', device_id=dev)
     tb = W.orbit_tables(num_scenes, seed=seed)
+    first, count = sharding.scene_range(num_scenes, world, rank)          # this rank's scenes (x2 views)
+    for key in ('w2o', 'camera'):
+        tb[key] = tb[key][2 * first:2 * (first + count)]
+    num_scenes = count
+    verbose = verbose and rank == 0
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    cfg = R.RenderConfig(n=n, samples=4, shader=tb['shader'], transpose=0, seed=11)
+    cfg = R.RenderConfig(n=n, samples=4, shader=tb['shader'], transpose=0, seed=11, scene_begin=2 * first)
     obj_type, material, light, camera = t(tb['obj_type']), t(tb['material']), t(tb['light']), t(tb['camera'])
     B = 2 * num_scenes
     # data: the scenes rendered at their true centres (planet_orbit.py), as uint8 like the dataset
     X, _, _ = R.render_forward(cfg, obj_type, t(tb['w2o']), material, light, camera, None, want_hit=False)
     X = (X * 255).to(torch.uint8).float() / 255.0                                        # [B,n,n,3]
+    torch.manual_seed(0)                                     # identical replicas on every rank
     enc = Encoder(n * n * 3).to(dev)
     opt = torch.optim.SGD(enc.parameters(), lr=lr)
     fixed = torch.tensor([0., 0., 48.], device=dev).expand(B, 3)
@@ -53,8 +70,16 @@ def main(num_scenes=256, steps=30, lr=2e-8, n=64, seed=1234, verbose=True):
         loss = R.render_fused_mse_loss(cfg, obj_type, w2o, material, light, camera, X).sum()
         opt.zero_grad(set_to_none=True)
         loss.backward()
+        if world > 1:                                        # one flat allreduce: [grads..., loss]
+            flat = torch.cat([p.grad.reshape(-1) for p in enc.parameters()] + [loss.detach().reshape(1)])
+            dist.all_reduce(flat)
+            off = 0
+            for p in enc.parameters():
+                p.grad.copy_(flat[off:off + p.numel()].reshape(p.shape))
+                off += p.numel()
+            loss = flat[-1]
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
         if verbose:
             print('step %d cost %.3f' % (step, losses[-1]))
     return losses

@@ -100,7 +100,7 @@ typedef struct rrt_scene {
     /* Anti-alias jitter in [0,1), IMAGE index space, slab-local:
      * jitter_x[scene][a - row_begin][b][s] is the value the reference adds to ray
      * channel 0 of the ray that shades pixel (a,b) (scene.py:24-25,31-32,73-74).
-     * NULL => in-kernel counter RNG keyed by (seed, scene, a*n+b, s).                   */
+     * NULL => in-kernel counter RNG keyed by (seed, scene_begin+scene, a*n+b, s).                   */
     const float* jitter_x;
     const float* jitter_y;
 
@@ -116,6 +116,11 @@ typedef struct rrt_scene {
      * the float64 grid themselves.  Same bits either way; the table only saves the
      * float64 divide/sqrt chains per pixel (small images, batches of scenes).          */
     const float* base_rays;
+
+    /* Global index of this call's scene 0 (scene-batch sharding across GPUs): only keys the
+     * in-kernel jitter RNG, so that a sharded batch draws the same jitter as the whole one. */
+    int32_t scene_begin;
+    int32_t reserved;
 } rrt_scene;
 
 int rrt_version(void);

@@ -379,8 +379,8 @@ static inline void orc_pixel_ray(const rrt_scene* sc, const orc_glob* g, int sce
         jx = sc->jitter_x[off];
         jy = sc->jitter_y[off];
     } else {
-        jx = orc_rng(sc->seed, (uint32_t)scene, (uint32_t)(a * n + b), (uint32_t)s, 0);
-        jy = orc_rng(sc->seed, (uint32_t)scene, (uint32_t)(a * n + b), (uint32_t)s, 1);
+        jx = orc_rng(sc->seed, (uint32_t)(scene + sc->scene_begin), (uint32_t)(a * n + b), (uint32_t)s, 0);
+        jy = orc_rng(sc->seed, (uint32_t)(scene + sc->scene_begin), (uint32_t)(a * n + b), (uint32_t)s, 1);
     }
     (void)rows;
     int i = sc->transpose ? b : a, j = sc->transpose ? a : b;

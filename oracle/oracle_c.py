@@ -28,6 +28,7 @@ class RrtScene(C.Structure):
         ('w2o_scene_stride', C.c_int64), ('material_scene_stride', C.c_int64),
         ('light_scene_stride', C.c_int64), ('camera_scene_stride', C.c_int64),
         ('jitter_scene_stride', C.c_int64), ('base_rays', C.c_void_p),
+        ('scene_begin', C.c_int32), ('reserved', C.c_int32),
     ]
 
 
@@ -74,7 +75,7 @@ class PackedScene:
 
     def __init__(self, n, samples, obj_type, w2o, material, light, camera, shader,
                  transpose, max_depth=1.0, jitter_x=None, jitter_y=None, seed=0,
-                 camera_grad=0, row_begin=0, row_count=0):
+                 camera_grad=0, row_begin=0, row_count=0, scene_begin=0):
         self.n, self.samples = int(n), int(samples)
         self.obj_type = np.ascontiguousarray(obj_type, dtype=np.int32)
         self.N = int(self.obj_type.shape[0])
@@ -91,6 +92,7 @@ class PackedScene:
         self.camera_grad = int(camera_grad)
         self.row_begin = int(row_begin)
         self.row_count = int(row_count)
+        self.scene_begin = int(scene_begin)
         self.rows = self.row_count if self.row_count > 0 else self.n - self.row_begin
         self.jitter_x = None if jitter_x is None else np.ascontiguousarray(jitter_x, dtype=np.float32)
         self.jitter_y = None if jitter_y is None else np.ascontiguousarray(jitter_y, dtype=np.float32)
@@ -130,6 +132,7 @@ class PackedScene:
         d.n, d.samples, d.num_objects, d.num_scenes = self.n, self.samples, self.N, self.B
         d.shader, d.transpose = self.shader, self.transpose
         d.row_begin, d.row_count = self.row_begin, self.row_count
+        d.scene_begin = self.scene_begin
         d.max_depth, d.camera_grad, d.seed = self.max_depth, self.camera_grad, self.seed
         d.obj_type, d.w2o, d.material = _ptr(self.obj_type), _ptr(self.w2o), _ptr(self.material)
         d.light, d.camera = _ptr(self.light), _ptr(self.camera)

@@ -673,8 +673,8 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                     jx = __ldg(sc.jitter_x + off);
                     jy = __ldg(sc.jitter_y + off);
                 } else {
-                    jx = rrt_rng(sc.seed, scene, (uint32_t)(a * n + b), s, 0);
-                    jy = rrt_rng(sc.seed, scene, (uint32_t)(a * n + b), s, 1);
+                    jx = rrt_rng(sc.seed, scene + sc.scene_begin, (uint32_t)(a * n + b), s, 0);
+                    jy = rrt_rng(sc.seed, scene + sc.scene_begin, (uint32_t)(a * n + b), s, 1);
                 }
                 const float ox = P.pow2 ? jitter_offset_pow2(jx, s, P.inv_s, P.inv_n) : jitter_offset(jx, s, S, n);
                 const float oy = P.pow2 ? jitter_offset_pow2(jy, s, P.inv_s, P.inv_n) : jitter_offset(jy, s, S, n);

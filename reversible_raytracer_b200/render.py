@@ -28,6 +28,7 @@ class RenderConfig:
     seed: int = 0                       # in-kernel jitter seed when no jitter tensors are given
     row_begin: int = 0                  # multi-GPU row slab
     row_count: int = 0
+    scene_begin: int = 0                # multi-GPU scene-batch shard: global index of scene 0 (jitter RNG key)
 
     @property
     def rows(self):
@@ -96,6 +97,7 @@ class _Tables:
         d.n, d.samples, d.num_objects, d.num_scenes = cfg.n, cfg.samples, self.N, self.B
         d.shader, d.transpose = cfg.shader, cfg.transpose
         d.row_begin, d.row_count = cfg.row_begin, cfg.row_count
+        d.scene_begin = cfg.scene_begin
         d.max_depth, d.camera_grad, d.seed = cfg.max_depth, cfg.camera_grad, cfg.seed & 0xFFFFFFFFFFFFFFFF
         d.obj_type, d.w2o, d.material = self.obj_type.data_ptr(), self.w2o.data_ptr(), self.material.data_ptr()
         d.light, d.camera = self.light.data_ptr(), self.camera.data_ptr()

@@ -249,3 +249,24 @@ def test_random_scenes_forward_and_gradients(seed, cuda):
         # random scenes contain grazing hits whose single-ray gradient dominates a block: compare
         # against the whole vector's scale here; per-block comparisons are in the config tests
         assert np.max(np.abs(g - r)) <= GRAD_TOL * scale, np.max(np.abs(g - r)) / scale
+
+
+def test_scene_batch_shards_reproduce_the_whole_batch(cuda):
+    """Scene-batch sharding (C4 across GPUs): rendering scenes [4,10) as their own call with
+    scene_begin=4 gives the same bits as the whole batch (in-kernel jitter is keyed by the
+    global scene index); checked against the oracle too."""
+    from reversible_raytracer_b200 import workloads as W
+    tb = W.orbit_tables(5)                                      # 10 scene-views
+    ps = oc.PackedScene(32, 4, tb['obj_type'], tb['w2o'], tb['material'], tb['light'], tb['camera'], tb['shader'], 0,
+                        seed=99, camera_grad=1)
+    img_o, hit_o, _ = oc.render_forward(ps)
+    cfg, ot, w2o, mat, light, cam, _ = to_device(ps, cuda, with_jitter=False)
+    img, hit, _ = R.render_forward(cfg, ot, w2o, mat, light, cam, None)
+    assert np.array_equal(hit.cpu().numpy(), hit_o)
+    from dataclasses import replace
+    part, hit_p, _ = R.render_forward(replace(cfg, scene_begin=4), ot, w2o[4:], mat, light, cam[4:], None)
+    assert torch.equal(part, img[4:]) and torch.equal(hit_p, hit[4:])
+    ps_part = oc.PackedScene(32, 4, tb['obj_type'], tb['w2o'][4:], tb['material'], tb['light'], tb['camera'][4:], tb['shader'], 0,
+                             seed=99, camera_grad=1, scene_begin=4)
+    _, hit_op, _ = oc.render_forward(ps_part)
+    assert np.array_equal(hit_op, hit_o[4:])
