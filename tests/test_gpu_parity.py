@@ -270,3 +270,52 @@ def test_scene_batch_shards_reproduce_the_whole_batch(cuda):
                              seed=99, camera_grad=1, scene_begin=4)
     _, hit_op, _ = oc.render_forward(ps_part)
     assert np.array_equal(hit_op, hit_o[4:])
+
+
+def test_full_size_c5_properties(cuda):
+    """BASELINE's full stress config (4096 x 4096, S=4, 1024 spheres, in-kernel RNG) through
+    size-independent properties: (1) 8 row slabs reproduce the full render bit for bit,
+    (2) sampled rows match the oracle bit-exactly (masks) / within tolerance (pixels),
+    (3) fused forward+loss+reverse == forward, torch loss, separate reverse pass,
+    (4) the reverse pass is linear in dL/dimage, (5) two runs give identical masks."""
+    from reversible_raytracer_b200 import workloads as W, _native as nat
+    n, S, N = 4096, 4, 1024
+    tb = W.stress_tables(N)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    args = (t(tb['obj_type']), t(tb['w2o']), t(tb['material']), t(tb['light']), t(tb['camera']))
+    cfg = R.RenderConfig(n=n, samples=S, shader=nat.SHADER_PHONG, transpose=1, seed=4321)
+    img, hit, _ = R.render_forward(cfg, *args, None, want_hit=True)
+    # (5)
+    img2, hit2, _ = R.render_forward(cfg, *args, None, want_hit=True)
+    assert torch.equal(hit, hit2) and torch.equal(img, img2)
+    del img2, hit2
+    # (1)
+    for r in range(8):
+        part, hpart, _ = R.render_forward(cfg.slab(512 * r, 512), *args, None, want_hit=True)
+        assert torch.equal(part, img[512 * r:512 * (r + 1)])
+        assert torch.equal(hpart, hit[:, 512 * r:512 * (r + 1)])
+        del part, hpart
+    # (2)
+    for row in (0, 1717, 4095):
+        ps = oc.PackedScene(n, S, tb['obj_type'], tb['w2o'], tb['material'], tb['light'], tb['camera'], tb['shader'], 1,
+                            seed=4321, row_begin=row, row_count=1)
+        img_o, hit_o, _ = oc.render_forward(ps)
+        assert np.array_equal(hit[:, row:row + 1].cpu().numpy(), hit_o[0])
+        np.testing.assert_allclose(img[row:row + 1].cpu().numpy(), img_o[0], rtol=PIX_RTOL, atol=PIX_ATOL)
+    # (3) on a 256-row slab (keeps the test light)
+    sl = cfg.slab(1024, 256)
+    target = torch.rand(256, n, 3, device=cuda)
+    loss_f, grad_f, image_f, _ = R.render_fused_mse(sl, *args, target, want_image=True)
+    assert torch.equal(image_f, img[1024:1280])
+    dl = 2 * (image_f - target)
+    grad_b = R.render_backward(sl, *args, dl, hit[:, 1024:1280].contiguous())
+    np.testing.assert_allclose(float(loss_f), float(((image_f.double() - target.double()) ** 2).sum()), rtol=1e-5)
+    compare_grads(grad_f.double().cpu().numpy(), grad_b.double().cpu().numpy(), N)
+    # (4)
+    g1, g2 = torch.randn_like(dl), torch.randn_like(dl)
+    h = hit[:, 1024:1280].contiguous()
+    ga = R.render_backward(sl, *args, g1, h).double()
+    gb = R.render_backward(sl, *args, g2, h).double()
+    gc = R.render_backward(sl, *args, 0.5 * g1 - 2.0 * g2, h).double()
+    ref = (0.5 * ga - 2.0 * gb).cpu().numpy()
+    assert np.max(np.abs(gc.cpu().numpy() - ref)) <= 2e-3 * np.max(np.abs(ref))
