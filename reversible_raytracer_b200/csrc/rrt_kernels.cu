@@ -322,15 +322,24 @@ __device__ __forceinline__ float object_max_det(uint32_t rec, const RayPack& rp,
 template <bool GENERAL>
 __device__ __forceinline__ void sweep_spheres(const float4* __restrict__ tab, int count, int kbase, const RayPack& rp,
                                               const float* dw, float* tmin, int* idx) {
-    int k = 0;
-    uint32_t rec = (uint32_t)__cvta_generic_to_shared(tab);
+    // one induction variable (the shared-window address) and a warp-uniform branch keep the
+    // loop control at compare+branch; the object index is only reconstructed on the rare path
+    uint32_t rec0 = (uint32_t)__cvta_generic_to_shared(tab);
+    uint32_t rec_end = rec0 + 64u * (uint32_t)(count - count % kGroup);
+    // launder both through an opaque move: otherwise ptxas rematerialises the shared-window
+    // arithmetic (S2UR/ULEA) inside the loop instead of keeping two registers live
+    asm volatile("mov.u32 %0, %0;" : "+r"(rec0));
+    asm volatile("mov.u32 %0, %0;" : "+r"(rec_end));
+    uint32_t rec = rec0;
 #pragma unroll 1
-    for (; k + kGroup <= count; k += kGroup, rec += 64 * kGroup) {
+    for (; rec != rec_end; rec += 64 * kGroup) {
         float gmax = 0.0f;
 #pragma unroll
         for (int j = 0; j < kGroup; j++) gmax = object_max_det<GENERAL>(rec + 64 * j, rp, gmax);
-        if (__builtin_expect(gmax > 0.0f, 0)) rare_group(tab, k, kGroup, kbase, dw, tmin, idx);
+        if (__builtin_expect(__any_sync(0xffffffffu, gmax > 0.0f), 0))
+            rare_group(tab, (int)((rec - rec0) >> 6), kGroup, kbase, dw, tmin, idx);
     }
+    const int k = count - count % kGroup;
     if (k < count) rare_group(tab, k, count - k, kbase, dw, tmin, idx);
 }
 
