@@ -17,8 +17,10 @@
 //     broadcast from shared memory (LDS.128, scalar-broadcast operand form);
 //   * the object table is transformed once per CTA into 64-byte sweep records in
 //     shared memory, streamed in chunks when N is large;
-//   * hits are rare per (ray, object): the hot loop only tests det > 0 and branches
-//     to a scalar canonical-order routine that computes t and updates the winner;
+//   * hits are rare per (ray, object): the hot loop is branch-free over groups of 4
+//     objects (packed discriminants folded into a running max, FMNMX3), one warp-uniform
+//     compare-and-branch per group into an out-of-line routine that re-tests the group
+//     and runs the scalar canonical-order hit computation (sqrt, div, strict '<');
 //   * shading and the reverse pass run once per winning ray after the sweep; hit
 //     records are recomputed, never stored; per-object gradients are reduced
 //     thread -> warp (shuffle) -> CTA (shared-memory slots) -> one atomic per CTA.
@@ -37,7 +39,13 @@ namespace {
 
 typedef unsigned long long u64;
 
-constexpr int kRays = 8;          // rays per thread (4 packed pairs)
+#ifndef RRT_RAYS
+#define RRT_RAYS 8
+#endif
+constexpr int kRays = RRT_RAYS;   // rays per thread (kRays/2 packed pairs)
+// Tuning knobs (measured on B200, C5: DESIGN.md 4.3).  8 rays/thread, 128-thread CTAs at
+// 5 CTAs/SM (96 registers), 512-object chunks (32 KB) and groups of 4 were the best of the
+// variants tried; 16 rays/thread, 256-thread CTAs, groups of 2/3/5/6/8 were all slower.
 #ifndef RRT_OBJ_CHUNK
 #define RRT_OBJ_CHUNK 512
 #endif
@@ -1265,7 +1273,7 @@ int launch(KParams& P, cudaStream_t st) {
     P.vec_ok = (sc.n % 4 == 0) && (((uintptr_t)P.image & 15) == 0) && (((uintptr_t)P.target & 15) == 0);
     const int S = sc.samples;
     int pix;
-    if (S == 1) pix = 8; else if (S == 2) pix = 4; else if (S == 4) pix = 2; else pix = 1;
+    if (S == 1) pix = kRays; else if (S == 2) pix = kRays / 2; else if (S == 4) pix = kRays / 4; else pix = 1;
     // block height: keep the grid >= ~2 waves of 148 SMs when the image is small
     const int cols = (sc.n + 32 * pix - 1) / (32 * pix);
     int warps = kMaxWarps;
@@ -1275,10 +1283,10 @@ int launch(KParams& P, cudaStream_t st) {
     const int staged = sc.num_objects < kObjChunk ? sc.num_objects : kObjChunk;
     size_t smem = (size_t)(staged > 0 ? staged : 1) * 64;
     void (*kern)(const KParams) = nullptr;
-    if (S == 1) kern = render_kernel<8, 1, MODE>;
-    else if (S == 2) kern = render_kernel<4, 2, MODE>;
-    else if (S == 4) kern = render_kernel<2, 4, MODE>;
-    else kern = render_kernel<1, 8, MODE>;
+    if (S == 1) kern = render_kernel<kRays, 1, MODE>;
+    else if (S == 2) kern = render_kernel<kRays / 2, 2, MODE>;
+    else if (S == 4) kern = render_kernel<kRays / 4, 4, MODE>;
+    else kern = render_kernel<1, kRays, MODE>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -1343,8 +1351,8 @@ int rrt_render_fused_mse(const rrt_scene* scene, const float* target, const floa
     if (rc) return rc;
     if (!target || !loss || !grad) return fail(RRT_ERR_INVALID, "target, loss and grad are required");
     const int S = scene->samples;
-    if (!(S == 1 || S == 2 || S == 4 || S == 8))
-        return fail(RRT_ERR_UNSUPPORTED, "fused kernel supports samples in {1,2,4,8}; use forward + backward");
+    if (S > kRays)   // one thread must own all samples of its pixels (single sample chunk)
+        return fail(RRT_ERR_UNSUPPORTED, "fused kernel supports samples <= 8; use forward + backward");
     P.sc = *scene;
     P.target = target;
     P.cw[0] = channel_weight ? channel_weight[0] : 1.f;
