@@ -32,7 +32,18 @@ CASES = {
     'ragged_n1': lambda: scenes.optimize_brightness(n=1),
     'ragged_n5': lambda: scenes.match_mirror(n=5),
     'many_objects_chunked': lambda: scenes.stress(n=32, num_objects=1500),
+    'many_general_chunked': lambda: scenes.stress(n=24, num_objects=1100, general=True),
+    'many_mixed_chunked': lambda: _mixed_many(),
 }
+
+
+def _mixed_many():
+    """> 512 objects (two table chunks) with squares and general spheres interleaved."""
+    from oracle import oracle_numpy as on
+    base = scenes.stress(n=20, num_objects=600, general=True)
+    base['obj_type'] = base['obj_type'].copy()
+    base['obj_type'][::7] = on.SQUARE
+    return base
 
 
 def check_forward(ps, dev):
