@@ -366,6 +366,8 @@ def run_b200(args):
         cpu = None
         if world == 1:
             peak_tf, _ = R.measure_fp32_peak(1, 4096)
+            peak_scalar, _ = R.measure_fp32_peak(0, 4096)
+            peak_mixed, _ = R.measure_fp32_peak(2, 4096)
             ach = flops / (ms_step * 1e-3) / 1e12
             traffic, traffic_src = None, None
             try:
@@ -378,6 +380,11 @@ def run_b200(args):
             roof = dict(bound='fp32', achieved=ach, peak=peak_tf, unit='TFLOP/s', frac=ach / peak_tf, traffic=traffic,
                         traffic_unit='bytes per launch (dram read+write)', traffic_source=traffic_src,
                         kernel='render_kernel<2,4,FUSED>', algorithmic_flops=flops,
+                        issue_model=dict(
+                            ffma2_only_tflops=peak_tf, scalar_ffma_tflops=peak_scalar, ffma2_plus_1_alu_per_4_tflops=peak_mixed,
+                            note='an FFMA2 holds the SMSP issue port for 2 cycles (nothing issues in its shadow), so every '
+                                 'non-FMA instruction of the sweep costs FP32 throughput; the canonical order itself caps '
+                                 'at 16 credited flops / 22 FMA-lane-ops = 72.7% of peak'),
                         peak_source='measured in this run: packed FFMA2 micro-benchmark (rrt_measure_fp32_peak); '
                                     'MEASURED_PEAKS.json has no FP32 entry; theoretical 148*128*2*1.965 GHz = 74.45',
                         hbm=dict(algorithmic_bytes=float(n) * n * 24,

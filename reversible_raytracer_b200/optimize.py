@@ -14,6 +14,8 @@ Both call shapes found in the reference are accepted:
     optimize(tVars, loss, lr, momentum) -> fn()            optimize_brightness.py:50-52,
                                                            match_mirror.py:48 (stale form)
 """
+import warnings
+
 import torch
 
 from .util import get_epsilon  # noqa: F401
@@ -77,7 +79,8 @@ class GDOptimizer(object):
             if use_graph and st['graph'] is None and not st['failed'] and st['calls'] > 2:
                 try:
                     capture()
-                except Exception:                  # closure not capturable: keep stepping eagerly
+                except Exception as e:             # closure not capturable: keep stepping eagerly
+                    warnings.warn('GDOptimizer: CUDA-graph capture of the step failed (%r); stepping eagerly' % (e,))
                     st['failed'] = True
                     st['graph'] = None
                     torch.cuda.synchronize()

@@ -73,7 +73,8 @@ class _Tables:
         if not self.batched:
             w2o = w2o.unsqueeze(0)
         self.B, self.N = int(w2o.shape[0]), int(w2o.shape[1])
-        assert w2o.shape[2] == nat.W2O_STRIDE
+        if w2o.shape[2] != nat.W2O_STRIDE:
+            raise ValueError('w2o must be [..., N, 12] (rows 0..2 of shape.w2o.m)')
         self.w2o = w2o
         self.material = _f32(material, 'material').reshape(-1 if self.N else 1, self.N, nat.MAT_STRIDE)
         self.light = _f32(light, 'light').reshape(-1, nat.LIGHT_STRIDE)
@@ -81,17 +82,19 @@ class _Tables:
         if not obj_type.is_cuda:
             raise nat.NativeError('obj_type must be a CUDA tensor')
         self.obj_type = obj_type.to(torch.int32).contiguous()
-        assert self.obj_type.numel() == self.N
+        if self.obj_type.numel() != self.N:
+            raise ValueError('obj_type must have one entry per object')
         self.cfg = cfg
         self.device = w2o.device
         self.jx = self.jy = None
         if jitter is not None:
             self.jx, self.jy = _f32(jitter[0], 'jitter_x'), _f32(jitter[1], 'jitter_y')
             per = cfg.rows * cfg.n * cfg.samples
-            assert self.jx.numel() in (per, per * self.B) and self.jy.numel() == self.jx.numel(), \
-                'jitter must be [rows,n,S] (shared) or [B,rows,n,S], slab-local, image index space'
-        for t, per in ((self.material, 1), (self.light, 1), (self.camera, 1)):
-            assert t.shape[0] in (1, self.B)
+            if self.jx.numel() not in (per, per * self.B) or self.jy.numel() != self.jx.numel():
+                raise ValueError('jitter must be [rows,n,S] (shared) or [B,rows,n,S], slab-local, image index space')
+        for name, t in (('material', self.material), ('light', self.light), ('camera', self.camera)):
+            if t.shape[0] not in (1, self.B):
+                raise ValueError('%s must be shared or have one table per scene' % name)
 
         d = nat.RrtScene()
         d.n, d.samples, d.num_objects, d.num_scenes = cfg.n, cfg.samples, self.N, self.B
@@ -141,12 +144,14 @@ def render_backward(cfg, obj_type, w2o, material, light, camera, dl_dimage, hit_
     """-> flat gradient [B, N*19+21] (layout: include/rrt_b200.h)."""
     T = _Tables(cfg, obj_type, w2o, material, light, camera, jitter)
     dl = _f32(dl_dimage, 'dl_dimage')
-    assert dl.numel() == T.B * cfg.rows * cfg.n * 3
+    if dl.numel() != T.B * cfg.rows * cfg.n * 3:
+        raise ValueError('dl_dimage must be [B, rows, n, 3]')
     with torch.cuda.device(T.device):
         grad = torch.empty((T.B, nat.grad_size(T.N)), dtype=torch.float32, device=T.device)
         if hit_index is not None:
             hit_index = hit_index.to(torch.int32).contiguous()
-            assert hit_index.numel() == T.B * cfg.samples * cfg.rows * cfg.n
+            if hit_index.numel() != T.B * cfg.samples * cfg.rows * cfg.n:
+                raise ValueError('hit_index must be [B, S, rows, n]')
         rc = nat.lib().rrt_render_backward(C.byref(T.desc), dl.data_ptr(),
                                            hit_index.data_ptr() if hit_index is not None else None,
                                            grad.data_ptr(), T.stream())
@@ -160,7 +165,8 @@ def render_fused_mse(cfg, obj_type, w2o, material, light, camera, target, channe
     -> loss float64 [B], grad float32 [B, N*19+21], image or None, hit_index or None."""
     T = _Tables(cfg, obj_type, w2o, material, light, camera, jitter)
     tg = _f32(target, 'target')
-    assert tg.numel() == T.B * cfg.rows * cfg.n * 3
+    if tg.numel() != T.B * cfg.rows * cfg.n * 3:
+        raise ValueError('target must be [B, rows, n, 3]')
     cw = None
     if channel_weight is not None:
         cw = (C.c_float * 3)(*[float(v) for v in channel_weight])
