@@ -166,10 +166,10 @@ def other_configs(dev):
     us = L.timeit(fn, warm=5, iters=100)
     out['C4_orbit_256x2_fused'] = dict(us_per_batch=round(us, 1), Mrays_s=round(rays / us, 1))
 
-    def stress(general, fwd_only, samples=4, n=4096, N=1024, iters=3):
+    def stress(general, fwd_only, samples=4, n=4096, N=1024, iters=3, cull=0):
         tb = W.stress_tables(N, general=general)
         t = lambda a: torch.from_numpy(a).to(dev)
-        cfg = R.RenderConfig(n=n, samples=samples, shader=nat.SHADER_PHONG, transpose=1, seed=4321)
+        cfg = R.RenderConfig(n=n, samples=samples, shader=nat.SHADER_PHONG, transpose=1, seed=4321, cull=cull)
         args = (t(tb['obj_type']), t(tb['w2o']), t(tb['material']), t(tb['light']), t(tb['camera']))
         target, _, _ = R.render_forward(cfg, *args, None, want_hit=False)
         fn = (lambda: R.render_forward(cfg, *args, None, want_hit=False)) if fwd_only else \
@@ -181,6 +181,10 @@ def other_configs(dev):
     g = stress(True, False)
     g['frac_fp32_peak_28flop_per_test'] = None
     out['C5g_general_affine_fused'] = g
+    # NOT roofline-accountable: conservative per-tile culling skips work (results bit-identical, tested)
+    c = stress(False, False, cull=1, iters=5)
+    c['note'] = 'RRT_FLAG_CULL: same bits as the exhaustive sweep, reported separately, never as a roofline fraction'
+    out['C5_fused_with_culling'] = c
     return out
 
 

@@ -68,6 +68,14 @@ extern "C" {
 /* flat gradient vector per scene: [N][RRT_OBJ_GRAD_STRIDE] then [RRT_GLOBAL_GRAD] */
 #define RRT_GRAD_SIZE(num_objects) ((size_t)(num_objects) * RRT_OBJ_GRAD_STRIDE + RRT_GLOBAL_GRAD)
 
+/* rrt_scene.flags */
+/* Conservative per-tile object culling before the sweep: every CTA bounds its rays by a
+ * cone, rejects objects whose (inflated) bounding ball the cone cannot touch, and runs the
+ * canonical hit test only on the survivors, in list order.  Results are BIT-IDENTICAL to
+ * the exhaustive sweep (tested); only the work changes, so throughput measured with this
+ * flag is never reported as a roofline fraction. */
+#define RRT_FLAG_CULL 1
+
 #define RRT_OK 0
 #define RRT_ERR_INVALID (-1)   /* bad argument (message in rrt_last_error)            */
 #define RRT_ERR_CUDA (-2)      /* CUDA runtime error at launch                        */
@@ -120,7 +128,7 @@ typedef struct rrt_scene {
     /* Global index of this call's scene 0 (scene-batch sharding across GPUs): only keys the
      * in-kernel jitter RNG, so that a sharded batch draws the same jitter as the whole one. */
     int32_t scene_begin;
-    int32_t reserved;
+    int32_t flags;        /* RRT_FLAG_* */
 } rrt_scene;
 
 int rrt_version(void);

@@ -39,7 +39,7 @@ class RrtScene(C.Structure):
         ('w2o_scene_stride', C.c_int64), ('material_scene_stride', C.c_int64),
         ('light_scene_stride', C.c_int64), ('camera_scene_stride', C.c_int64),
         ('jitter_scene_stride', C.c_int64), ('base_rays', C.c_void_p),
-        ('scene_begin', C.c_int32), ('reserved', C.c_int32),
+        ('scene_begin', C.c_int32), ('flags', C.c_int32),
     ]
 
 
@@ -91,6 +91,7 @@ def lib():
 EXPORTS = ['rrt_version', 'rrt_last_error', 'rrt_render_forward', 'rrt_render_backward',
            'rrt_render_fused_mse', 'rrt_measure_fp32_peak', 'rrt_chain_forward', 'rrt_chain_backward', 'rrt_primary_rays']
 
+FLAG_CULL = 1
 CHAIN_TRANSLATE, CHAIN_SCALE, CHAIN_ROTATE, CHAIN_INVERT, CHAIN_MAX_OPS = 1, 2, 3, 0x100, 8
 
 

@@ -153,13 +153,14 @@ __device__ __forceinline__ float dot3_canon(float a0, float a1, float a2, float 
 // ---------------------------------------------------------------- object records
 // 64-byte sweep record (4 x float4) in shared memory:
 //   q0 = (a00, a11, a22, o'x)   q1 = (o'y, o'z, -cc, flags)
-//   q2 = (a01, a02, a10, a12)   q3 = (a20, a21, 0, 0)
+//   q2 = (a01, a02, a10, a12)   q3 = (a20, a21, |A|_F, 0)
 // flags bit0 = square, bit1 = general (some off-diagonal of A is non-zero).
 struct Obj {
     float a[9];
     float o[3];
     float ncc;
     int flags;
+    float afro;   // Frobenius norm of A (culling bound only)
 };
 
 struct Globals {       // per-scene constants, held in shared memory
@@ -188,13 +189,17 @@ __device__ __forceinline__ void make_obj(const float* __restrict__ w, int type, 
     ob.ncc = -cc;
     bool general = (ob.a[1] != 0.f) || (ob.a[2] != 0.f) || (ob.a[3] != 0.f) || (ob.a[5] != 0.f) || (ob.a[6] != 0.f) || (ob.a[7] != 0.f);
     ob.flags = (type == RRT_OBJ_SQUARE ? 1 : 0) | (general ? 2 : 0);
+    float f2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 9; q++) f2 += ob.a[q] * ob.a[q];
+    ob.afro = sqrtf(f2);
 }
 
 __device__ __forceinline__ void store_rec(float4* rec, const Obj& ob) {
     rec[0] = make_float4(ob.a[0], ob.a[4], ob.a[8], ob.o[0]);
     rec[1] = make_float4(ob.o[1], ob.o[2], ob.ncc, __int_as_float(ob.flags));
     rec[2] = make_float4(ob.a[1], ob.a[2], ob.a[3], ob.a[5]);
-    rec[3] = make_float4(ob.a[6], ob.a[7], 0.f, 0.f);
+    rec[3] = make_float4(ob.a[6], ob.a[7], ob.afro, 0.f);
 }
 
 __device__ __forceinline__ void load_rec(const float4* rec, Obj& ob) {
@@ -202,7 +207,7 @@ __device__ __forceinline__ void load_rec(const float4* rec, Obj& ob) {
     ob.a[0] = q0.x; ob.a[4] = q0.y; ob.a[8] = q0.z; ob.o[0] = q0.w;
     ob.o[1] = q1.x; ob.o[2] = q1.y; ob.ncc = q1.z; ob.flags = __float_as_int(q1.w);
     ob.a[1] = q2.x; ob.a[2] = q2.y; ob.a[3] = q2.z; ob.a[5] = q2.w;
-    ob.a[6] = q3.x; ob.a[7] = q3.y;
+    ob.a[6] = q3.x; ob.a[7] = q3.y; ob.afro = q3.z;
 }
 
 // ---------------------------------------------------------------- one ray-object test
@@ -556,6 +561,46 @@ __device__ __forceinline__ void warp_flush(int key, float (&acc)[19], int* slot_
     for (int v = 0; v < 19; v++) acc[v] = 0.f;
 }
 
+// ---------------------------------------------------------------- conservative tile culling
+// RRT_FLAG_CULL.  The CTA's rays (world directions, all through the camera origin) are
+// bounded by a circular cone (axis u, half-angle theta).  In an object's space every ray
+// direction lies within theta' of u' = A.u with sin(theta') <= |A|_F tan(theta) / |u'|.  The
+// LINE through o' with such a direction passes the object's origin no closer than
+// |o'| sin(phi - theta'), phi = angle(line u', -o') -- lines, not rays, because spheres have
+// no t > 0 test (shape.py:109-126).  The object is skipped only if that distance exceeds its
+// bounding radius (1 for the unit sphere, sqrt(1/2) for the unit square) inflated by far more
+// than the float32 error of the canonical discriminant (delta(det/vn) <= ~6e-7 |o'|^2) and of
+// this test itself.  Every comparison is written so that NaN keeps the object.
+struct TileCone {
+    float u[3];
+    float tan_theta;
+    int ok;
+};
+
+__device__ __forceinline__ bool cull_keep(const float4* __restrict__ rec, const TileCone& tc) {
+    if (!tc.ok) return true;
+    Obj ob;
+    load_rec(rec, ob);
+    const float ux = ob.a[0] * tc.u[0] + ob.a[1] * tc.u[1] + ob.a[2] * tc.u[2];
+    const float uy = ob.a[3] * tc.u[0] + ob.a[4] * tc.u[1] + ob.a[5] * tc.u[2];
+    const float uz = ob.a[6] * tc.u[0] + ob.a[7] * tc.u[1] + ob.a[8] * tc.u[2];
+    const float lu = sqrtf(ux * ux + uy * uy + uz * uz);
+    if (!(lu > 0.f)) return true;
+    const float s = ob.afro * tc.tan_theta / lu * 1.001f;
+    if (!(s < 0.99f)) return true;
+    const float theta_o = asinf(s) + 1e-4f;
+    const float lo2 = ob.o[0] * ob.o[0] + ob.o[1] * ob.o[1] + ob.o[2] * ob.o[2];
+    const float r2 = (ob.flags & 1) ? 0.5f : 1.0f;
+    const float rinfl = sqrtf(r2 + 1e-5f * (1.0f + lo2)) * 1.001f;
+    const float lo = sqrtf(lo2);
+    if (!(lo > rinfl)) return true;
+    float cphi = fabsf(ob.o[0] * ux + ob.o[1] * uy + ob.o[2] * uz) / (lo * lu);
+    cphi = fminf(cphi, 1.0f);
+    const float phi = acosf(cphi);
+    const float need = asinf(rinfl / lo) + 1e-4f;
+    return !(phi - theta_o > need);   // keep unless provably out of reach
+}
+
 // ---------------------------------------------------------------- the render kernel
 // grid = (ceil(n / (32*PIX)), ceil(rows / warps), B); block = 32 * warps.
 // Thread (warp w, lane l) owns pixels (row = tile_row0 + w, cols = col0 + l*PIX .. +PIX-1),
@@ -571,6 +616,9 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
     __shared__ float loss_warp[kMaxWarps];
     __shared__ __align__(16) float stage[kMaxWarps][32 * PIX * 3];   // per-warp tile-row staging (vector I/O)
     __shared__ int cam_identity_s;
+    __shared__ float cone_red[kMaxWarps][6];
+    __shared__ TileCone tcone;
+    __shared__ unsigned keepmask[(kObjChunk + 31) / 32];
     __shared__ int chunk_class;  // sticky per CTA: bit0 squares, bit1 general spheres seen
 
     const rrt_scene& sc = P.sc;
@@ -721,8 +769,65 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
             for (int p = 0; p < kRays / 2; p++) { rp.dx[p] = dp[p]; rp.dy[p] = dp[kRays / 2 + p]; rp.dz[p] = dp[kRays + p]; }
         }
 
-        // ---- nearest-hit sweep (or stored winners)
         const bool use_stored = (MODE == MODE_BWD) && (P.hit_in != nullptr);
+        const bool cull = (sc.flags & RRT_FLAG_CULL) && !use_stored;
+        if (cull) {   // ---- bounding cone of this CTA's rays (exact min/max of the rays built above)
+            const float big = 3.0e38f;
+            float lo3[3] = {big, big, big}, hi3[3] = {-big, -big, -big};
+#pragma unroll 1
+            for (int r = 0; r < kRays; r++) {
+                const float x = l_dw[r], y = l_dw[kRays + r], z = l_dw[2 * kRays + r];
+                if (x != 0.f || y != 0.f || z != 0.f) {
+                    lo3[0] = fminf(lo3[0], x); hi3[0] = fmaxf(hi3[0], x);
+                    lo3[1] = fminf(lo3[1], y); hi3[1] = fmaxf(hi3[1], y);
+                    lo3[2] = fminf(lo3[2], z); hi3[2] = fmaxf(hi3[2], z);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    lo3[c] = fminf(lo3[c], __shfl_xor_sync(0xffffffffu, lo3[c], o));
+                    hi3[c] = fmaxf(hi3[c], __shfl_xor_sync(0xffffffffu, hi3[c], o));
+                }
+            if (sc0 > 0) __syncthreads();          // previous use of cone_red / tcone is over
+            if (lane == 0) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) { cone_red[warp][c] = lo3[c]; cone_red[warp][3 + c] = hi3[c]; }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                float l[3] = {big, big, big}, h[3] = {-big, -big, -big};
+                for (int w = 0; w < nwarps; w++)
+                    for (int c = 0; c < 3; c++) { l[c] = fminf(l[c], cone_red[w][c]); h[c] = fmaxf(h[c], cone_red[w][3 + c]); }
+                TileCone tc;
+                tc.ok = 0; tc.tan_theta = 0.f; tc.u[0] = tc.u[1] = tc.u[2] = 0.f;
+                if (l[0] <= h[0]) {
+                    const float cx = 0.5f * (l[0] + h[0]), cy = 0.5f * (l[1] + h[1]), cz = 0.5f * (l[2] + h[2]);
+                    const float cn = sqrtf(cx * cx + cy * cy + cz * cz);
+                    if (cn > 1e-20f) {
+                        tc.u[0] = cx / cn; tc.u[1] = cy / cn; tc.u[2] = cz / cn;
+                        float cosmin = 1.0f;
+                        bool good = true;
+                        for (int q = 0; q < 8; q++) {
+                            const float vx = (q & 1) ? h[0] : l[0], vy = (q & 2) ? h[1] : l[1], vz = (q & 4) ? h[2] : l[2];
+                            const float vn = sqrtf(vx * vx + vy * vy + vz * vz);
+                            if (!(vn > 1e-20f)) { good = false; break; }
+                            cosmin = fminf(cosmin, (vx * tc.u[0] + vy * tc.u[1] + vz * tc.u[2]) / vn);
+                        }
+                        if (good && cosmin > 0.2f) {
+                            const float theta = acosf(fminf(cosmin, 1.0f)) * 1.001f + 1e-4f;
+                            tc.tan_theta = tanf(theta);
+                            tc.ok = 1;
+                        }
+                    }
+                }
+                tcone = tc;
+            }
+            __syncthreads();
+        }
+
+        // ---- nearest-hit sweep (or stored winners)
         if (use_stored) {
 #pragma unroll 1
             for (int r = 0; r < kRays; r++) {
@@ -750,7 +855,26 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                 }
                 __syncthreads();
                 const int cls = chunk_class;
-                if (cls == 0) sweep_spheres<false>(smem_tab, cnt, kb, rp, l_dw, l_tmin, l_idx);
+                if (cull) {
+                    // one ballot word per 32 objects keeps list order without a compaction pass
+                    for (int k0 = warp * 32; k0 < cnt; k0 += 32 * nwarps) {
+                        const int k = k0 + lane;
+                        const bool keep = (k < cnt) && cull_keep(smem_tab + 4 * k, tcone);
+                        const unsigned m = __ballot_sync(0xffffffffu, keep);
+                        if (lane == 0) keepmask[k0 >> 5] = m;
+                    }
+                    __syncthreads();
+#pragma unroll 1
+                    for (int w = 0; w < (cnt + 31) / 32; w++) {
+                        unsigned m = keepmask[w];
+#pragma unroll 1
+                        while (m) {
+                            const int bit = __ffs(m) - 1;
+                            m &= m - 1;
+                            rare_group(smem_tab, w * 32 + bit, 1, kb, l_dw, l_tmin, l_idx);
+                        }
+                    }
+                } else if (cls == 0) sweep_spheres<false>(smem_tab, cnt, kb, rp, l_dw, l_tmin, l_idx);
                 else if (!(cls & 1)) sweep_spheres<true>(smem_tab, cnt, kb, rp, l_dw, l_tmin, l_idx);
                 else sweep_mixed(smem_tab, cnt, kb, rp, l_dw, l_tmin, l_idx);
             }

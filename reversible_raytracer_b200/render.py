@@ -29,6 +29,7 @@ class RenderConfig:
     row_begin: int = 0                  # multi-GPU row slab
     row_count: int = 0
     scene_begin: int = 0                # multi-GPU scene-batch shard: global index of scene 0 (jitter RNG key)
+    cull: int = 0                       # 1: conservative per-tile object culling (bit-identical results, less work)
 
     @property
     def rows(self):
@@ -101,6 +102,7 @@ class _Tables:
         d.shader, d.transpose = cfg.shader, cfg.transpose
         d.row_begin, d.row_count = cfg.row_begin, cfg.row_count
         d.scene_begin = cfg.scene_begin
+        d.flags = nat.FLAG_CULL if cfg.cull else 0
         d.max_depth, d.camera_grad, d.seed = cfg.max_depth, cfg.camera_grad, cfg.seed & 0xFFFFFFFFFFFFFFFF
         d.obj_type, d.w2o, d.material = self.obj_type.data_ptr(), self.w2o.data_ptr(), self.material.data_ptr()
         d.light, d.camera = self.light.data_ptr(), self.camera.data_ptr()

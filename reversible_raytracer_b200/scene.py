@@ -218,7 +218,9 @@ class Scene(object):
         cam = torch.cat([cam_rows, self.camera.look_at.reshape(3).to(device)])
         return st['obj_type'], w2o, mat, light, cam
 
-    def config(self, antialias_samples=4):
+    CULL_MIN_OBJECTS = 32    # Scene.build turns conservative culling on from this many shapes
+
+    def config(self, antialias_samples=4, cull=None):
         cam = self.camera
         if cam.x_dims != cam.y_dims:
             raise ValueError('the reference renderer only works for x_dims == y_dims '
@@ -226,10 +228,11 @@ class Scene(object):
         return R.RenderConfig(n=cam.x_dims, samples=int(antialias_samples), shader=self.shader.shader_id,
                               transpose=0 if cam.has_transform else 1,
                               max_depth=float(getattr(self.shader, 'maxDepth', 1.0)),
-                              camera_grad=1 if cam.has_transform else 0)
+                              camera_grad=1 if cam.has_transform else 0,
+                              cull=int(len(self.shapes) >= self.CULL_MIN_OBJECTS if cull is None else bool(cull)))
 
     # -- rendering ------------------------------------------------------------------
-    def build(self, antialias_samples=4, jitter=None, seed=None):
+    def build(self, antialias_samples=4, jitter=None, seed=None, cull=None):
         """Render the scene (scene.py:18-52) -> image (x_dims, y_dims, 3) float32 on the
         GPU, differentiable w.r.t. shape transforms, materials, the light and (orbit
         variant) the camera transform."""
@@ -238,7 +241,7 @@ class Scene(object):
         device = self.device()
         if device.type != 'cuda':
             device = torch.device('cuda', torch.cuda.current_device())
-        cfg = self.config(antialias_samples)
+        cfg = self.config(antialias_samples, cull)     # culling never changes a bit of the result
         obj_type, w2o, mat, light, cam = self.pack(device)
         jit = self._jitter_for(cfg.n, cfg.samples, jitter, seed, device)
         self.camera._rays, self.camera._last_sample = None, ('lazy', jit, cfg.samples, not self.camera.has_transform)

@@ -330,3 +330,53 @@ def test_full_size_c5_properties(cuda):
     gc = R.render_backward(sl, *args, 0.5 * g1 - 2.0 * g2, h).double()
     ref = (0.5 * ga - 2.0 * gb).cpu().numpy()
     assert np.max(np.abs(gc.cpu().numpy() - ref)) <= 2e-3 * np.max(np.abs(ref))
+
+
+def _cull_equal(ps, cuda):
+    from dataclasses import replace
+    cfg, ot, w2o, mat, light, cam, jit = to_device(ps, cuda)
+    a = R.render_forward(cfg, ot, w2o, mat, light, cam, jit, want_hit=True, want_tmin=True)
+    b = R.render_forward(replace(cfg, cull=1), ot, w2o, mat, light, cam, jit, want_hit=True, want_tmin=True)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y), 'culling changed the result'
+    if cfg.samples <= 8:
+        target = torch.zeros_like(a[0])
+        l0, g0, _, _ = R.render_fused_mse(cfg, ot, w2o, mat, light, cam, target, None, jit)
+        l1, g1, _, _ = R.render_fused_mse(replace(cfg, cull=1), ot, w2o, mat, light, cam, target, None, jit)
+        np.testing.assert_allclose(float(l1.sum()), float(l0.sum()), rtol=1e-6)
+        s = float(g0.abs().max())
+        if s > 0:
+            assert float((g1 - g0).abs().max()) <= 1e-4 * s        # only the atomic order differs
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_culling_is_bit_identical_configs(name, cuda):
+    """RRT_FLAG_CULL (conservative per-tile object culling) never changes a bit of the image,
+    the hit masks or tmin."""
+    _cull_equal(oc.PackedScene.from_spec(CASES[name](), camera_grad=1), cuda)
+
+
+@pytest.mark.parametrize('seed', range(16))
+def test_culling_is_bit_identical_random(seed, cuda):
+    _cull_equal(oc.PackedScene.from_spec(_random_spec(np.random.RandomState(5000 + seed)), camera_grad=1), cuda)
+
+
+def test_culling_full_size_slab(cuda):
+    """C5 at full resolution (rows where culling rejects almost everything) + extreme
+    geometry: spheres behind the camera (negative t still hits), huge and tiny spheres."""
+    from dataclasses import replace
+    from reversible_raytracer_b200 import workloads as W, _native as nat
+    tb = W.stress_tables(1024)
+    w = tb['w2o'].reshape(-1, 3, 4).copy()
+    w[5] = W.w2o_translate_scale(np.array([[0.3, -0.2, -6.0]]), np.array([[1.5, 1.5, 1.5]])).reshape(3, 4)     # behind the camera
+    w[6] = W.w2o_translate_scale(np.array([[0.0, 0.0, 40.0]]), np.array([[30., 30., 30.]])).reshape(3, 4)      # huge, far
+    w[7] = W.w2o_translate_scale(np.array([[0.01, 0.02, 3.0]]), np.array([[1e-3, 1e-3, 1e-3]])).reshape(3, 4)  # sub-pixel
+    w[8] = W.w2o_translate_scale(np.array([[0.0, 0.0, 0.5]]), np.array([[2., 2., 2.]])).reshape(3, 4)          # camera inside
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    args = (t(tb['obj_type']), t(w.reshape(-1, 12)), t(tb['material']), t(tb['light']), t(tb['camera']))
+    for rb in (0, 2040, 4032):
+        cfg = R.RenderConfig(n=4096, samples=4, shader=nat.SHADER_PHONG, transpose=1, seed=4321, row_begin=rb, row_count=64)
+        a = R.render_forward(cfg, *args, None, want_hit=True, want_tmin=True)
+        b = R.render_forward(replace(cfg, cull=1), *args, None, want_hit=True, want_tmin=True)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
