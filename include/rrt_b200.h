@@ -75,6 +75,9 @@ extern "C" {
  * the exhaustive sweep (tested); only the work changes, so throughput measured with this
  * flag is never reported as a roofline fraction. */
 #define RRT_FLAG_CULL 1
+/* Force the general 8-rays-per-thread kernel even where the small-scene (one ray per thread)
+ * kernel would be chosen.  Results agree; this exists for A/B measurements and tests. */
+#define RRT_FLAG_NO_SMALL 2
 
 #define RRT_OK 0
 #define RRT_ERR_INVALID (-1)   /* bad argument (message in rrt_last_error)            */

@@ -30,6 +30,7 @@ class RenderConfig:
     row_count: int = 0
     scene_begin: int = 0                # multi-GPU scene-batch shard: global index of scene 0 (jitter RNG key)
     cull: int = 0                       # 1: conservative per-tile object culling (bit-identical results, less work)
+    no_small: int = 0                   # 1: never take the small-scene (one ray per thread) kernel (A/B, tests)
 
     @property
     def rows(self):
@@ -102,7 +103,7 @@ class _Tables:
         d.shader, d.transpose = cfg.shader, cfg.transpose
         d.row_begin, d.row_count = cfg.row_begin, cfg.row_count
         d.scene_begin = cfg.scene_begin
-        d.flags = nat.FLAG_CULL if cfg.cull else 0
+        d.flags = (nat.FLAG_CULL if cfg.cull else 0) | (nat.FLAG_NO_SMALL if cfg.no_small else 0)
         d.max_depth, d.camera_grad, d.seed = cfg.max_depth, cfg.camera_grad, cfg.seed & 0xFFFFFFFFFFFFFFFF
         d.obj_type, d.w2o, d.material = self.obj_type.data_ptr(), self.w2o.data_ptr(), self.material.data_ptr()
         d.light, d.camera = self.light.data_ptr(), self.camera.data_ptr()
@@ -187,6 +188,87 @@ def render_fused_mse(cfg, obj_type, w2o, material, light, camera, target, channe
         image = image[0] if image is not None else None
         hit = hit[0] if hit is not None else None
     return loss, grad, image, hit
+
+
+class StreamedFusedMSE:
+    """Fused forward + squared-error loss + reverse pass of ONE big image whose target (and,
+    optionally, rendered image) live in pinned HOST memory: the image is cut into row slabs
+    and the three legs of every slab run on their own CUDA streams --
+
+        copy-in stream :  target slab k+1   host -> device
+        kernel streams :  fused kernel on slab k        (two streams, so that the tail of
+                          one slab's grid overlaps the head of the next)
+        copy-out stream:  image slab k-1    device -> host
+
+    -- so a step costs max(kernel, PCIe) instead of their sum.  Slab results are the same
+    bits as the whole-image launch (rays are keyed by image row, RenderConfig.slab); the
+    per-slab gradient vectors and losses are summed on the caller's stream.  Buffers,
+    streams and events are created once (the equivalent of the reference's compile step,
+    optimize.py:29); __call__ only enqueues work."""
+
+    def __init__(self, cfg, num_objects, device, slabs=8, want_image=True):
+        self.cfg, self.N, self.device = cfg, int(num_objects), torch.device(device)
+        rows, slabs = cfg.rows, max(1, min(int(slabs), cfg.rows))
+        per = (rows + slabs - 1) // slabs
+        per = (per + 3) // 4 * 4                      # whole CTAs (4 rows each) per slab
+        self.bounds = [(r0, min(per, rows - r0)) for r0 in range(0, rows, per)]
+        K = len(self.bounds)
+        with torch.cuda.device(self.device):
+            self.dev_target = torch.empty((rows, cfg.n, 3), dtype=torch.float32, device=self.device)
+            self.dev_image = torch.empty_like(self.dev_target) if want_image else None
+            self.grads = torch.empty((K, nat.grad_size(self.N)), dtype=torch.float32, device=self.device)
+            self.losses = torch.empty((K,), dtype=torch.float64, device=self.device)
+            self.s_in, self.s_out = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+            self.s_k = [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
+            self.e_in = [torch.cuda.Event() for _ in range(K)]
+            self.e_k = [torch.cuda.Event() for _ in range(K)]
+            self.e_fork, self.e_out = torch.cuda.Event(), torch.cuda.Event()
+        self.launches_per_call = 2 * K                # fused kernel + finalize per slab
+
+    def __call__(self, obj_type, w2o, material, light, camera, target_host, image_host=None, channel_weight=None):
+        cfg, dev = self.cfg, self.device
+        if target_host.is_cuda or not target_host.is_pinned():
+            raise ValueError('target_host must be a pinned host tensor (use render_fused_mse for device targets)')
+        if tuple(target_host.shape) != tuple(self.dev_target.shape) or target_host.dtype != torch.float32:
+            raise ValueError('target_host must be float32 [rows, n, 3]')
+        if image_host is not None:
+            if self.dev_image is None:
+                raise ValueError('constructed with want_image=False')
+            if image_host.is_cuda or not image_host.is_pinned() or tuple(image_host.shape) != tuple(self.dev_image.shape):
+                raise ValueError('image_host must be a pinned host float32 [rows, n, 3] tensor')
+        cw = (C.c_float * 3)(*[float(v) for v in channel_weight]) if channel_weight is not None else None
+        L = nat.lib()
+        cur = torch.cuda.current_stream(dev)
+        self.e_fork.record(cur)                       # parameter tables are ready from here on
+        for s in (self.s_in, self.s_out, *self.s_k):
+            s.wait_event(self.e_fork)
+        keep = []
+        for k, (r0, rc) in enumerate(self.bounds):
+            with torch.cuda.stream(self.s_in):
+                self.dev_target[r0:r0 + rc].copy_(target_host[r0:r0 + rc], non_blocking=True)
+                self.e_in[k].record(self.s_in)
+            sk = self.s_k[k & 1]
+            T = _Tables(cfg.slab(cfg.row_begin + r0, rc), obj_type, w2o, material, light, camera, None)
+            keep.append(T)
+            if T.B != 1:
+                raise ValueError('StreamedFusedMSE renders one scene (use render_fused_mse for scene batches)')
+            sk.wait_event(self.e_in[k])
+            with torch.cuda.device(dev):
+                rc_ = L.rrt_render_fused_mse(C.byref(T.desc), self.dev_target[r0:r0 + rc].data_ptr(), cw,
+                                             self.dev_image[r0:r0 + rc].data_ptr() if self.dev_image is not None else None,
+                                             None, self.losses[k:k + 1].data_ptr(), self.grads[k].data_ptr(),
+                                             C.c_void_p(sk.cuda_stream))
+            nat.check(rc_, 'rrt_render_fused_mse')
+            self.e_k[k].record(sk)
+            if image_host is not None:
+                self.s_out.wait_event(self.e_k[k])
+                with torch.cuda.stream(self.s_out):
+                    image_host[r0:r0 + rc].copy_(self.dev_image[r0:r0 + rc], non_blocking=True)
+        self.e_out.record(self.s_out)
+        for e in self.e_k:                            # join
+            cur.wait_event(e)
+        cur.wait_event(self.e_out)
+        return self.losses.sum(), self.grads.sum(0)
 
 
 def split_grad(flat, N):

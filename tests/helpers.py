@@ -4,12 +4,17 @@ import torch
 
 from reversible_raytracer_b200.render import RenderConfig
 
+# Set by the parity module's `kernel_choice` fixture: True forces the general 8-rays-per-thread
+# kernel where the small-scene kernel would be chosen, so every case is checked on both.
+NO_SMALL = False
+
 
 def to_device(ps, device, with_jitter=True):
     """oracle.oracle_c.PackedScene -> (cfg, obj_type, w2o, material, light, camera, jitter)."""
     cfg = RenderConfig(n=ps.n, samples=ps.samples, shader=ps.shader, transpose=ps.transpose,
                        max_depth=ps.max_depth, camera_grad=ps.camera_grad, seed=ps.seed,
-                       row_begin=ps.row_begin, row_count=ps.row_count, scene_begin=getattr(ps, 'scene_begin', 0))
+                       row_begin=ps.row_begin, row_count=ps.row_count, scene_begin=getattr(ps, 'scene_begin', 0),
+                       no_small=int(NO_SMALL))
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
     w2o = t(ps.w2o) if ps.B > 1 else t(ps.w2o[0])
     jitter = None

@@ -10,9 +10,18 @@ import torch
 
 from oracle import oracle_c as oc, scenes
 from reversible_raytracer_b200 import render as R
+import helpers
 from helpers import to_device, block_rel_err
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=['auto', 'general'], autouse=True)
+def kernel_choice(request, monkeypatch):
+    """Every case runs twice: with the library's own kernel choice (small scenes take the
+    one-ray-per-thread kernel) and with the general kernel forced (RRT_FLAG_NO_SMALL)."""
+    monkeypatch.setattr(helpers, 'NO_SMALL', request.param == 'general')
+    return request.param
 
 PIX_RTOL, PIX_ATOL, GRAD_TOL = 1e-4, 1e-5, 1e-3
 
@@ -380,3 +389,84 @@ def test_culling_full_size_slab(cuda):
         b = R.render_forward(replace(cfg, cull=1), *args, None, want_hit=True, want_tmin=True)
         for x, y in zip(a, b):
             assert torch.equal(x, y)
+
+
+def test_streamed_host_buffers_equal_single_launch(cuda):
+    """render.StreamedFusedMSE (row slabs pipelined over copy-in / kernel / copy-out streams,
+    target and image in pinned HOST memory) == one whole-image launch: image bit-identical,
+    loss / gradients up to the summation order; and against the oracle."""
+    spec = scenes.stress(n=96, num_objects=40, samples=4, seed=11)
+    ps = oc.PackedScene.from_spec(spec, camera_grad=0)
+    cfg, ot, w2o, mat, light, cam, _ = to_device(ps, cuda, with_jitter=False)
+    cfg = R.RenderConfig(n=cfg.n, samples=cfg.samples, shader=cfg.shader, transpose=cfg.transpose, seed=77)
+    target = torch.rand((cfg.n, cfg.n, 3), device=cuda)
+    loss0, grad0, img0, _ = R.render_fused_mse(cfg, ot, w2o, mat, light, cam, target, want_image=True)
+    pin_t = target.cpu().pin_memory()
+    pin_i = torch.empty_like(pin_t).pin_memory()
+    for slabs in (1, 3, 5):
+        st = R.StreamedFusedMSE(cfg, w2o.shape[0], cuda, slabs=slabs)
+        for rep in range(2):                     # second call reuses buffers / events
+            pin_i.zero_()
+            loss, grad = st(ot, w2o, mat, light, cam, pin_t, pin_i)
+            torch.cuda.synchronize()
+            assert torch.equal(pin_i, img0.cpu())
+            np.testing.assert_allclose(float(loss), float(loss0), rtol=1e-6)
+            s = float(grad0.abs().max())
+            assert float((grad - grad0).abs().max()) <= 1e-4 * s
+    with pytest.raises(ValueError):
+        st(ot, w2o, mat, light, cam, target.cpu(), pin_i)       # not pinned
+
+
+def test_sparse_upstream_gradient_early_out(cuda):
+    """Reverse pass with two non-zero upstream pixels (optimize_brightness.py:51): CTAs without
+    upstream gradient leave early; result == oracle and == the dense kernel path on the same
+    gradient with a tiny value added everywhere (which disables the early-out)."""
+    ps = oc.PackedScene.from_spec(scenes.optimize_brightness(n=128, samples=4, seed=5), camera_grad=0)
+    cfg, ot, w2o, mat, light, cam, jit = to_device(ps, cuda)
+    dl = np.zeros((1, 128, 128, 3), dtype=np.float32)
+    dl[0, 90, 85] = -1.0
+    dl[0, 50, 90] = -1.0
+    g_o = oc.render_backward(ps, dl)[0]
+    g = R.render_backward(cfg, ot, w2o, mat, light, cam, torch.from_numpy(dl).to(cuda), None, jit).double().cpu().numpy()
+    assert np.max(np.abs(g - g_o)) <= 1e-3 * np.max(np.abs(g_o))
+    assert np.max(np.abs(g_o)) > 0
+    g_zero = R.render_backward(cfg, ot, w2o, mat, light, cam, torch.zeros((1, 128, 128, 3), device=cuda), None, jit)
+    assert float(g_zero.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('name', ['C1_optimize_brightness', 'C3_match_mirror_square', 'C4_orbit_view0', 'S8', 'S1'])
+def test_small_and_general_kernels_agree(name, cuda):
+    """The small-scene kernel and the general kernel share the canonical routines and the
+    sample summation order: masks, tmin AND pixels are bit-identical; gradients agree up to
+    the reduction order."""
+    from dataclasses import replace
+    ps = oc.PackedScene.from_spec(CASES[name](), camera_grad=1)
+    cfg, ot, w2o, mat, light, cam, jit = to_device(ps, cuda)
+    a = R.render_forward(replace(cfg, no_small=0), ot, w2o, mat, light, cam, jit, want_hit=True, want_tmin=True)
+    b = R.render_forward(replace(cfg, no_small=1), ot, w2o, mat, light, cam, jit, want_hit=True, want_tmin=True)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    assert torch.equal(a[0], b[0]), float((a[0] - b[0]).abs().max())
+    target = torch.zeros_like(a[0])
+    l0, g0, _, _ = R.render_fused_mse(replace(cfg, no_small=0), ot, w2o, mat, light, cam, target, None, jit)
+    l1, g1, _, _ = R.render_fused_mse(replace(cfg, no_small=1), ot, w2o, mat, light, cam, target, None, jit)
+    np.testing.assert_allclose(float(l0.sum()), float(l1.sum()), rtol=1e-6)
+    assert float((g1 - g0).abs().max()) <= 1e-4 * float(g0.abs().max())
+
+
+def test_fused_many_samples_small_scene(cuda):
+    """S = 16 fused: beyond the general fused kernel's 8 samples, served by the small-scene kernel."""
+    ps = oc.PackedScene.from_spec(scenes.stress(n=20, num_objects=9, samples=16), camera_grad=1)
+    img_o, _, _ = oc.render_forward(ps, want_aux=False)
+    target = np.clip(img_o + 0.1, 0, 1).astype(np.float32)
+    image_o, hit_o, loss_o, grad_o = oc.render_fused_mse(ps, target)
+    cfg, ot, w2o, mat, light, cam, jit = to_device(ps, cuda)
+    if cfg.no_small:
+        with pytest.raises(Exception):
+            R.render_fused_mse(cfg, ot, w2o, mat, light, cam, torch.from_numpy(target).to(cuda), None, jit)
+        return
+    loss, grad, image, hit = R.render_fused_mse(cfg, ot, w2o, mat, light, cam, torch.from_numpy(target).to(cuda),
+                                                None, jit, want_image=True, want_hit=True)
+    assert np.array_equal(hit.cpu().numpy().reshape(hit_o.shape), hit_o)
+    np.testing.assert_allclose(image.cpu().numpy().reshape(image_o.shape), image_o, rtol=PIX_RTOL, atol=PIX_ATOL)
+    np.testing.assert_allclose(float(loss), loss_o[0], rtol=1e-4)
+    compare_grads(grad.cpu().numpy().astype(np.float64), grad_o[0], ps.N)
