@@ -91,6 +91,8 @@ class ChainProgram(object):
                 ops.append([kind_id[kind] | (nat.CHAIN_INVERT if inv else 0), offs[0][1],
                             offs[1][1] if len(offs) > 1 else 0, 0])
             begin.append(len(ops))
+        if not ops:                                # identity-only chains: keep the table non-empty (non-NULL)
+            ops = [[0, 0, 0, 0]]
         self.ops = torch.tensor(np.asarray(ops, dtype=np.int32).reshape(-1, 4), device=device)
         self.chain_begin = torch.tensor(np.asarray(begin, dtype=np.int32), device=device)
         self.const_block = torch.tensor(np.concatenate(consts) if consts else np.zeros(0, dtype=np.float32),

@@ -50,8 +50,13 @@ class GDOptimizer(object):
             grads = torch.autograd.grad(value, tVars, allow_unused=True)
             with torch.no_grad():
                 for var, g in zip(tVars, grads):
-                    if g is not None:
-                        var.sub_(step_lr * g.to(var.device))
+                    if g is None:
+                        continue
+                    g = g.to(var.device)
+                    if isinstance(step_lr, torch.Tensor):       # captured step: lr lives on the device
+                        var.addcmul_(g, step_lr.to(g.dtype), value=-1.0)      # one kernel per variable
+                    else:
+                        var.sub_(g, alpha=float(step_lr))
             return value
 
         def capture():

@@ -184,10 +184,19 @@ class Scene(object):
         from .chain import ChainProgram
         st = dict(device=device, shapes=shapes, w2o=[s.w2o for s in shapes], camera=self.camera, light=self.lights[0])
         st['obj_type'] = torch.tensor([s.kind for s in shapes], dtype=torch.int32, device=device)
-        try:
-            st['prog'] = ChainProgram([s.w2o for s in shapes] + [self.camera.o2w], device) if device.type == 'cuda' else None
-        except ValueError:
-            st['prog'] = None                      # explicit-matrix transforms: torch path
+        # two programs, so that the shapes' rows ARE the renderer's w2o table (no slicing of a
+        # joint output and no scatter of its gradient), and a constant camera is evaluated once
+        st['prog'] = st['cam_prog'] = None
+        if device.type == 'cuda':
+            try:
+                st['prog'] = ChainProgram([s.w2o for s in shapes], device) if shapes else None
+            except ValueError:
+                pass                               # explicit-matrix transforms: torch path
+            try:
+                st['cam_prog'] = ChainProgram([self.camera.o2w], device)
+            except ValueError:
+                pass
+        st['cam_t'] = None
         st['mat'] = None
         if shapes and not any(s.material.dynamic for s in shapes):
             st['mat'] = torch.stack([s.material.packed(device) for s in shapes]).detach()
@@ -202,12 +211,10 @@ class Scene(object):
         st = self._static(device)
         N = len(self.shapes)
         if st['prog'] is not None:
-            rows = st['prog'].evaluate()           # one kernel: every w2o + the camera matrix
-            w2o, cam_rows = rows[:N], rows[N]
+            w2o = st['prog'].evaluate()            # one kernel: every shape's w2o rows
         else:
             w2o = torch.stack([s.w2o.m[:3, :].reshape(12).to(device) for s in self.shapes]) if N else \
                 torch.zeros((0, 12), dtype=torch.float32, device=device)
-            cam_rows = self.camera.o2w.m[:3, :].reshape(12).to(device)
         if st['mat'] is not None:
             mat = st['mat']
         elif N:
@@ -215,7 +222,16 @@ class Scene(object):
         else:
             mat = torch.zeros((0, 7), dtype=torch.float32, device=device)
         light = st['light_t'] if st['light_t'] is not None else self.lights[0].packed(device)
-        cam = torch.cat([cam_rows, self.camera.look_at.reshape(3).to(device)])
+        look = self.camera.look_at
+        cam_static = st['cam_prog'] is not None and not st['cam_prog'].dynamic and not look.requires_grad
+        if cam_static and st['cam_t'] is not None:
+            cam = st['cam_t']                      # constant camera: packed once
+        else:
+            cam_rows = st['cam_prog'].evaluate()[0] if st['cam_prog'] is not None else \
+                self.camera.o2w.m[:3, :].reshape(12).to(device)
+            cam = torch.cat([cam_rows, look.reshape(3).to(device)])
+            if cam_static:
+                st['cam_t'] = cam = cam.detach()
         return st['obj_type'], w2o, mat, light, cam
 
     CULL_MIN_OBJECTS = 32    # Scene.build turns conservative culling on from this many shapes
