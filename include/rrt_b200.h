@@ -78,6 +78,18 @@ extern "C" {
 /* Force the general 8-rays-per-thread kernel even where the small-scene (one ray per thread)
  * kernel would be chosen.  Results agree; this exists for A/B measurements and tests. */
 #define RRT_FLAG_NO_SMALL 2
+/* Hard shadows (the reference's call site is commented out, scene.py:41-45,
+ * and its helper is broken, shape.py:100-106, so PARITY IS WEAKLY PINNED: the formula of
+ * Sphere.shadow, shape.py:85-97, is followed, evaluated in the frame of the shadow caster).
+ * A winning ray with parameter t is in shadow if for some OTHER SPHERE k (list order)
+ *     y = o'_k + t d'_k ;  x = y . (-Lhat) ;  dec = (x^2 - y.y) + 1 ;
+ *     dec > 0  and  (-x - sqrt(dec)) >= 0
+ * (unit sphere of the caster's object space, WORLD-space light direction like the shading,
+ * squares cast no shadow: Square has no shadow method).  A shadowed ray shades to (0,0,0)
+ * and carries no gradient (masks are constants).  hit_index keeps the winner and gets
+ * RRT_HIT_SHADOWED or-ed in, so the shadow mask is observable and testable bit for bit. */
+#define RRT_FLAG_SHADOWS 4
+#define RRT_HIT_SHADOWED 0x40000000
 
 #define RRT_OK 0
 #define RRT_ERR_INVALID (-1)   /* bad argument (message in rrt_last_error)            */

@@ -52,6 +52,7 @@ typedef struct {
     float look[3];
     float L[3], I[3];
     double Lh[3], Ln; /* normalised light direction, |L| (scene.py:83-86) */
+    float U[3];       /* -Lhat in float32, canonical order (shadow test only) */
 } orc_glob;
 
 /* ---- jitter RNG shared (by specification) with the CUDA kernels ------------- */
@@ -108,6 +109,10 @@ static void orc_prep(const rrt_scene* sc, int scene, orc_obj* objs, orc_glob* g)
     }
     g->Ln = sqrt((double)g->L[0] * g->L[0] + (double)g->L[1] * g->L[1] + (double)g->L[2] * g->L[2]);
     for (int r = 0; r < 3; r++) g->Lh[r] = g->L[r] / g->Ln;
+    {   /* canonical float32 -Lhat for the shadow mask: sqrt and div round-to-nearest */
+        float ln = sqrtf(FMAF(g->L[2], g->L[2], FMAF(g->L[1], g->L[1], g->L[0] * g->L[0])));
+        for (int r = 0; r < 3; r++) g->U[r] = -(g->L[r] / ln);
+    }
     for (int k = 0; k < sc->num_objects; k++) {
         const float* w = sc->w2o + (size_t)scene * sc->w2o_scene_stride + (size_t)k * RRT_W2O_STRIDE;
         const float* m = sc->material + (size_t)scene * sc->material_scene_stride + (size_t)k * RRT_MAT_STRIDE;
@@ -187,6 +192,25 @@ static inline int orc_sweep(const orc_obj* objs, int N, const float dw[3], float
     }
     *tmin_out = tmin;
     return idx;
+}
+
+/* Hard shadows, RRT_FLAG_SHADOWS (include/rrt_b200.h): the formula of Sphere.shadow,
+ * shape.py:85-97, at the call site scene.py:41-45 (commented out in the reference), in
+ * canonical float32 order.  `t` is the winner's ray parameter; the surface point is taken
+ * in the CASTER's object space (y = o'_k + t d'_k = w2o_k (c + t d)). */
+static inline int orc_shadowed(const orc_obj* objs, int N, int winner, const float dw[3], float t, const float U[3]) {
+    for (int k = 0; k < N; k++) {
+        if (k == winner || objs[k].type != RRT_OBJ_SPHERE) continue;
+        const orc_obj* o = &objs[k];
+        float d[3], y[3];
+        orc_mat3(o->A, dw, d);
+        for (int c = 0; c < 3; c++) y[c] = FMAF(t, d[c], o->o[c]);
+        float x = FMAF(y[2], U[2], FMAF(y[1], U[1], y[0] * U[0]));
+        float yy = FMAF(y[2], y[2], FMAF(y[1], y[1], y[0] * y[0]));
+        float dec = FMAF(x, x, -yy) + 1.0f;
+        if (dec > 0.0f && (-x - sqrtf(dec)) >= 0.0f) return 1;
+    }
+    return 0;
 }
 
 /* vectorisable sphere-only sweep used when every object is a sphere (bit-identical:
@@ -427,8 +451,11 @@ static int orc_run(const rrt_scene* sc, int mode, float* image, int32_t* hit_out
                     for (int s = 0; s < S; s++) {
                         orc_pixel_ray(sc, &g, scene, a, b, s, rc[s], dws[s]);
                         size_t ro = (((size_t)scene * S + s) * rows + al) * n + b;
+                        int shadowed = 0;
                         if (hit_in) {
                             idx[s] = hit_in[ro];
+                            if (idx[s] >= 0 && (idx[s] & RRT_HIT_SHADOWED)) { shadowed = 1; idx[s] &= ~RRT_HIT_SHADOWED; }
+                            if (idx[s] >= N) idx[s] = -1;
                             tm[s] = INFINITY;
                         } else {
                             idx[s] = all_sph ? orc_sweep_spheres(objs, &soa, N, dws[s], &tm[s])
@@ -439,10 +466,15 @@ static int orc_run(const rrt_scene* sc, int mode, float* image, int32_t* hit_out
                             orc_hit h;
                             orc_shade_rec r;
                             tm[s] = orc_test(&objs[idx[s]], dws[s], &h);
-                            orc_promote(&objs[idx[s]], dws[s], &h);
-                            orc_shade(sc, &objs[idx[s]], &g, &h, &r, rgbs[s]);
+                            if (!hit_in && (sc->flags & RRT_FLAG_SHADOWS) && isfinite(tm[s]))
+                                shadowed = orc_shadowed(objs, N, idx[s], dws[s], tm[s], g.U);
+                            if (!shadowed) {
+                                orc_promote(&objs[idx[s]], dws[s], &h);
+                                orc_shade(sc, &objs[idx[s]], &g, &h, &r, rgbs[s]);
+                            }
                         }
-                        if (hit_out) hit_out[ro] = idx[s];
+                        if (hit_out) hit_out[ro] = (shadowed && idx[s] >= 0) ? (idx[s] | RRT_HIT_SHADOWED) : idx[s];
+                        if (shadowed) idx[s] = -1;   /* (0,0,0) and no gradient from here on */
                         if (tmin_out) tmin_out[ro] = tm[s];
                         for (int c = 0; c < 3; c++) pix[c] += rgbs[s][c]; /* scene.py:49 */
                     }

@@ -65,6 +65,9 @@ def use_all_cores():
     return num_threads()
 
 
+FLAG_SHADOWS, HIT_SHADOWED = 4, 0x40000000
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -75,7 +78,7 @@ class PackedScene:
 
     def __init__(self, n, samples, obj_type, w2o, material, light, camera, shader,
                  transpose, max_depth=1.0, jitter_x=None, jitter_y=None, seed=0,
-                 camera_grad=0, row_begin=0, row_count=0, scene_begin=0):
+                 camera_grad=0, row_begin=0, row_count=0, scene_begin=0, shadows=0):
         self.n, self.samples = int(n), int(samples)
         self.obj_type = np.ascontiguousarray(obj_type, dtype=np.int32)
         self.N = int(self.obj_type.shape[0])
@@ -93,6 +96,7 @@ class PackedScene:
         self.row_begin = int(row_begin)
         self.row_count = int(row_count)
         self.scene_begin = int(scene_begin)
+        self.shadows = int(shadows)
         self.rows = self.row_count if self.row_count > 0 else self.n - self.row_begin
         self.jitter_x = None if jitter_x is None else np.ascontiguousarray(jitter_x, dtype=np.float32)
         self.jitter_y = None if jitter_y is None else np.ascontiguousarray(jitter_y, dtype=np.float32)
@@ -116,14 +120,15 @@ class PackedScene:
             np.concatenate([spec['light_dir'], spec['light_int']]), camera, spec['shader'],
             transpose=1 if root else 0, max_depth=spec.get('max_depth', 1.0),
             jitter_x=jx, jitter_y=jy, seed=use_rng_seed or 0,
-            camera_grad=(0 if root else 1) if camera_grad is None else camera_grad)
+            camera_grad=(0 if root else 1) if camera_grad is None else camera_grad,
+            shadows=int(bool(spec.get('shadows', 0))))
 
     def slab(self, row_begin, row_count):
         jx = None if self.jitter_x is None else self.jitter_x.reshape(-1, self.n, self.n, self.samples)[:, row_begin:row_begin + row_count]
         jy = None if self.jitter_y is None else self.jitter_y.reshape(-1, self.n, self.n, self.samples)[:, row_begin:row_begin + row_count]
         return PackedScene(self.n, self.samples, self.obj_type, self.w2o, self.material, self.light,
                            self.camera, self.shader, self.transpose, self.max_depth, jx, jy, self.seed,
-                           self.camera_grad, row_begin, row_count)
+                           self.camera_grad, row_begin, row_count, shadows=self.shadows)
 
     def desc(self):
         def stride(a, per):
@@ -133,6 +138,7 @@ class PackedScene:
         d.shader, d.transpose = self.shader, self.transpose
         d.row_begin, d.row_count = self.row_begin, self.row_count
         d.scene_begin = self.scene_begin
+        d.flags = FLAG_SHADOWS if self.shadows else 0
         d.max_depth, d.camera_grad, d.seed = self.max_depth, self.camera_grad, self.seed
         d.obj_type, d.w2o, d.material = _ptr(self.obj_type), _ptr(self.w2o), _ptr(self.material)
         d.light, d.camera = _ptr(self.light), _ptr(self.camera)

@@ -168,6 +168,27 @@ def sphere_normals(w2o, origin, rays):
         return proj / np.sqrt(np.sum(proj ** 2, 2))[:, :, None]
 
 
+def sphere_shadow(points, light_dir):
+    """Sphere.shadow, shape.py:85-97: -1 where the point is not in this (unit) sphere's
+    shadow, else the first root (>= 0 means in shadow at the call site, scene.py:44-45).
+    `points` = "vector from points to our center", i.e. in THIS sphere's object space."""
+    y = points
+    with np.errstate(all='ignore'):
+        x = np.tensordot(y, -1 * normed_dir(light_dir), 1)
+        decider = np.square(x) - np.sum(np.multiply(y, y), 2) + 1
+        bad = np.isnan(decider) | (decider <= 0)
+        return np.where(bad, -1, -x - np.sqrt(decider))
+
+
+def surface_pts(w2o, origin, rays, distance):
+    """Sphere.surface_pts, shape.py:100-106 with its undefined name `rays` read as
+    rf.rays (the only reading that type-checks): rf.origin + stabilized * rf.rays.
+    `w2o` is the frame the points are wanted in (see render(): the shadow CASTER's)."""
+    o, r = apply_rayfield(w2o, origin, rays)
+    stabilized = np.where(np.isinf(distance), F32(1000), distance)
+    return o + stabilized[:, :, None] * r
+
+
 def square_hit(rays, origin):
     """Square._hit, shape.py:25-40 (strict inequalities)."""
     with np.errstate(all='ignore'):
@@ -258,6 +279,8 @@ def render(spec, return_aux=True):
     hit_index = np.full((S, n, n), -1, dtype=np.int32)
     tmins = np.full((S, n, n), np.inf, dtype=F32)
     shader = spec['shader']
+    shadows = bool(spec.get('shadows', 0))
+    shadow_mask = np.zeros((S, n, n), dtype=bool)
     for s in range(S):
         sdx = (jx[:, :, s] + F32(s)) / F32(S)          # scene.py:31
         sdy = (jy[:, :, s] + F32(s)) / F32(S)          # scene.py:32
@@ -280,13 +303,29 @@ def render(spec, return_aux=True):
                 shad = phong_shade(nrm, dist, spec['material'][k], spec['light_dir'],
                                    spec['light_int'], spec['look_at'],
                                    specular=(shader == 'phong'))
+            in_shadow = np.zeros((n, n), dtype=bool)
+            if shadows:
+                # scene.py:41-45 (commented out in the reference): for each shape != obj draw
+                # its shadow on obj.  Points are taken in the CASTER's frame -- the reading
+                # under which Sphere.shadow's "vector from points to our center" holds;
+                # Square has no shadow method, so squares cast none.
+                for k2 in range(len(spec['obj_type'])):
+                    if k2 == k or spec['obj_type'][k2] != SPHERE:
+                        continue
+                    pts = surface_pts(spec['w2o'][k2], origin, rays, dist)
+                    lit = sphere_shadow(pts, spec['light_dir']) < 0
+                    shad = np.where(lit[:, :, None], shad, 0.0)
+                    in_shadow |= ~lit
             take = dist < min_d                                      # scene.py:46 (strict)
             img_s = np.where(take[:, :, None], shad, img_s)
             min_d = np.where(take, dist, min_d)                      # scene.py:47
             hit_index[s][take] = k
+            shadow_mask[s][take] = in_shadow[take]
         tmins[s] = min_d
         image = image + img_s                                        # scene.py:49
     image = image / S                                                # scene.py:50
     if return_aux:
+        if shadows:
+            hit_index = np.where(shadow_mask & (hit_index >= 0), hit_index | 0x40000000, hit_index)
         return image, hit_index, tmins
     return image

@@ -105,3 +105,23 @@ def stress(n=256, num_objects=64, samples=4, seed=1234, general=False, jitter_se
         shapes.append((on.SPHERE, t, _mat(col[k], 0.3, kd[k], ka[k], 50.)))
     return spec_from(n, samples, shapes, ((-1., -1., 2.), (0.961, 1., 0.87)), 'phong',
                      seed=jitter_seed)
+
+
+def shadow_scene(n=64, samples=4, seed=0, shader='phong', general=False):
+    """Shadows (scene.py:41-45 + shape.py:85-97, not live in the reference):
+    two small spheres between the light and a big sphere / a big square, light like C1."""
+    m1 = _mat((0.2, 0.9, 0.4), 0.3, 0.7, 0.5, 50.)
+    m2 = _mat((0.87, 0.1, 0.507), 0.3, 0.9, 0.4, 50.)
+    m3 = _mat((0.5, 0.5, 0.9), 0.2, 0.8, 0.4, 30.)
+    big = _chain(on.translate((-0.3, -0.3, 5.0)), on.scale((1.2, 1.2, 1.2)))
+    c1 = _chain(on.translate((0.25, 0.2, 3.6)), on.scale((0.3, 0.3, 0.3)))
+    c2 = on.translate((0.9, -0.8, 4.0))
+    if general:
+        c2 = _chain(c2, on.rotate(30, (0, 0, 1)), on.scale((0.5, 0.25, 0.4)))
+    else:
+        c2 = _chain(c2, on.scale((0.35, 0.35, 0.35)))
+    wall = _chain(on.translate((0, 0, 6.5)), on.scale((7, 7, 1)))
+    spec = spec_from(n, samples, [(on.SPHERE, c1, m2), (on.SPHERE, big, m1), (on.SQUARE, wall, m3), (on.SPHERE, c2, m2)],
+                     ((-1., -1., 2.), (0.961, 1., 0.87)), shader, max_depth=8.0, seed=seed)
+    spec['shadows'] = 1
+    return spec

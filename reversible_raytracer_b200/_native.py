@@ -91,7 +91,8 @@ def lib():
 EXPORTS = ['rrt_version', 'rrt_last_error', 'rrt_render_forward', 'rrt_render_backward',
            'rrt_render_fused_mse', 'rrt_measure_fp32_peak', 'rrt_chain_forward', 'rrt_chain_backward', 'rrt_primary_rays']
 
-FLAG_CULL, FLAG_NO_SMALL = 1, 2
+FLAG_CULL, FLAG_NO_SMALL, FLAG_SHADOWS = 1, 2, 4
+HIT_SHADOWED = 0x40000000
 CHAIN_TRANSLATE, CHAIN_SCALE, CHAIN_ROTATE, CHAIN_INVERT, CHAIN_MAX_OPS = 1, 2, 3, 0x100, 8
 
 

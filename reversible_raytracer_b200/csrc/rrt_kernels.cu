@@ -169,7 +169,14 @@ struct Globals {       // per-scene constants, held in shared memory
     float look[3];
     float L[3], I[3];
     float Lh[3], Ln;
+    float U[3];        // -Lhat in canonical float32 order (shadow mask only)
 };
+
+// canonical -Lhat (bit-identical to orc_prep in oracle/oracle_c.c): RN sqrt and div
+__device__ __forceinline__ void canon_to_light(const float* L, float* U) {
+    const float ln = __fsqrt_rn(__fmaf_rn(L[2], L[2], __fmaf_rn(L[1], L[1], __fmul_rn(L[0], L[0]))));
+    U[0] = -__fdiv_rn(L[0], ln); U[1] = -__fdiv_rn(L[1], ln); U[2] = -__fdiv_rn(L[2], ln);
+}
 
 __device__ __forceinline__ void make_obj(const float* __restrict__ w, int type, const float* ct, Obj& ob) {
     float m[12];
@@ -368,6 +375,44 @@ __device__ __forceinline__ void sweep_mixed(const float4* __restrict__ tab, int 
         if (!(flags & 1)) gmax = object_max_det<true>((uint32_t)__cvta_generic_to_shared(tab + 4 * k), rp, 0.0f);
         if (gmax > 0.0f) rare_group(tab, k, 1, kbase, dw, tmin, idx);
     }
+}
+
+// ---------------------------------------------------------------- hard shadows (RRT_FLAG_SHADOWS)
+// Sphere.shadow, shape.py:85-97, at the (commented-out) call site scene.py:41-45, in the
+// caster's object space and canonical float32 order -- bit-identical to orc_shadowed in
+// oracle/oracle_c.c.  `t` is the winner's ray parameter.
+__device__ __forceinline__ bool shadow_test(const float4* __restrict__ rec, float wx, float wy, float wz, float t,
+                                            const float* U) {
+    Obj ob;
+    load_rec(rec, ob);
+    if (ob.flags & 1) return false;            // Square has no shadow method: casts none
+    const float d0 = dot3_canon(ob.a[0], ob.a[1], ob.a[2], wx, wy, wz);
+    const float d1 = dot3_canon(ob.a[3], ob.a[4], ob.a[5], wx, wy, wz);
+    const float d2 = dot3_canon(ob.a[6], ob.a[7], ob.a[8], wx, wy, wz);
+    const float y0 = __fmaf_rn(t, d0, ob.o[0]), y1 = __fmaf_rn(t, d1, ob.o[1]), y2 = __fmaf_rn(t, d2, ob.o[2]);
+    const float x = dot3_canon(y0, y1, y2, U[0], U[1], U[2]);
+    const float yy = dot3_canon(y0, y1, y2, y0, y1, y2);
+    const float dec = __fadd_rn(__fmaf_rn(x, x, -yy), 1.0f);
+    return dec > 0.0f && __fsub_rn(-x, __fsqrt_rn(dec)) >= 0.0f;
+}
+
+// General kernel: tests the thread's winning rays against one staged chunk of objects.
+// Scalar and divergent on purpose -- shadows are an opt-in extension outside the
+// roofline-accountable sweep; out of line so that the hot loop's registers are untouched.
+__device__ __noinline__ unsigned shadow_chunk(const float4* __restrict__ tab, int cnt, int kbase, const float* dw,
+                                              const float* tmin, const int* idx, const float* U, unsigned shadowed) {
+#pragma unroll 1
+    for (int r = 0; r < kRays; r++) {
+        const int win = idx[r];
+        if (win < 0 || (shadowed >> r & 1u)) continue;
+        const float t = tmin[r], wx = dw[r], wy = dw[kRays + r], wz = dw[2 * kRays + r];
+#pragma unroll 1
+        for (int k = 0; k < cnt; k++) {
+            if (kbase + k == win) continue;
+            if (shadow_test(tab + 4 * k, wx, wy, wz, t, U)) { shadowed |= 1u << r; break; }
+        }
+    }
+    return shadowed;
 }
 
 // ---------------------------------------------------------------- shading (float32)
@@ -653,6 +698,7 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
             float ln = sqrtf(g.L[0] * g.L[0] + g.L[1] * g.L[1] + g.L[2] * g.L[2]);  // scene.py:83-86
             g.Ln = ln;
             g.Lh[0] = g.L[0] / ln; g.Lh[1] = g.L[1] / ln; g.Lh[2] = g.L[2] / ln;
+            canon_to_light(g.L, g.U);
             chunk_class = 0;
             cam_identity_s = (g.C[0] == 1.f && g.C[4] == 1.f && g.C[8] == 1.f && g.C[1] == 0.f && g.C[2] == 0.f &&
                               g.C[3] == 0.f && g.C[5] == 0.f && g.C[6] == 0.f && g.C[7] == 0.f);
@@ -845,7 +891,9 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                 if (row_ok && b < n && s < S)
 {
                     const int kk = P.hit_in[(((size_t)scene * S + s) * P.rows + al) * n + b];
-                    l_idx[r] = (kk >= 0 && kk < N) ? kk : -1;      // never trust an index buffer blindly
+                    // never trust an index buffer blindly; a winner stored with RRT_HIT_SHADOWED
+                    // (>= N) shades to zero and carries no gradient
+                    l_idx[r] = (kk >= 0 && kk < N) ? kk : -1;
                 }
             }
         } else {
@@ -890,6 +938,25 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
             }
         }
 
+        // ---- hard shadows (opt-in): second pass over the object table for the winners
+        unsigned shadowed = 0;
+        if ((sc.flags & RRT_FLAG_SHADOWS) && !use_stored) {
+#pragma unroll 1
+            for (int kb = 0; kb < N; kb += kObjChunk) {
+                const int cnt = min(kObjChunk, N - kb);
+                if (N > kObjChunk) {                       // otherwise the whole table is still staged
+                    __syncthreads();
+                    for (int k = tid; k < cnt; k += blockDim.x) {
+                        Obj ob;
+                        make_obj(w2o + (size_t)(kb + k) * RRT_W2O_STRIDE, sc.obj_type[kb + k], g.ct, ob);
+                        store_rec(smem_tab + 4 * k, ob);
+                    }
+                    __syncthreads();
+                }
+                shadowed = shadow_chunk(smem_tab, cnt, kb, l_dw, l_tmin, l_idx, g.U, shadowed);
+            }
+        }
+
         // ---- outputs of the sweep
         if (MODE != MODE_BWD && (P.hit_out || P.tmin_out)) {
 #pragma unroll 1
@@ -897,10 +964,15 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                 const int px = r / SPT, s = sc0 * SPT + r % SPT, b = b0 + px;
                 if (row_ok && b < n && s < S) {
                     size_t ro = (((size_t)scene * S + s) * P.rows + al) * n + b;
-                    if (P.hit_out) __stcs(P.hit_out + ro, l_idx[r]);
+                    if (P.hit_out) __stcs(P.hit_out + ro, l_idx[r] | ((shadowed >> r & 1u) ? RRT_HIT_SHADOWED : 0));
                     if (MODE == MODE_FWD && P.tmin_out) __stcs(P.tmin_out + ro, l_tmin[r]);
                 }
             }
+        }
+        if (shadowed) {                                    // (0,0,0) and no gradient from here on
+#pragma unroll 1
+            for (int r = 0; r < kRays; r++)
+                if (shadowed >> r & 1u) l_idx[r] = -1;
         }
 
         // ---- shade the winners (forward value)
@@ -1109,12 +1181,13 @@ __global__ void __launch_bounds__(kSmallThreads) render_small_kernel(const __gri
     const int scene = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned full = 0xffffffffu;
-    const long long rays_scene = (long long)P.rows * n * S;
-    const long long gid = (long long)blockIdx.x * kSmallThreads + tid;
+    // 32-bit index arithmetic (the launcher guarantees rows*n*S < 2^31; S is a power of two)
+    const unsigned rays_scene = (unsigned)P.rows * (unsigned)n * (unsigned)S;
+    const unsigned gid = blockIdx.x * kSmallThreads + tid;
     const bool active = gid < rays_scene;
-    const int s = (int)(gid % S);
-    const long long pl = gid / S;                       // slab-local pixel index
-    const int al = active ? (int)(pl / n) : 0, b = active ? (int)(pl % n) : 0;
+    const int s = (int)(gid & (unsigned)(S - 1));
+    const unsigned pl = gid >> (31 - __clz(S));         // slab-local pixel index
+    const int al = active ? (int)(pl / (unsigned)n) : 0, b = active ? (int)(pl - (unsigned)al * (unsigned)n) : 0;
     const int a = sc.row_begin + al;
     const size_t po = (((size_t)scene * P.rows + al) * n + b) * 3;
     const float inv = 1.0f / (float)S;
@@ -1154,7 +1227,11 @@ __global__ void __launch_bounds__(kSmallThreads) render_small_kernel(const __gri
             const float ln = sqrtf(l0 * l0 + l1 * l1 + l2 * l2);          // scene.py:83-86
             g.L[lane] = li[lane];
             g.Lh[lane] = li[lane] / ln;
-            if (lane == 0) g.Ln = ln;
+            if (lane == 0) {
+                g.Ln = ln;
+                const float L3[3] = {l0, l1, l2};
+                canon_to_light(L3, g.U);
+            }
         }
     }
 
@@ -1190,8 +1267,8 @@ __global__ void __launch_bounds__(kSmallThreads) render_small_kernel(const __gri
     const bool use_stored = (MODE == MODE_BWD) && (P.hit_in != nullptr);
     if (use_stored && active) {
         const int kk = P.hit_in[(((size_t)scene * S + s) * P.rows + al) * n + b];
-        stored = (kk >= 0 && kk < N) ? kk : -1;          // never trust an index buffer blindly
-    }
+        stored = (kk >= 0 && kk < N) ? kk : -1;          // never trust an index buffer blindly; a winner
+    }                                                    // flagged RRT_HIT_SHADOWED (>= N) carries no gradient
     __syncthreads();
 
     // camera.o2w (orbit_experiments/scene.py:80); the fma chain returns its input for C = I
@@ -1215,11 +1292,18 @@ __global__ void __launch_bounds__(kSmallThreads) render_small_kernel(const __gri
             if (t < tmin) { tmin = t; idx = k; }
         }
     }
+    bool in_shadow = false;
+    if ((sc.flags & RRT_FLAG_SHADOWS) && !use_stored && idx >= 0) {   // hard shadows (opt-in)
+#pragma unroll 1
+        for (int k = 0; k < N && !in_shadow; k++)
+            if (k != idx) in_shadow = shadow_test(tab + 4 * k, wx, wy, wz, tmin, g.U);
+    }
     if (MODE != MODE_BWD && active) {
         const size_t ro = (((size_t)scene * S + s) * P.rows + al) * n + b;
-        if (P.hit_out) P.hit_out[ro] = idx;
+        if (P.hit_out) P.hit_out[ro] = idx | (in_shadow ? RRT_HIT_SHADOWED : 0);
         if (MODE == MODE_FWD && P.tmin_out) P.tmin_out[ro] = tmin;
     }
+    if (in_shadow) idx = -1;                             // (0,0,0) and no gradient from here on
 
     // ---- winner: hit record, shading
     Obj ob;
@@ -1643,7 +1727,7 @@ bool use_small_kernel(const KParams& P) {
         limit = e ? atoll(e) : kSmallDefaultMaxRays;
     }
     const long long rays_scene = (long long)P.rows * sc.n * S;
-    if (rays_scene > 0x7fffffffLL * kSmallThreads / 2) return false;
+    if (rays_scene >= 0x7fffffffLL - kSmallThreads) return false;    // 32-bit ray index in the kernel
     return rays_scene * sc.num_scenes <= limit;
 }
 

@@ -122,7 +122,11 @@ class Camera(object):
 class Scene(object):
     """scene.py:11-52"""
 
-    def __init__(self, shapes, lights, camera, shader):
+    def __init__(self, shapes, lights, camera, shader, shadows=False):
+        """`shadows=True` switches on the hard-shadow pass the reference has commented out
+        (scene.py:41-45, Sphere.shadow shape.py:85-97; semantics in include/rrt_b200.h) --
+        an extension, off by default like in the reference."""
+        self.shadows = bool(shadows)
         self.shapes = shapes
         self.lights = lights
         self.camera = camera
@@ -245,7 +249,8 @@ class Scene(object):
                               transpose=0 if cam.has_transform else 1,
                               max_depth=float(getattr(self.shader, 'maxDepth', 1.0)),
                               camera_grad=1 if cam.has_transform else 0,
-                              cull=int(len(self.shapes) >= self.CULL_MIN_OBJECTS if cull is None else bool(cull)))
+                              cull=int(len(self.shapes) >= self.CULL_MIN_OBJECTS if cull is None else bool(cull)),
+                              shadows=int(self.shadows))
 
     # -- rendering ------------------------------------------------------------------
     def build(self, antialias_samples=4, jitter=None, seed=None, cull=None):

@@ -14,7 +14,7 @@ def to_device(ps, device, with_jitter=True):
     cfg = RenderConfig(n=ps.n, samples=ps.samples, shader=ps.shader, transpose=ps.transpose,
                        max_depth=ps.max_depth, camera_grad=ps.camera_grad, seed=ps.seed,
                        row_begin=ps.row_begin, row_count=ps.row_count, scene_begin=getattr(ps, 'scene_begin', 0),
-                       no_small=int(NO_SMALL))
+                       no_small=int(NO_SMALL), shadows=int(getattr(ps, 'shadows', 0)))
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
     w2o = t(ps.w2o) if ps.B > 1 else t(ps.w2o[0])
     jitter = None

@@ -286,3 +286,22 @@ def test_camera_rays_after_build_match_reference_semantics(cuda):
     kernel_hit = (hit_o[0][3] == 0)
     # object 0 is hit wherever it wins; where it is hit but loses, another object is nearer
     assert np.all(dense_hit[kernel_hit])
+
+
+def test_scene_shadows_flag(cuda):
+    """Scene(..., shadows=True): the drop-in API reaches the shadow pass; gradients flow only
+    through lit rays (the shadowed region of the image is exactly zero)."""
+    m1 = Material((0.2, 0.9, 0.4), 0.3, 0.7, 0.5, 50.)
+    m2 = Material((0.87, 0.1, 0.507), 0.3, 0.9, 0.4, 50.)
+    c = torch.tensor([0.25, 0.2, 3.6], device=cuda, requires_grad=True)
+    shapes = [Sphere(translate(c) * scale((0.3, 0.3, 0.3)), m2),
+              Sphere(translate((-0.3, -0.3, 5.0)) * scale((1.2, 1.2, 1.2)), m1)]
+    light = [Light((-1., -1., 2.), (0.961, 1., 0.87))]
+    lit = Scene(shapes, light, Camera(64, 64), PhongShader()).build(seed=1)
+    sc = Scene(shapes, light, Camera(64, 64), PhongShader(), shadows=True)
+    img = sc.build(seed=1)
+    darker = (lit.detach().sum(-1) > 0) & (img.detach().sum(-1) < lit.detach().sum(-1) - 1e-6)
+    assert int(darker.sum()) > 30                       # a shadow was cast
+    assert bool((img.detach() <= lit.detach() + 1e-6).all())
+    img.sum().backward()
+    assert c.grad is not None and bool(torch.isfinite(c.grad).all()) and float(c.grad.abs().max()) > 0

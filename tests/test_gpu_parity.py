@@ -470,3 +470,48 @@ def test_fused_many_samples_small_scene(cuda):
     np.testing.assert_allclose(image.cpu().numpy().reshape(image_o.shape), image_o, rtol=PIX_RTOL, atol=PIX_ATOL)
     np.testing.assert_allclose(float(loss), loss_o[0], rtol=1e-4)
     compare_grads(grad.cpu().numpy().astype(np.float64), grad_o[0], ps.N)
+
+
+SHADOWED = 0x40000000
+
+
+@pytest.mark.parametrize('case', ['phong', 'depth', 'general', 'many'])
+def test_shadows_parity(case, cuda):
+    """RRT_FLAG_SHADOWS (parity weakly pinned by the reference): winners AND
+    the shadow flag bit-exact against the canonical C oracle, pixels / loss / gradients at the
+    usual tolerances; forward, fused and backward (stored and re-swept winners)."""
+    if case == 'many':                                   # > 512 objects: re-staged table chunks
+        spec = scenes.stress(n=24, num_objects=700)
+        spec['shadows'] = 1
+    else:
+        spec = scenes.shadow_scene(shader='depth' if case == 'depth' else 'phong', general=(case == 'general'))
+    ps = oc.PackedScene.from_spec(spec, camera_grad=1)
+    img_o, hit_o = check_forward_flags(ps, cuda)
+    assert int(((hit_o >= 0) & ((hit_o & SHADOWED) != 0)).sum()) > 20
+    rng = np.random.RandomState(3)
+    target = np.clip(img_o + rng.normal(0, 0.1, img_o.shape), 0, 1).astype(np.float32)
+    image_o, hit_f, loss_o, grad_o = oc.render_fused_mse(ps, target)
+    cfg, ot, w2o, mat, light, cam, jit = to_device(ps, cuda)
+    assert cfg.shadows == 1
+    loss, grad, image, hit = R.render_fused_mse(cfg, ot, w2o, mat, light, cam, torch.from_numpy(target).to(cuda),
+                                                None, jit, want_image=True, want_hit=True)
+    assert np.array_equal(hit.cpu().numpy().reshape(hit_f.shape), hit_f)
+    np.testing.assert_allclose(image.cpu().numpy().reshape(image_o.shape), image_o, rtol=PIX_RTOL, atol=PIX_ATOL)
+    np.testing.assert_allclose(float(loss), loss_o[0], rtol=1e-4)
+    compare_grads(grad.cpu().numpy().astype(np.float64), grad_o[0], ps.N)
+    dl = rng.normal(0, 1, img_o.shape).astype(np.float32)
+    gb_o = oc.render_backward(ps, dl, hit_o)
+    for stored in (True, False):
+        h = torch.from_numpy(hit_o).to(cuda) if stored else None
+        gb = R.render_backward(cfg, ot, w2o, mat, light, cam, torch.from_numpy(dl).to(cuda), h, jit)
+        compare_grads(gb.cpu().numpy().astype(np.float64), gb_o[0], ps.N)
+
+
+def check_forward_flags(ps, dev):
+    img_o, hit_o, tmin_o = oc.render_forward(ps)
+    cfg, ot, w2o, mat, light, cam, jit = to_device(ps, dev)
+    img, hit, tmin = R.render_forward(cfg, ot, w2o, mat, light, cam, jit, want_hit=True, want_tmin=True)
+    assert np.array_equal(hit.cpu().numpy().reshape(hit_o.shape), hit_o), 'winners + shadow flags must be bit-exact'
+    assert np.array_equal(tmin.cpu().numpy().reshape(tmin_o.shape).view(np.uint32), tmin_o.view(np.uint32))
+    np.testing.assert_allclose(img.cpu().numpy().reshape(img_o.shape), img_o, rtol=PIX_RTOL, atol=PIX_ATOL)
+    return img_o, hit_o
