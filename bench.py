@@ -5,7 +5,8 @@ Metric (BASELINE.json): Mrays/s forward+backward on the synthetic stress scene C
 (4096 x 4096 image, 4 anti-alias samples, 1024 spheres), one "step" = one fused
 forward + squared-error loss + reverse pass over the whole image; with N GPUs the
 image's row slabs are sharded across ranks (total work fixed => strong scaling)
-and the small parameter-gradient vector + loss are summed with one NCCL allreduce.
+and the small parameter-gradient vector + loss are summed by ONE kernel of our own over
+NVLink peer memory (rrt_peer_allreduce; NCCL allreduce as the fallback).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            this framework
     python bench.py --impl reference [...]                         CPU restatement of the
@@ -229,6 +230,33 @@ def run_b200(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     G = nat.grad_size(N)
     red = torch.zeros(G + 2, dtype=torch.float64, device=dev)
+    # the one exchange step: our kernel over NVLink peer memory (sharding.PeerSum ->
+    # rrt_peer_allreduce); NCCL allreduce if the symmetric allocation is refused on this box
+    peer, collective = None, 'none'
+    if world > 1:
+        from reversible_raytracer_b200 import sharding as Sh
+        ok = torch.ones(1, device=dev)
+        try:
+            if os.environ.get('RRT_BENCH_NCCL'):
+                raise RuntimeError('RRT_BENCH_NCCL set')
+            peer = Sh.PeerSum(G, 1, dev)
+        except Exception as e:          # noqa: BLE001
+            ok.zero_()
+            sys.stderr.write('rank %d: PeerSum unavailable (%r), using NCCL\n' % (rank, e))
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok) < 1:
+            peer = None
+        collective = ('rrt_peer_allreduce: one own kernel per rank over NVLink peer memory, %d float64 per step' % (G + 1)
+                      if peer is not None else '1 NCCL allreduce of %d float64 per step' % (G + 2))
+
+    def exchange(loss, grad):
+        if peer is not None:
+            l, g = peer(grad, loss.reshape(1))
+            return l[0], g
+        red[:G] = grad
+        red[G] = loss
+        dist.all_reduce(red)            # one NCCL allreduce: gradient vector + loss
+        return red[G], red[:G]
 
     kev = []
 
@@ -241,10 +269,7 @@ def run_b200(args):
         if world > 1:
             k1.record()
             kev.append((k0, k1))
-            red[:G] = grad
-            red[G] = loss
-            dist.all_reduce(red)            # one NCCL allreduce: gradient vector + loss
-            return red[G], red[:G]
+            return exchange(loss, grad)
         return loss, grad
 
     for _ in range(max(args.warmup, 3)):
@@ -293,11 +318,9 @@ def run_b200(args):
         loss, grad, _, _ = R.render_fused_mse(cfg, obj_type, dd['w2o'], dd['material'], dd['light'], dd['camera'], target,
                                                want_image=True)
         if world > 1:
-            red[:G] = grad
-            red[G] = loss
-            dist.all_reduce(red)
-            pin_grad.copy_(red[:G].float(), non_blocking=True)
-            pin_loss.copy_(red[G:G + 1], non_blocking=True)
+            l, g = exchange(loss, grad)
+            pin_grad.copy_(g.float(), non_blocking=True)
+            pin_loss.copy_(l.reshape(1), non_blocking=True)
         else:
             pin_grad.copy_(grad, non_blocking=True)
             pin_loss.copy_(loss.reshape(1), non_blocking=True)
@@ -334,11 +357,9 @@ def run_b200(args):
 
     def finish(loss, grad):
         if world > 1:
-            red[:G] = grad
-            red[G] = loss
-            dist.all_reduce(red)
-            pin_grad.copy_(red[:G].float(), non_blocking=True)
-            pin_loss.copy_(red[G:G + 1], non_blocking=True)
+            l, g = exchange(loss, grad)
+            pin_grad.copy_(g.float(), non_blocking=True)
+            pin_loss.copy_(l.reshape(1), non_blocking=True)
         else:
             pin_grad.copy_(grad, non_blocking=True)
             pin_loss.copy_(loss.reshape(1), non_blocking=True)
@@ -419,7 +440,7 @@ def run_b200(args):
                    vs_baseline=None, dtype='f32', data='synthetic',
                    config=dict(workload=WORKLOAD if not args.general else WORKLOAD.replace('translate*scale', 'translate*rotate*scale'),
                                n=n, samples=S, objects=N, sharding='row slabs, %d rows per GPU' % rows_per,
-                               collective='1 NCCL allreduce of %d float64 per step' % (G + 2) if world > 1 else 'none',
+                               collective=collective,
                                l2='256 MiB flush write between timed iterations (outside the timed intervals)',
                                jitter='in-kernel counter RNG, seed 4321'),
                    e2e=dict(value=e2e_streamed_value, unit='Mrays/s', h2d_bytes_per_step=h2d + full_bytes,
@@ -432,7 +453,7 @@ def run_b200(args):
                                 value=e2e_value, unit='Mrays/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                                 note='target stays resident like the reference\'s compiled-in constant '
                                      '(match_mirror.py:45); only the parameter tables go up and loss + gradients come back')),
-                   gpu_launches=2 * args.steps, clocks=sampler.summary())
+                   gpu_launches=(2 + (1 if peer is not None else 0)) * args.steps, clocks=sampler.summary())
         if kernel_ms is not None:
             out['rank0_step_ms'] = [round(a.elapsed_time(b), 3) for a, b in evs]
             out['per_rank_render_ms'] = kernel_ms     # fused kernel + finalize per rank, before the allreduce

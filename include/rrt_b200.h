@@ -219,6 +219,26 @@ int rrt_chain_backward(const int32_t* ops, const int32_t* chain_begin, int num_c
                        const float* g_out, float* g_values, int num_values, void* stream);
 
 /*
+ * The one exchange step of the sharded path (the reference is single-process,
+ * so there is no reference interface to cite): sum of the per-rank vector
+ * [grad (n float32) | loss (nloss float64)] over the GPUs of one box, done by ONE kernel per
+ * rank over NVLink peer memory (push to every peer's slot, per-source epoch flags, sum in
+ * rank order => identical bits on every rank), instead of an NCCL allreduce.
+ *   peer_buf   DEVICE array [world] of pointers: rank p's exchange buffer as mapped into THIS
+ *              process (rrt_peer_buffer_bytes(n, nloss, world) bytes each, symmetric allocation,
+ *              e.g. torch.distributed._symmetric_memory / cuMem + IPC)
+ *   peer_sig   DEVICE array [world] of pointers: rank p's flag area (rrt_peer_signal_bytes()
+ *              bytes, ZEROED once before first use, never touched by the host afterwards)
+ *   out        [n + nloss] float64 (local): the sums
+ * All ranks must call it the same number of times with the same sizes; the kernels of
+ * different ranks wait for each other on the device (no host synchronisation).
+ */
+size_t rrt_peer_buffer_bytes(int n, int nloss, int world);
+size_t rrt_peer_signal_bytes(void);
+int rrt_peer_allreduce(const float* grad, const double* loss, int n, int nloss, void* const* peer_buf,
+                       void* const* peer_sig, int rank, int world, double* out, void* stream);
+
+/*
  * FP32 pipe micro-benchmark used as the roofline denominator (MEASURED_PEAKS.json
  * has no FP32 entry).  mode 0 = scalar FFMA, 1 = packed FFMA2 (fma.rn.f32x2),
  * 2 = FFMA2 + one ALU-pipe FMNMX3 per 4 (diagnostic: shows FFMA2 does not dual-issue).

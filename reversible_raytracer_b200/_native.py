@@ -81,6 +81,12 @@ def lib():
         L.rrt_chain_forward.argtypes = [P, P, C.c_int, P, P, P]
         L.rrt_chain_backward.argtypes = [P, P, C.c_int, P, P, P, C.c_int, P]
         L.rrt_measure_fp32_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), P]
+        L.rrt_peer_buffer_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.rrt_peer_buffer_bytes.restype = C.c_size_t
+        L.rrt_peer_signal_bytes.argtypes = []
+        L.rrt_peer_signal_bytes.restype = C.c_size_t
+        L.rrt_peer_allreduce.argtypes = [P, P, C.c_int, C.c_int, P, P, C.c_int, C.c_int, P, P]
+        L.rrt_peer_allreduce.restype = C.c_int
         for f in (L.rrt_render_forward, L.rrt_render_backward, L.rrt_render_fused_mse, L.rrt_measure_fp32_peak,
                   L.rrt_chain_forward, L.rrt_chain_backward, L.rrt_primary_rays):
             f.restype = C.c_int
@@ -89,7 +95,8 @@ def lib():
 
 
 EXPORTS = ['rrt_version', 'rrt_last_error', 'rrt_render_forward', 'rrt_render_backward',
-           'rrt_render_fused_mse', 'rrt_measure_fp32_peak', 'rrt_chain_forward', 'rrt_chain_backward', 'rrt_primary_rays']
+           'rrt_render_fused_mse', 'rrt_measure_fp32_peak', 'rrt_chain_forward', 'rrt_chain_backward', 'rrt_primary_rays',
+           'rrt_peer_allreduce', 'rrt_peer_buffer_bytes', 'rrt_peer_signal_bytes']
 
 FLAG_CULL, FLAG_NO_SMALL, FLAG_SHADOWS = 1, 2, 4
 HIT_SHADOWED = 0x40000000

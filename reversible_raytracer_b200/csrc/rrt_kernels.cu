@@ -1486,6 +1486,73 @@ __global__ void finalize_grads(const __grid_constant__ KParams P) {
     }
 }
 
+// ---------------------------------------------------------------- gradient exchange over peer memory
+// The one exchange step of the sharded path (row slabs / scene ranges per GPU): every rank holds
+// a small vector [gradient (float32) | loss (float64)] and all ranks need the sum.  Instead of
+// an NCCL allreduce (plus the two copy kernels that pack its buffer) ONE kernel per rank
+//   1. PUSHES its values, converted to float64, into slot[rank] of every peer's buffer with
+//      plain stores through the NVLink peer mapping,
+//   2. publishes a per-(CTA, source) flag on every peer (fence + release store) and waits for
+//      the same flags from all peers (acquire loads) -- CTA c only depends on CTA c of the
+//      peers, so no grid-wide barrier is needed,
+//   3. sums the `world` slots in RANK ORDER (every rank gets the same bits; deterministic).
+// Buffers alternate by epoch parity: a rank can only start epoch e+2 after every peer has
+// finished reading epoch e (it needs their epoch e+1 flags first), so two copies suffice.
+// Flags carry the epoch number, one per source, so a fast peer's next epoch cannot be
+// mistaken for a slow peer's current one.
+constexpr int kPeerCtas = 16;
+constexpr int kPeerMaxWorld = 16;
+constexpr int kPeerEpochOffset = kPeerCtas * kPeerMaxWorld;   // per-CTA epoch counters (local use only)
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) peer_allreduce_kernel(const float* __restrict__ grad, const double* __restrict__ loss,
+                                                             int n, int nloss, void* const* __restrict__ peer_buf,
+                                                             void* const* __restrict__ peer_sig, int rank, int world,
+                                                             double* __restrict__ out) {
+    const int cta = blockIdx.x, tid = threadIdx.x;
+    unsigned* sig_local = reinterpret_cast<unsigned*>(peer_sig[rank]);
+    __shared__ unsigned epoch_s;
+    if (tid == 0) {
+        epoch_s = sig_local[kPeerEpochOffset + cta] + 1u;
+        sig_local[kPeerEpochOffset + cta] = epoch_s;
+    }
+    __syncthreads();
+    const unsigned epoch = epoch_s;
+    const int total = n + nloss;
+    const int per = (total + gridDim.x - 1) / gridDim.x;
+    const int lo = cta * per, hi = min(total, lo + per);
+    const size_t slot = ((size_t)(epoch & 1u) * world + rank) * (size_t)total;
+    // 1. push
+    for (int i = lo + tid; i < hi; i += blockDim.x) {
+        const double v = i < n ? (double)grad[i] : loss[i - n];
+        for (int p = 0; p < world; p++) reinterpret_cast<double*>(peer_buf[p])[slot + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    // 2. publish + wait
+    if (tid < world) {
+        st_release_sys(reinterpret_cast<unsigned*>(peer_sig[tid]) + cta * kPeerMaxWorld + rank, epoch);
+        const unsigned* mine = sig_local + cta * kPeerMaxWorld + tid;
+        while ((int)(ld_acquire_sys(mine) - epoch) < 0) { }
+    }
+    __syncthreads();
+    // 3. sum in rank order
+    const double* local = reinterpret_cast<const double*>(peer_buf[rank]) + (size_t)(epoch & 1u) * world * (size_t)total;
+    for (int i = lo + tid; i < hi; i += blockDim.x) {
+        double sum = 0.0;
+        for (int p = 0; p < world; p++) sum += __ldcg(local + (size_t)p * total + i);
+        out[i] = sum;
+    }
+}
+
 // ---------------------------------------------------------------- parameter -> matrix chain
 // Affine 3x4 matrices [A|b] (bottom row 0 0 0 1 implied).  See include/rrt_b200.h.
 struct Aff {
@@ -1879,6 +1946,25 @@ int rrt_chain_backward(const int32_t* ops, const int32_t* chain_begin, int num_c
     chain_backward_kernel<<<(num_chains + 63) / 64, 64, 0, st>>>(ops, chain_begin, num_chains, values, g_out, g_values);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "chain backward launch: %s", cudaGetErrorString(e));
+    return RRT_OK;
+}
+
+size_t rrt_peer_buffer_bytes(int n, int nloss, int world) {
+    if (n < 0 || nloss < 0 || world < 1) return 0;
+    return (size_t)2 * (size_t)world * (size_t)(n + nloss) * sizeof(double);
+}
+
+size_t rrt_peer_signal_bytes(void) { return (size_t)(kPeerEpochOffset + kPeerCtas) * sizeof(unsigned); }
+
+int rrt_peer_allreduce(const float* grad, const double* loss, int n, int nloss, void* const* peer_buf,
+                       void* const* peer_sig, int rank, int world, double* out, void* stream) {
+    if (world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world) return fail(RRT_ERR_INVALID, "bad rank/world (world <= 16)");
+    if (n < 0 || nloss < 0 || n + nloss <= 0) return fail(RRT_ERR_INVALID, "nothing to reduce");
+    if ((n > 0 && !grad) || (nloss > 0 && !loss) || !peer_buf || !peer_sig || !out)
+        return fail(RRT_ERR_INVALID, "rrt_peer_allreduce: NULL argument");
+    peer_allreduce_kernel<<<kPeerCtas, 256, 0, (cudaStream_t)stream>>>(grad, loss, n, nloss, peer_buf, peer_sig, rank, world, out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "peer allreduce launch: %s", cudaGetErrorString(e));
     return RRT_OK;
 }
 
