@@ -132,3 +132,37 @@ class MGDAutoOptimizer(object):
             def opt(lr):
                 return step(ae.cost(train_data[0]), lr, 1.0)
         return opt
+
+    def optimizeADAM(self, train_data, beta1=0.1, beta2=0.001, epsilon=1e-8, l=1e-8):
+        """optimize.py:86-124 (root variant): the ADAM form of the autoencoder trainer, with the
+        reference's own constants and its 5x step on 1-D parameters.  Returns
+        (opt(lr) -> cost, get_grad, get_gradb) like the reference (gradients of the last
+        capsule's weight and bias)."""
+        ae = self.ae
+        for p in ae.params:
+            p.requires_grad_(True)
+        m = [torch.zeros_like(p) for p in ae.params]
+        v = [torch.zeros_like(p) for p in ae.params]
+        state = dict(t=1.0)
+
+        def grads_now():
+            return torch.autograd.grad(ae.cost(train_data[0]), ae.params, allow_unused=True)
+
+        def opt(lr):
+            cost = ae.cost(train_data[0])
+            grads = torch.autograd.grad(cost, ae.params, allow_unused=True)
+            t = state['t']
+            with torch.no_grad():
+                for p, g, m_, v_ in zip(ae.params, grads, m, v):
+                    if g is None:
+                        continue
+                    b1_t = 1 - (1 - beta1) * (l ** (t - 1))
+                    m_.copy_(b1_t * g + (1 - b1_t) * m_)
+                    v_.copy_(beta2 * g * g + (1 - beta2) * v_)
+                    m_hat = m_ / (1 - (1 - beta1) ** t)
+                    v_hat = v_ / (1 - (1 - beta2) ** t)
+                    p.sub_((5.0 if p.dim() == 1 else 1.0) * lr * m_hat / (torch.sqrt(v_hat) + epsilon))
+            state['t'] = t + 1
+            return float(cost.detach())
+
+        return opt, (lambda: grads_now()[-2]), (lambda: grads_now()[-1])

@@ -223,6 +223,30 @@ def test_mgd_auto_optimizer():
     assert not torch.equal(ae2.params[1], b0)
 
 
+def test_mgd_auto_optimizer_adam():
+    """optimizeADAM (optimize.py:86-124): the reference's update rule with its own constants."""
+    class AE:
+        def __init__(self):
+            self.params = [torch.tensor([[1.0, 2.0]]), torch.tensor([0.5])]
+        def cost(self, X):
+            y = (self.params[0] * X).sum() + self.params[1].sum()
+            return y * y
+    ae = AE()
+    opt, get_grad, get_gradb = MGDAutoOptimizer(ae).optimizeADAM(torch.tensor([[1.0, 1.0]]))
+    g0 = get_grad().clone()
+    assert g0.shape == (1, 2) and get_gradb().shape == (1,)
+    costs = [opt(0.05) for _ in range(40)]
+    assert costs[-1] < 0.05 * costs[0]
+    # first step by hand: t=1 => b1_t = 1-(1-.1)*1 = .1, m = .1 g, v = .001 g^2, bias-corrected m/.1, v/.001
+    ae2 = AE()
+    opt2, _, _ = MGDAutoOptimizer(ae2).optimizeADAM(torch.tensor([[1.0, 1.0]]))
+    w0, b0 = ae2.params[0].clone(), ae2.params[1].clone()
+    opt2(0.01)
+    g = 2 * 3.5                                        # d/dw of ((1+2)+0.5)^2 w.r.t. each weight
+    np.testing.assert_allclose((w0 - ae2.params[0]).detach().numpy(), 0.01 * g / (abs(g) + 1e-8) * np.ones((1, 2)), rtol=1e-5)
+    np.testing.assert_allclose((b0 - ae2.params[1]).detach().numpy(), [5 * 0.01 * g / (abs(g) + 1e-8)], rtol=1e-5)
+
+
 # ---- sharding
 def test_row_slabs_partition():
     for n, world in ((4096, 8), (4096, 3), (7, 8), (64, 1), (33, 4)):
