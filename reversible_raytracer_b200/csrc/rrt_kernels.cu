@@ -977,16 +977,22 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
 
         // ---- shade the winners (forward value)
         if (MODE != MODE_BWD) {
+            // a thread's rays (samples of one pixel, neighbouring pixels) mostly share their
+            // winner: the object record and material are re-fetched only when it changes
+            Obj ob;
+            float m7[7];
+            int k_loaded = -1;
 #pragma unroll 1
             for (int r = 0; r < kRays; r++) {
                 const int k = l_idx[r];
                 if (k < 0) continue;
-                Obj ob;
-                make_obj(w2o + (size_t)k * RRT_W2O_STRIDE, sc.obj_type[k], g.ct, ob);
-                const float* mat = mats + (size_t)k * RRT_MAT_STRIDE;
-                float m7[7];
+                if (k != k_loaded) {
+                    make_obj(w2o + (size_t)k * RRT_W2O_STRIDE, sc.obj_type[k], g.ct, ob);
+                    const float* mat = mats + (size_t)k * RRT_MAT_STRIDE;
 #pragma unroll
-                for (int q = 0; q < 7; q++) m7[q] = __ldg(mat + q);
+                    for (int q = 0; q < 7; q++) m7[q] = __ldg(mat + q);
+                    k_loaded = k;
+                }
                 const float dwx = l_dw[r], dwy = l_dw[kRays + r], dwz = l_dw[2 * kRays + r];
                 HitRec h;
                 obj_test(ob, dwx, dwy, dwz, h);
@@ -1074,14 +1080,15 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
         if (MODE != MODE_FWD) {
             // one extra (sentinel) trip after the last ray of the last sample chunk flushes the
             // running accumulator, so the warp-level flush code exists exactly once
+            Obj ob;
+            float m7[7];
+            int k_loaded = -1;                       // see the shading loop
 #pragma unroll 1
             for (int r = 0; r <= kRays; r++) {
                 const bool fin = (r == kRays);
                 if (fin && !last_chunk) break;
                 int k = fin ? -1 : l_idx[r];
                 HitRec h;
-                Obj ob;
-                float m7[7];
                 float dwx = 0.f, dwy = 0.f, dwz = 0.f;
                 float gc[3] = {0.f, 0.f, 0.f};
                 if (!fin) {
@@ -1094,7 +1101,13 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                 // losses such as optimize_brightness.py:51 touch two pixels): skip it
                 if (gc[0] == 0.f && gc[1] == 0.f && gc[2] == 0.f) k = -1;
                 if (k >= 0) {
-                    make_obj(w2o + (size_t)k * RRT_W2O_STRIDE, sc.obj_type[k], g.ct, ob);
+                    if (k != k_loaded) {
+                        make_obj(w2o + (size_t)k * RRT_W2O_STRIDE, sc.obj_type[k], g.ct, ob);
+                        const float* mat = mats + (size_t)k * RRT_MAT_STRIDE;
+#pragma unroll
+                        for (int q = 0; q < 7; q++) m7[q] = __ldg(mat + q);
+                        k_loaded = k;
+                    }
                     dwx = l_dw[r]; dwy = l_dw[kRays + r]; dwz = l_dw[2 * kRays + r];
                     obj_test(ob, dwx, dwy, dwz, h);
                     if (!(h.t < __int_as_float(0x7f800000))) k = -1;  // stale stored winner
@@ -1106,9 +1119,6 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                     acc_key = -1;
                 }
                 if (k >= 0) {
-                    const float* mat = mats + (size_t)k * RRT_MAT_STRIDE;
-#pragma unroll
-                    for (int q = 0; q < 7; q++) m7[q] = __ldg(mat + q);
                     ShadeRec sr;
                     float rgb[3];
                     shade(sc.shader, sc.max_depth, ob, m7, g, h, sr, rgb);
