@@ -144,7 +144,18 @@ typedef struct rrt_scene {
      * in-kernel jitter RNG, so that a sharded batch draws the same jitter as the whole one. */
     int32_t scene_begin;
     int32_t flags;        /* RRT_FLAG_* */
+
+    /* Optional [B][N][RRT_RECORD_FLOATS] float32 table of sweep records (the per-object
+     * constants of the ray-object test: A's diagonal, o' = A.c + b, 1 - o'.o', the
+     * off-diagonals), as filled by rrt_build_records() for THIS scene's current w2o / camera
+     * tables; 16-byte aligned.  With it the render kernels stage the object table in shared
+     * memory by one TMA bulk copy (cp.async.bulk + mbarrier) per 512-object chunk instead of
+     * rebuilding the records in every CTA.  NULL => the kernels build the records themselves.
+     * Same bits either way.  Must be rebuilt whenever w2o or the camera changes.               */
+    const float* obj_records;
 } rrt_scene;
+
+#define RRT_RECORD_FLOATS 16
 
 int rrt_version(void);
 const char* rrt_last_error(void);
@@ -185,6 +196,13 @@ int rrt_render_backward(const rrt_scene* scene, const float* dl_dimage,
 int rrt_render_fused_mse(const rrt_scene* scene, const float* target,
                          const float* channel_weight, float* image, int32_t* hit_index,
                          double* loss, float* grad, void* stream);
+
+/*
+ * Fills rrt_scene.obj_records: records [B][N][RRT_RECORD_FLOATS] from scene->w2o, obj_type and
+ * the camera translation (o' = A.c + b, transform.py:44; cc = o'.o' - 1, shape.py:79,82).
+ * One tiny kernel; call it before the render entry points whenever the tables changed.
+ */
+int rrt_build_records(const rrt_scene* scene, float* records, void* stream);
 
 /*
  * Camera.make_rays grid (scene.py:66-72: float64 linspace / normalise, cast to float32),

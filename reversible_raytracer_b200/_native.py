@@ -39,7 +39,7 @@ class RrtScene(C.Structure):
         ('w2o_scene_stride', C.c_int64), ('material_scene_stride', C.c_int64),
         ('light_scene_stride', C.c_int64), ('camera_scene_stride', C.c_int64),
         ('jitter_scene_stride', C.c_int64), ('base_rays', C.c_void_p),
-        ('scene_begin', C.c_int32), ('flags', C.c_int32),
+        ('scene_begin', C.c_int32), ('flags', C.c_int32), ('obj_records', C.c_void_p),
     ]
 
 
@@ -81,6 +81,9 @@ def lib():
         L.rrt_chain_forward.argtypes = [P, P, C.c_int, P, P, P]
         L.rrt_chain_backward.argtypes = [P, P, C.c_int, P, P, P, C.c_int, P]
         L.rrt_measure_fp32_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), P]
+        if hasattr(L, 'rrt_build_records'):      # absent only in older A/B builds loaded through RRT_B200_LIB
+            L.rrt_build_records.argtypes = [C.POINTER(RrtScene), P, P]
+            L.rrt_build_records.restype = C.c_int
         L.rrt_peer_buffer_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
         L.rrt_peer_buffer_bytes.restype = C.c_size_t
         L.rrt_peer_signal_bytes.argtypes = []
@@ -96,7 +99,7 @@ def lib():
 
 EXPORTS = ['rrt_version', 'rrt_last_error', 'rrt_render_forward', 'rrt_render_backward',
            'rrt_render_fused_mse', 'rrt_measure_fp32_peak', 'rrt_chain_forward', 'rrt_chain_backward', 'rrt_primary_rays',
-           'rrt_peer_allreduce', 'rrt_peer_buffer_bytes', 'rrt_peer_signal_bytes']
+           'rrt_peer_allreduce', 'rrt_peer_buffer_bytes', 'rrt_peer_signal_bytes', 'rrt_build_records']
 
 FLAG_CULL, FLAG_NO_SMALL, FLAG_SHADOWS = 1, 2, 4
 HIT_SHADOWED = 0x40000000

@@ -178,7 +178,8 @@ __device__ __forceinline__ void canon_to_light(const float* L, float* U) {
     U[0] = -__fdiv_rn(L[0], ln); U[1] = -__fdiv_rn(L[1], ln); U[2] = -__fdiv_rn(L[2], ln);
 }
 
-__device__ __forceinline__ void make_obj(const float* __restrict__ w, int type, const float* ct, Obj& ob) {
+__device__ __forceinline__ void make_obj(const float* __restrict__ w, int type, const float* ct, Obj& ob,
+                                         bool want_afro = false) {
     float m[12];
     const float4* w4 = reinterpret_cast<const float4*>(w);
     float4 r0 = __ldg(w4), r1 = __ldg(w4 + 1), r2 = __ldg(w4 + 2);
@@ -197,10 +198,11 @@ __device__ __forceinline__ void make_obj(const float* __restrict__ w, int type, 
     ob.ncc = -cc;
     bool general = (ob.a[1] != 0.f) || (ob.a[2] != 0.f) || (ob.a[3] != 0.f) || (ob.a[5] != 0.f) || (ob.a[6] != 0.f) || (ob.a[7] != 0.f);
     ob.flags = (type == RRT_OBJ_SQUARE ? 1 : 0) | (general ? 2 : 0);
+    (void)want_afro;                                   // (dead-code eliminated where afro is unused)
     float f2 = 0.f;
 #pragma unroll
     for (int q = 0; q < 9; q++) f2 += ob.a[q] * ob.a[q];
-    ob.afro = sqrtf(f2);
+    ob.afro = sqrtf(f2);                               // culling bound only
 }
 
 __device__ __forceinline__ void store_rec(float4* rec, const Obj& ob) {
@@ -318,6 +320,40 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
     return v;
+}
+
+// ---------------------------------------------------------------- TMA staging of precomputed records
+// One elected thread arms an mbarrier with the chunk's byte count and issues ONE bulk copy
+// global -> shared (cp.async.bulk, SASS UBLKCP); every thread then waits on the barrier's
+// phase.  Replaces ~90 instructions per object and thread of in-CTA record building.
+__device__ __forceinline__ void mbar_init(uint32_t mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_bulk_load(uint32_t dst, const void* src, unsigned bytes, uint32_t mbar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, unsigned phase) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(mbar), "r"(phase) : "memory");
+    } while (!ok);
+}
+
+// Out of line on purpose, like rare_group: keeps the render kernel's register allocation
+// around the hot loop exactly as it is without the record table.  The barrier's phase lives in
+// shared memory (flipped by thread 0 after the CTA-wide barrier that follows every staging).
+__device__ __noinline__ void stage_records_tma(float4* smem_tab, const float* src, int cnt, unsigned long long* bar,
+                                               const unsigned* phase_s, int* chunk_class, int tid) {
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(bar);
+    const unsigned phase = *phase_s;
+    if (tid == 0) tma_bulk_load((uint32_t)__cvta_generic_to_shared(smem_tab), src, (unsigned)cnt * 64u, mbar);
+    mbar_wait(mbar, phase);
+    // rrt_build_records left the chunk's class bits in the spare slot of its first record
+    if (tid == 0 && chunk_class) *chunk_class |= __float_as_int(smem_tab[3].w);
 }
 
 template <bool GENERAL>
@@ -666,6 +702,8 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
     __shared__ TileCone tcone;
     __shared__ unsigned keepmask[(kObjChunk + 31) / 32];
     __shared__ int chunk_class;  // sticky per CTA: bit0 squares, bit1 general spheres seen
+    __shared__ __align__(8) unsigned long long tma_bar;   // mbarrier of the record-table bulk copies
+    __shared__ unsigned tma_phase;
 
     const rrt_scene& sc = P.sc;
     // S is a compile-time constant except in the generic (PIX=1, SPT=8) instantiation, so the
@@ -705,6 +743,10 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
         }
         if (tid < kSlots) slot_key[tid] = -1;
         if (tid < 9) gglob[tid] = 0.f;
+        if (tid == 0) {
+            tma_phase = 0;
+            if (sc.obj_records) mbar_init((uint32_t)__cvta_generic_to_shared(&tma_bar), 1);
+        }
     }
     for (int q = tid; q < kSlots * kSlotStride; q += blockDim.x) slots[q] = 0.f;
     __syncthreads();
@@ -901,17 +943,25 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
             for (int kb = 0; kb < N; kb += kObjChunk) {
                 const int cnt = min(kObjChunk, N - kb);
                 if (kb > 0 || sc0 > 0) __syncthreads();   // previous chunk fully consumed
+                bool staged_by_tma = false;
                 if (N > kObjChunk || sc0 == 0) {
-                    int cls = 0;                           // bit0: squares present, bit1: general spheres present
-                    for (int k = tid; k < cnt; k += blockDim.x) {
-                        Obj ob;
-                        make_obj(w2o + (size_t)(kb + k) * RRT_W2O_STRIDE, sc.obj_type[kb + k], g.ct, ob);
-                        store_rec(smem_tab + 4 * k, ob);
-                        cls |= ob.flags;
+                    if (sc.obj_records) {                  // precomputed records: one TMA bulk copy
+                        stage_records_tma(smem_tab, sc.obj_records + ((size_t)scene * N + kb) * RRT_RECORD_FLOATS, cnt,
+                                          &tma_bar, &tma_phase, &chunk_class, tid);
+                        staged_by_tma = true;
+                    } else {
+                        int cls = 0;                       // bit0: squares present, bit1: general spheres present
+                        for (int k = tid; k < cnt; k += blockDim.x) {
+                            Obj ob;
+                            make_obj(w2o + (size_t)(kb + k) * RRT_W2O_STRIDE, sc.obj_type[kb + k], g.ct, ob, cull);
+                            store_rec(smem_tab + 4 * k, ob);
+                            cls |= ob.flags;
+                        }
+                        if (cls) atomicOr(&chunk_class, cls);
                     }
-                    if (cls) atomicOr(&chunk_class, cls);
                 }
                 __syncthreads();
+                if (staged_by_tma && tid == 0) tma_phase ^= 1u;   // read again only after the next CTA-wide barrier
                 const int cls = chunk_class;
                 if (cull) {
                     // one ballot word per 32 objects keeps list order without a compaction pass
@@ -946,12 +996,18 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                 const int cnt = min(kObjChunk, N - kb);
                 if (N > kObjChunk) {                       // otherwise the whole table is still staged
                     __syncthreads();
-                    for (int k = tid; k < cnt; k += blockDim.x) {
-                        Obj ob;
-                        make_obj(w2o + (size_t)(kb + k) * RRT_W2O_STRIDE, sc.obj_type[kb + k], g.ct, ob);
-                        store_rec(smem_tab + 4 * k, ob);
+                    if (sc.obj_records) {
+                        stage_records_tma(smem_tab, sc.obj_records + ((size_t)scene * N + kb) * RRT_RECORD_FLOATS, cnt,
+                                          &tma_bar, &tma_phase, nullptr, tid);
+                    } else {
+                        for (int k = tid; k < cnt; k += blockDim.x) {
+                            Obj ob;
+                            make_obj(w2o + (size_t)(kb + k) * RRT_W2O_STRIDE, sc.obj_type[kb + k], g.ct, ob);
+                            store_rec(smem_tab + 4 * k, ob);
+                        }
                     }
                     __syncthreads();
+                    if (sc.obj_records && tid == 0) tma_phase ^= 1u;
                 }
                 shadowed = shadow_chunk(smem_tab, cnt, kb, l_dw, l_tmin, l_idx, g.U, shadowed);
             }
@@ -1412,6 +1468,32 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
     }
 }
 
+// ---------------------------------------------------------------- sweep-record table (for TMA staging)
+// grid = (chunks of kObjChunk objects, scenes).  Writes the 64-byte records the render kernels
+// bulk-copy into shared memory; the chunk's class bits (squares / general spheres present) go
+// into the spare slot of its first record.
+__global__ void __launch_bounds__(128) build_records_kernel(const rrt_scene sc, float* __restrict__ records) {
+    __shared__ int cls_s;
+    const int scene = blockIdx.y, kb = blockIdx.x * kObjChunk, N = sc.num_objects;
+    const int cnt = min(kObjChunk, N - kb);
+    if (threadIdx.x == 0) cls_s = 0;
+    __syncthreads();
+    const float* cam = sc.camera + (size_t)scene * sc.camera_scene_stride;
+    const float ct[3] = {__ldg(cam + 3), __ldg(cam + 7), __ldg(cam + 11)};
+    const float* w2o = sc.w2o + (size_t)scene * sc.w2o_scene_stride;
+    float4* out = reinterpret_cast<float4*>(records + ((size_t)scene * N + kb) * RRT_RECORD_FLOATS);
+    int cls = 0;
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+        Obj ob;
+        make_obj(w2o + (size_t)(kb + k) * RRT_W2O_STRIDE, sc.obj_type[kb + k], ct, ob, true);
+        store_rec(out + 4 * k, ob);
+        cls |= ob.flags;
+    }
+    if (cls) atomicOr(&cls_s, cls);
+    __syncthreads();
+    if (threadIdx.x == 0 && cnt > 0) reinterpret_cast<float*>(out)[15] = __int_as_float(cls_s);
+}
+
 // ---------------------------------------------------------------- primary-ray grid table
 __global__ void primary_rays_kernel(int n, double step, float* __restrict__ out) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
@@ -1797,6 +1879,7 @@ int check_scene(const rrt_scene* sc, int* rows_out) {
     if ((sc->jitter_x == nullptr) != (sc->jitter_y == nullptr)) return fail(RRT_ERR_INVALID, "jitter_x and jitter_y must both be set or both NULL");
     if (((uintptr_t)sc->w2o & 15) || (sc->w2o_scene_stride & 3)) return fail(RRT_ERR_INVALID, "w2o must be 16-byte aligned");
     if (sc->shader == RRT_SHADER_DEPTH && !(sc->max_depth != 0.0f)) return fail(RRT_ERR_INVALID, "max_depth must be non-zero");
+    if ((uintptr_t)sc->obj_records & 15) return fail(RRT_ERR_INVALID, "obj_records must be 16-byte aligned");
     *rows_out = rows;
     return RRT_OK;
 }
@@ -1931,6 +2014,19 @@ int rrt_render_fused_mse(const rrt_scene* scene, const float* target, const floa
     rc = launch<MODE_FUSED>(P, st);
     if (rc) return rc;
     return launch_finalize(P, st);
+}
+
+int rrt_build_records(const rrt_scene* scene, float* records, void* stream) {
+    int rows = 0;
+    int rc = check_scene(scene, &rows);
+    if (rc) return rc;
+    if (scene->num_objects == 0) return RRT_OK;
+    if (!records || ((uintptr_t)records & 15)) return fail(RRT_ERR_INVALID, "records must be a 16-byte aligned device buffer");
+    dim3 grid((scene->num_objects + kObjChunk - 1) / kObjChunk, scene->num_scenes);
+    build_records_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*scene, records);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "build records launch: %s", cudaGetErrorString(e));
+    return RRT_OK;
 }
 
 int rrt_primary_rays(int n, float* out, void* stream) {

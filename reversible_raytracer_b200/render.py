@@ -31,6 +31,7 @@ class RenderConfig:
     scene_begin: int = 0                # multi-GPU scene-batch shard: global index of scene 0 (jitter RNG key)
     cull: int = 0                       # 1: conservative per-tile object culling (bit-identical results, less work)
     no_small: int = 0                   # 1: never take the small-scene (one ray per thread) kernel (A/B, tests)
+    use_records: int = 1                # 0: never precompute / TMA-stage the sweep records (A/B, tests)
     shadows: int = 0                    # 1: hard shadows (scene.py:41-45 + shape.py:85-97; include/rrt_b200.h)
 
     @property
@@ -48,6 +49,9 @@ def _f32(t, name):
         t = t.float()
     return t.contiguous()
 
+
+RECORDS_MIN_N = 64           # from this many objects the sweep records are built once per render
+                             # (rrt_build_records) and TMA-staged, instead of rebuilt in every CTA
 
 _BASE_RAYS = {}
 BASE_RAYS_MAX_N = 1024       # table = 12*n*n bytes; above this the kernels evaluate the grid themselves
@@ -122,6 +126,13 @@ class _Tables:
             self.base = base_rays(cfg.n, self.device)
             d.base_rays = self.base.data_ptr()
         self.desc = d
+        self.records = None
+        if self.N >= RECORDS_MIN_N and cfg.use_records:
+            with torch.cuda.device(self.device):
+                self.records = torch.empty((self.B, self.N, 16), dtype=torch.float32, device=self.device)
+                rc = nat.lib().rrt_build_records(C.byref(d), self.records.data_ptr(), self.stream())
+            nat.check(rc, 'rrt_build_records')
+            d.obj_records = self.records.data_ptr()
 
     def stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

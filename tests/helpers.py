@@ -7,6 +7,7 @@ from reversible_raytracer_b200.render import RenderConfig
 # Set by the parity module's `kernel_choice` fixture: True forces the general 8-rays-per-thread
 # kernel where the small-scene kernel would be chosen, so every case is checked on both.
 NO_SMALL = False
+USE_RECORDS = True     # False: the kernels build the sweep records per CTA instead of TMA-staging a prebuilt table
 
 
 def to_device(ps, device, with_jitter=True):
@@ -14,7 +15,8 @@ def to_device(ps, device, with_jitter=True):
     cfg = RenderConfig(n=ps.n, samples=ps.samples, shader=ps.shader, transpose=ps.transpose,
                        max_depth=ps.max_depth, camera_grad=ps.camera_grad, seed=ps.seed,
                        row_begin=ps.row_begin, row_count=ps.row_count, scene_begin=getattr(ps, 'scene_begin', 0),
-                       no_small=int(NO_SMALL), shadows=int(getattr(ps, 'shadows', 0)))
+                       no_small=int(NO_SMALL), shadows=int(getattr(ps, 'shadows', 0)),
+                       use_records=int(USE_RECORDS))
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
     w2o = t(ps.w2o) if ps.B > 1 else t(ps.w2o[0])
     jitter = None

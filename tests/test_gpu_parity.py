@@ -16,11 +16,14 @@ from helpers import to_device, block_rel_err
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=['auto', 'general'], autouse=True)
+@pytest.fixture(params=['auto', 'general', 'norecords'], autouse=True)
 def kernel_choice(request, monkeypatch):
-    """Every case runs twice: with the library's own kernel choice (small scenes take the
-    one-ray-per-thread kernel) and with the general kernel forced (RRT_FLAG_NO_SMALL)."""
+    """Every case runs three times: with the library's own choices (small scenes take the
+    one-ray-per-thread kernel, >= 64 objects get a prebuilt record table staged by TMA), with
+    the general kernel forced (RRT_FLAG_NO_SMALL), and with the record table switched off (the
+    kernels build the sweep records per CTA)."""
     monkeypatch.setattr(helpers, 'NO_SMALL', request.param == 'general')
+    monkeypatch.setattr(helpers, 'USE_RECORDS', request.param != 'norecords')
     return request.param
 
 PIX_RTOL, PIX_ATOL, GRAD_TOL = 1e-4, 1e-5, 1e-3
@@ -558,3 +561,16 @@ def test_pathological_objects_masks_bit_exact(cuda):
     from dataclasses import replace
     h2 = R.render_forward(replace(cfg, cull=1), ot, w2o, mat, light, cam, jit, want_hit=True)[1]
     assert torch.equal(h2, hit)
+
+
+def test_record_table_is_bit_identical(cuda):
+    """rrt_build_records + TMA staging vs records built per CTA: every output bit-identical
+    (two table chunks, squares + general spheres, culling on and off)."""
+    from dataclasses import replace
+    ps = oc.PackedScene.from_spec(_mixed_many(), camera_grad=1)
+    cfg, ot, w2o, mat, light, cam, jit = to_device(ps, cuda)
+    for cull in (0, 1):
+        a = R.render_forward(replace(cfg, use_records=1, cull=cull), ot, w2o, mat, light, cam, jit, want_hit=True, want_tmin=True)
+        b = R.render_forward(replace(cfg, use_records=0, cull=cull), ot, w2o, mat, light, cam, jit, want_hit=True, want_tmin=True)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)

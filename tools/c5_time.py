@@ -1,7 +1,8 @@
-"""C5 fused step time with a realistic (perturbed) target, like bench.py, plus miss-only."""
+"""C5 fused step time with a realistic (perturbed) target, like bench.py; A/B of the record table."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+from dataclasses import replace
 from reversible_raytracer_b200 import render as R, workloads as W, _native as nat
 from tools.latency import timeit
 dev = torch.device('cuda')
@@ -10,7 +11,8 @@ t = lambda a: torch.from_numpy(a).to(dev)
 args = (t(tb['obj_type']), t(tb['w2o']), t(tb['material']), t(tb['light']), t(tb['camera']))
 cfg = R.RenderConfig(n=4096, samples=4, shader=nat.SHADER_PHONG, transpose=1, seed=4321)
 target = R.render_forward(cfg, args[0], t(tt['w2o']), *args[2:], None, want_hit=False)[0]
-res = []
-for rep in range(3):
-    res.append(timeit(lambda: R.render_fused_mse(cfg, *args, target, want_image=True), warm=2, iters=8) / 1e3)
-print(os.environ.get('RRT_B200_LIB', 'default'), 'C5 fused ms:', ' '.join('%.3f' % x for x in res))
+for rep in range(2):
+    for rec in (1, 0):
+        c = replace(cfg, use_records=rec)
+        ms = timeit(lambda: R.render_fused_mse(c, *args, target, want_image=True), warm=2, iters=8) / 1e3
+        print('use_records=%d C5 fused ms: %.3f' % (rec, ms))
