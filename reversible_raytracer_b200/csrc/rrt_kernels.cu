@@ -53,6 +53,9 @@ constexpr int kRays = RRT_RAYS;   // rays per thread (kRays/2 packed pairs)
 #ifndef RRT_GROUP
 #define RRT_GROUP 4
 #endif
+#ifndef RRT_SWEEP_UNROLL
+#define RRT_SWEEP_UNROLL 1
+#endif
 #ifndef RRT_MIN_BLOCKS
 #define RRT_MIN_BLOCKS 5
 #endif
@@ -381,22 +384,26 @@ __device__ __forceinline__ void sweep_spheres(const float4* __restrict__ tab, in
                                               const float* dw, float* tmin, int* idx) {
     // one induction variable (the shared-window address) and a warp-uniform branch keep the
     // loop control at compare+branch; the object index is only reconstructed on the rare path
+    constexpr int kUnroll = RRT_SWEEP_UNROLL;   // groups per loop trip (loop control amortised over kUnroll*kGroup objects)
     uint32_t rec0 = (uint32_t)__cvta_generic_to_shared(tab);
-    uint32_t rec_end = rec0 + 64u * (uint32_t)(count - count % kGroup);
+    uint32_t rec_end = rec0 + 64u * (uint32_t)(count - count % (kGroup * kUnroll));
     // launder both through an opaque move: otherwise ptxas rematerialises the shared-window
     // arithmetic (S2UR/ULEA) inside the loop instead of keeping two registers live
     asm volatile("mov.u32 %0, %0;" : "+r"(rec0));
     asm volatile("mov.u32 %0, %0;" : "+r"(rec_end));
     uint32_t rec = rec0;
 #pragma unroll 1
-    for (; rec != rec_end; rec += 64 * kGroup) {
-        float gmax = 0.0f;
+    for (; rec != rec_end; rec += 64 * kGroup * kUnroll) {
 #pragma unroll
-        for (int j = 0; j < kGroup; j++) gmax = object_max_det<GENERAL>(rec + 64 * j, rp, gmax);
-        if (__builtin_expect(__any_sync(0xffffffffu, gmax > 0.0f), 0))
-            rare_group(tab, (int)((rec - rec0) >> 6), kGroup, kbase, dw, tmin, idx);
+        for (int u = 0; u < kUnroll; u++) {
+            float gmax = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kGroup; j++) gmax = object_max_det<GENERAL>(rec + 64 * (u * kGroup + j), rp, gmax);
+            if (__builtin_expect(__any_sync(0xffffffffu, gmax > 0.0f), 0))
+                rare_group(tab, (int)((rec - rec0) >> 6) + u * kGroup, kGroup, kbase, dw, tmin, idx);
+        }
     }
-    const int k = count - count % kGroup;
+    const int k = count - count % (kGroup * kUnroll);
     if (k < count) rare_group(tab, k, count - k, kbase, dw, tmin, idx);
 }
 
