@@ -353,7 +353,7 @@ def run_b200(args):
     # render.StreamedFusedMSE (row slabs pipelined over copy-in / kernel / copy-out streams).
     pin_target = target.cpu().pin_memory()
     pin_image = torch.empty_like(pin_target).pin_memory()
-    streamed = R.StreamedFusedMSE(cfg, N, dev, slabs=8, want_image=True)
+    streamed = R.StreamedFusedMSE(cfg, N, dev, want_image=True)
 
     def finish(loss, grad):
         if world > 1:
@@ -447,7 +447,7 @@ def run_b200(args):
                             d2h_bytes_per_step=d2h + full_bytes,
                             note='every step: scene-parameter tables AND the target slab come from pinned host memory, '
                                  'loss + gradient vector AND the rendered image slab go back to pinned host memory; '
-                                 'render.StreamedFusedMSE pipelines 8 row slabs over copy-in / kernel / copy-out streams',
+                                 'render.StreamedFusedMSE pipelines %d row slabs over copy-in / kernel / copy-out streams' % len(streamed.bounds),
                             same_buffers_unpipelined=dict(value=e2e_full_value, unit='Mrays/s'),
                             parameters_only=dict(
                                 value=e2e_value, unit='Mrays/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,

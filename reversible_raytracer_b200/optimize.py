@@ -90,7 +90,9 @@ class GDOptimizer(object):
                     st['graph'] = None
                     torch.cuda.synchronize()
             if st['graph'] is not None:
-                st['lr'].fill_(float(step_lr))
+                if st.get('lr_value') != float(step_lr):       # the learning rate lives on the device: upload on change only
+                    st['lr'].fill_(float(step_lr))
+                    st['lr_value'] = float(step_lr)
                 st['graph'].replay()
                 return float(st['value'].detach())
             return float(step(step_lr).detach())
