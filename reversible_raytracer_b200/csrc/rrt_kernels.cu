@@ -231,10 +231,19 @@ struct HitRec {
     float vn, pd, det, t;
 };
 
+template <bool DIAG_SHORTCUT = false>
 __device__ __forceinline__ float obj_test(const Obj& ob, float dwx, float dwy, float dwz, HitRec& h) {
-    h.d[0] = dot3_canon(ob.a[0], ob.a[1], ob.a[2], dwx, dwy, dwz);
-    h.d[1] = dot3_canon(ob.a[3], ob.a[4], ob.a[5], dwx, dwy, dwz);
-    h.d[2] = dot3_canon(ob.a[6], ob.a[7], ob.a[8], dwx, dwy, dwz);
+    if (DIAG_SHORTCUT && !(ob.flags & 2)) {
+        // diagonal A (translate*scale objects): the fma chain with exact-zero off-diagonals
+        // returns a_ii*d_i up to the sign of a zero, which nothing downstream can see
+        h.d[0] = __fmul_rn(ob.a[0], dwx);
+        h.d[1] = __fmul_rn(ob.a[4], dwy);
+        h.d[2] = __fmul_rn(ob.a[8], dwz);
+    } else {
+        h.d[0] = dot3_canon(ob.a[0], ob.a[1], ob.a[2], dwx, dwy, dwz);
+        h.d[1] = dot3_canon(ob.a[3], ob.a[4], ob.a[5], dwx, dwy, dwz);
+        h.d[2] = dot3_canon(ob.a[6], ob.a[7], ob.a[8], dwx, dwy, dwz);
+    }
     const float inf = __int_as_float(0x7f800000);
     if (!(ob.flags & 1)) {  // Sphere.distance shape.py:109-126
         h.vn = dot3_canon(h.d[0], h.d[1], h.d[2], h.d[0], h.d[1], h.d[2]);
@@ -1399,7 +1408,7 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
             Obj ob;
             load_rec(tab + 4 * k, ob);
             HitRec h;
-            const float t = obj_test(ob, wx, wy, wz, h);
+            const float t = obj_test<true>(ob, wx, wy, wz, h);
             if (t < tmin) { tmin = t; idx = k; }
         }
     }
@@ -1425,7 +1434,7 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
     if (MODE == MODE_BWD && gc[0] == 0.f && gc[1] == 0.f && gc[2] == 0.f) idx = -1;
     if (idx >= 0) {
         load_rec(tab + 4 * idx, ob);
-        obj_test(ob, wx, wy, wz, h);
+        obj_test<true>(ob, wx, wy, wz, h);
         if (!(h.t < inf)) idx = -1;                      // stale stored winner
     }
     if (idx >= 0) {
@@ -1439,9 +1448,17 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
         // pixel = mean over the S lanes of this pixel, summed in sample order like render_kernel
         const int base = lane & ~(S - 1);
         float sum[3] = {0.f, 0.f, 0.f};
-        for (int j = 0; j < S; j++) {
+        if (S == 4) {                                    // the reference's default (scene.py:18)
 #pragma unroll
-            for (int c = 0; c < 3; c++) sum[c] += __shfl_sync(full, rgb[c], base + j);
+            for (int j = 0; j < 4; j++) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) sum[c] += __shfl_sync(full, rgb[c], base + j);
+            }
+        } else {
+            for (int j = 0; j < S; j++) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) sum[c] += __shfl_sync(full, rgb[c], base + j);
+            }
         }
         const float v0 = sum[0] * inv, v1 = sum[1] * inv, v2 = sum[2] * inv;      // scene.py:49-50
         if (active && s == 0 && P.image) { P.image[po] = v0; P.image[po + 1] = v1; P.image[po + 2] = v2; }
