@@ -6,45 +6,34 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _common as C  # noqa: E402
 from reversible_raytracer_b200.optimize import GDOptimizer  # noqa: E402
 from reversible_raytracer_b200.scene import *  # noqa: E402,F401,F403
 from reversible_raytracer_b200.shader import *  # noqa: E402,F401,F403
 
 
+def build_scene(params):
+    green, pink = C.materials()
+    wall = Square(translate((0, 0, 3)) * rotate(50, [0., 1., 0.]), pink)
+    balls = [Sphere(translate(p), m) for p, m in zip(params, (green, pink))]
+    return Scene(balls + [wall], [Light((-1., -1., 2.), (1., 0.87, 0.961))], Camera(128, 128), PhongShader())
+
+
 def main(steps=90, out='output', dump=True, fused=False):
-    os.makedirs(out, exist_ok=True)
-    center1 = torch.tensor([-.5, -.5, 4.], device='cuda')
-    center2 = torch.tensor([.5, .5, 4.], device='cuda')
-    material1 = Material((0.2, 0.9, 0.4), 0.3, 0.7, 0.5, 50.)
-    material2 = Material((0.87, 0.1, 0.507), 0.3, 0.9, 0.4, 50.)
-    objs = [
-        Sphere(translate(center1), material1),
-        Sphere(translate(center2), material2),
-        Square(translate((0, 0, 3)) * rotate(50, [0., 1., 0.]), material2),
-    ]
-    light = Light((-1., -1., 2.), (1., 0.87, 0.961))
-    scene = Scene(objs, [light], Camera(128, 128), PhongShader())
-
-    print('Rendering initial scene')
-    render = scene.build().detach()
-    flipped = torch.flip(render, dims=[1])                      # np.fliplr, match_mirror.py:40
+    params = C.centres()
+    scene = build_scene(params)
+    first = scene.build().detach()
+    mirrored = torch.flip(first, dims=[1])                      # np.fliplr, match_mirror.py:40
     if dump:
-        draw(os.path.join(out, '0.png'), render)
-        draw(os.path.join(out, '0lr.png'), flipped)
-
-    if fused:
-        cost = lambda: scene.build_mse(flipped)
-    else:
-        cost = lambda: ((scene.build() - flipped) ** 2).sum()  # match_mirror.py:45
-    train = GDOptimizer().optimize([center1, center2], cost, 0.000008, 0.1)
-    losses = []
-    for i in range(steps):
-        losses.append(train())
-        print('Step', i + 1, losses[-1])
-        if dump:
-            draw(os.path.join(out, '%d.png' % (i + 1,)), scene.build().detach())
-    return losses, center1, center2
+        os.makedirs(out, exist_ok=True)
+        draw(os.path.join(out, '0.png'), first)
+        draw(os.path.join(out, '0lr.png'), mirrored)
+    # match_mirror.py:45 -- as tensor algebra, or as the fused single-kernel cost
+    cost = (lambda: scene.build_mse(mirrored)) if fused else (lambda: ((scene.build() - mirrored) ** 2).sum())
+    train = GDOptimizer().optimize(params, cost, 0.000008, 0.1)
+    losses = C.run(train, steps, lambda: scene.build().detach(), out if dump else None, draw)
+    return losses, params[0], params[1]
 
 
 if __name__ == '__main__':

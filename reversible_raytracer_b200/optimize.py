@@ -69,8 +69,11 @@ class GDOptimizer(object):
                 step(st['lr'])
             torch.cuda.current_stream(dev).wait_stream(side)
             g = torch.cuda.CUDAGraph()
+            st['host'] = torch.zeros((), dtype=torch.float32).pin_memory()
             with torch.cuda.graph(g):
                 st['value'] = step(st['lr'])
+                # the loss read-back is part of the graph: a copy node into pinned host memory
+                st['host'].copy_(st['value'].detach().to(torch.float32), non_blocking=True)
             with torch.no_grad():                  # lr was 0 during warm-up/capture; restore exactly anyway
                 for v, s0 in zip(tVars, saved):
                     v.copy_(s0)
@@ -94,7 +97,8 @@ class GDOptimizer(object):
                     st['lr'].fill_(float(step_lr))
                     st['lr_value'] = float(step_lr)
                 st['graph'].replay()
-                return float(st['value'].detach())
+                torch.cuda.current_stream(st['lr'].device).synchronize()
+                return float(st['host'])
             return float(step(step_lr).detach())
 
         train.state = st
