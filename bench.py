@@ -161,8 +161,11 @@ def other_configs(dev):
     out['C1_optimize_brightness_step_us'] = round(L.timeit(train, warm=6, iters=100), 1)
     train, _ = L.c3(False)
     out['C3_match_mirror_step_us'] = round(L.timeit(train, warm=6, iters=100), 1)
-    train, _ = L.c3(True)
+    train, _ = L.c3('graph')
     out['C3_match_mirror_fused_step_us'] = round(L.timeit(train, warm=6, iters=100), 1)
+    train, _ = L.c3(True)                       # Scene.mse_cost: whole step = one kernel launch (rrt_small_step_mse)
+    if train.state.get('whole_step') is not None:
+        out['C3_match_mirror_whole_step_kernel_us'] = round(L.timeit(train, warm=6, iters=100), 1)
     fn, rays = L.c4(256)
     us = L.timeit(fn, warm=5, iters=100)
     out['C4_orbit_256x2_fused'] = dict(us_per_batch=round(us, 1), Mrays_s=round(rays / us, 1))

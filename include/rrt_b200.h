@@ -237,6 +237,35 @@ int rrt_chain_backward(const int32_t* ops, const int32_t* chain_begin, int num_c
                        const float* g_out, float* g_values, int num_values, void* stream);
 
 /*
+ * A WHOLE optimise step of a small scene with a squared-error cost in ONE kernel launch -- the
+ * counterpart of the single compiled Theano function the reference builds from
+ * T.grad + updates (optimize.py:19-29) for the cost of match_mirror.py:45:
+ *     w2o rows = chains(values)                 transform.py:32-38, 56-122 (as rrt_chain_forward)
+ *     image, loss, d/d w2o                      as rrt_render_fused_mse (small-scene kernel)
+ *     d/d values = chains^T(d/d w2o)            as rrt_chain_backward
+ *     values[p] -= lr * d/d values[p]           for p >= param_begin   (optimize.py:26-27)
+ * The last CTA to finish (device-side ticket) runs everything after the render and re-zeroes the
+ * scratch buffers, so consecutive steps need no memsets and no other launches.  scene->w2o is not
+ * read (the chains replace it); one scene, <= 32 shapes, power-of-two samples.
+ */
+typedef struct rrt_step {
+    const int32_t* ops;          /* chain program of the scene's shapes, see rrt_chain_forward       */
+    const int32_t* chain_begin;  /* [num_objects + 1]                                                */
+    float* values;               /* [num_values] constants, then trainable parameters (updated)     */
+    int32_t num_values;
+    int32_t param_begin;         /* values[param_begin .. num_values) are trainable                  */
+    float lr;
+    int32_t reserved;
+    float* grad;                 /* scratch [RRT_GRAD_SIZE(N)], ZERO before the first step           */
+    float* g_values;             /* scratch [num_values], ZERO before the first step                 */
+    double* loss_acc;            /* scratch [1], ZERO before the first step                          */
+    float* loss_out;             /* [1]: the step's loss (evaluated before the update)               */
+    uint32_t* ticket;            /* scratch [1], ZERO before the first step                          */
+} rrt_step;
+int rrt_small_step_mse(const rrt_scene* scene, const rrt_step* step, const float* target,
+                       const float* channel_weight, float* image, void* stream);
+
+/*
  * The one exchange step of the sharded path (the reference is single-process,
  * so there is no reference interface to cite): sum of the per-rank vector
  * [grad (n float32) | loss (nloss float64)] over the GPUs of one box, done by ONE kernel per

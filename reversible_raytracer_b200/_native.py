@@ -60,6 +60,16 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+class RrtStep(C.Structure):
+    """`struct rrt_step` of include/rrt_b200.h (whole optimise step in one launch)."""
+    _fields_ = [
+        ('ops', C.c_void_p), ('chain_begin', C.c_void_p), ('values', C.c_void_p),
+        ('num_values', C.c_int32), ('param_begin', C.c_int32), ('lr', C.c_float), ('reserved', C.c_int32),
+        ('grad', C.c_void_p), ('g_values', C.c_void_p), ('loss_acc', C.c_void_p), ('loss_out', C.c_void_p),
+        ('ticket', C.c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -81,6 +91,9 @@ def lib():
         L.rrt_chain_forward.argtypes = [P, P, C.c_int, P, P, P]
         L.rrt_chain_backward.argtypes = [P, P, C.c_int, P, P, P, C.c_int, P]
         L.rrt_measure_fp32_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), P]
+        if hasattr(L, 'rrt_small_step_mse'):
+            L.rrt_small_step_mse.argtypes = [C.POINTER(RrtScene), C.POINTER(RrtStep), P, C.POINTER(C.c_float), P, P]
+            L.rrt_small_step_mse.restype = C.c_int
         if hasattr(L, 'rrt_build_records'):      # absent only in older A/B builds loaded through RRT_B200_LIB
             L.rrt_build_records.argtypes = [C.POINTER(RrtScene), P, P]
             L.rrt_build_records.restype = C.c_int
@@ -99,7 +112,8 @@ def lib():
 
 EXPORTS = ['rrt_version', 'rrt_last_error', 'rrt_render_forward', 'rrt_render_backward',
            'rrt_render_fused_mse', 'rrt_measure_fp32_peak', 'rrt_chain_forward', 'rrt_chain_backward', 'rrt_primary_rays',
-           'rrt_peer_allreduce', 'rrt_peer_buffer_bytes', 'rrt_peer_signal_bytes', 'rrt_build_records']
+           'rrt_peer_allreduce', 'rrt_peer_buffer_bytes', 'rrt_peer_signal_bytes', 'rrt_build_records',
+           'rrt_small_step_mse']
 
 FLAG_CULL, FLAG_NO_SMALL, FLAG_SHADOWS = 1, 2, 4
 HIT_SHADOWED = 0x40000000

@@ -86,6 +86,7 @@ struct KParams {
     float inv_s, inv_n; // exact reciprocals when S and n are powers of two
     int pow2;          // 1: (u+s)/S/n may be evaluated as exact multiplications
     int vec_ok;        // 1: image/target rows are 16-byte aligned (n % 4 == 0, aligned base pointers)
+    rrt_step step;     // rrt_small_step_mse only (whole optimise step in one launch)
 };
 
 // ---------------------------------------------------------------- packed f32x2
@@ -181,6 +182,8 @@ __device__ __forceinline__ void canon_to_light(const float* L, float* U) {
     U[0] = -__fdiv_rn(L[0], ln); U[1] = -__fdiv_rn(L[1], ln); U[2] = -__fdiv_rn(L[2], ln);
 }
 
+__device__ __forceinline__ void make_obj_rows(const float (&m)[12], int type, const float* ct, Obj& ob);
+
 __device__ __forceinline__ void make_obj(const float* __restrict__ w, int type, const float* ct, Obj& ob,
                                          bool want_afro = false) {
     float m[12];
@@ -189,6 +192,12 @@ __device__ __forceinline__ void make_obj(const float* __restrict__ w, int type, 
     m[0] = r0.x; m[1] = r0.y; m[2] = r0.z; m[3] = r0.w;
     m[4] = r1.x; m[5] = r1.y; m[6] = r1.z; m[7] = r1.w;
     m[8] = r2.x; m[9] = r2.y; m[10] = r2.z; m[11] = r2.w;
+    (void)want_afro;
+    make_obj_rows(m, type, ct, ob);
+}
+
+// from the 12 floats of w2o rows 0..2 (already in registers)
+__device__ __forceinline__ void make_obj_rows(const float (&m)[12], int type, const float* ct, Obj& ob) {
 #pragma unroll
     for (int r = 0; r < 3; r++) {
         ob.a[r * 3 + 0] = m[r * 4 + 0];
@@ -201,8 +210,7 @@ __device__ __forceinline__ void make_obj(const float* __restrict__ w, int type, 
     ob.ncc = -cc;
     bool general = (ob.a[1] != 0.f) || (ob.a[2] != 0.f) || (ob.a[3] != 0.f) || (ob.a[5] != 0.f) || (ob.a[6] != 0.f) || (ob.a[7] != 0.f);
     ob.flags = (type == RRT_OBJ_SQUARE ? 1 : 0) | (general ? 2 : 0);
-    (void)want_afro;                                   // (dead-code eliminated where afro is unused)
-    float f2 = 0.f;
+    float f2 = 0.f;                                    // (dead-code eliminated where afro is unused)
 #pragma unroll
     for (int q = 0; q < 9; q++) f2 += ob.a[q] * ob.a[q];
     ob.afro = sqrtf(f2);                               // culling bound only
@@ -1270,6 +1278,173 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
     }
 }
 
+// ---------------------------------------------------------------- parameter -> matrix chain
+// Affine 3x4 matrices [A|b] (bottom row 0 0 0 1 implied).  See include/rrt_b200.h.
+struct Aff {
+    float m[12];
+};
+
+__device__ __forceinline__ Aff aff_identity() {
+    Aff r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.m[i] = 0.f;
+    r.m[0] = r.m[5] = r.m[10] = 1.f;
+    return r;
+}
+
+// C = A . B   (transform.py:35-38); products with exact zeros stay exact zeros
+__device__ __forceinline__ Aff aff_mul(const Aff& A, const Aff& B) {
+    Aff C;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            float v = A.m[r * 4 + 0] * B.m[0 * 4 + c] + A.m[r * 4 + 1] * B.m[1 * 4 + c] + A.m[r * 4 + 2] * B.m[2 * 4 + c];
+            if (c == 3) v += A.m[r * 4 + 3];
+            C.m[r * 4 + c] = v;
+        }
+    }
+    return C;
+}
+
+// rotate(angle_deg, axis), transform.py:95-122 (Rodrigues form; axis assumed unit)
+__device__ __forceinline__ void rot_entries(float angle, const float* a, float* R) {
+    float s, c;
+    sincosf(angle * 0.017453292519943295f, &s, &c);
+    R[0] = a[0] * a[0] + (1.f - a[0] * a[0]) * c;
+    R[1] = a[0] * a[1] * (1.f - c) - a[2] * s;
+    R[2] = a[0] * a[2] * (1.f - c) + a[1] * s;
+    R[3] = a[0] * a[1] * (1.f - c) + a[2] * s;
+    R[4] = a[1] * a[1] + (1.f - a[1] * a[1]) * c;
+    R[5] = a[1] * a[2] * (1.f - c) - a[0] * s;
+    R[6] = a[0] * a[2] * (1.f - c) - a[1] * s;
+    R[7] = a[1] * a[2] * (1.f - c) + a[0] * s;
+    R[8] = a[2] * a[2] + (1.f - a[2] * a[2]) * c;
+}
+
+__device__ __forceinline__ Aff chain_op_matrix(const int32_t* op, const float* __restrict__ values) {
+    const int kind = op[0] & 0xff;
+    const bool inv = (op[0] & RRT_CHAIN_INVERT) != 0;
+    Aff M = aff_identity();
+    if (kind == RRT_CHAIN_TRANSLATE) {            // transform.py:60-75
+        const float* v = values + op[1];
+        M.m[3] = inv ? -v[0] : v[0]; M.m[7] = inv ? -v[1] : v[1]; M.m[11] = inv ? -v[2] : v[2];
+    } else if (kind == RRT_CHAIN_SCALE) {         // transform.py:78-93 (inverse is 1/x)
+        const float* v = values + op[1];
+        M.m[0] = inv ? 1.f / v[0] : v[0]; M.m[5] = inv ? 1.f / v[1] : v[1]; M.m[10] = inv ? 1.f / v[2] : v[2];
+    } else if (kind == RRT_CHAIN_ROTATE) {        // inverse = transpose
+        float R[9];
+        rot_entries(values[op[1]], values + op[2], R);
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) M.m[r * 4 + c] = inv ? R[c * 3 + r] : R[r * 3 + c];
+    }
+    return M;
+}
+
+__device__ __forceinline__ Aff chain_forward_one(const int32_t* __restrict__ ops, const int32_t* __restrict__ chain_begin,
+                                                 int k, const float* __restrict__ values) {
+    Aff M = aff_identity();
+    for (int j = chain_begin[k]; j < chain_begin[k + 1]; j++) M = aff_mul(M, chain_op_matrix(ops + 4 * j, values));
+    return M;
+}
+
+__global__ void chain_forward_kernel(const int32_t* __restrict__ ops, const int32_t* __restrict__ chain_begin,
+                                     int num_chains, const float* __restrict__ values, float* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= num_chains) return;
+    const Aff M = chain_forward_one(ops, chain_begin, k, values);
+#pragma unroll
+    for (int i = 0; i < 12; i++) out[(size_t)k * 12 + i] = M.m[i];
+}
+
+// dL/d(op j) = P_{j-1}^T . G . S_{j+1}^T with P = prefix product, S = suffix product
+// (4x4 with the implied bottom row); then into the primitive's own parameters.
+// G = dL/d(row k of the chain's output); accumulates into g_values with atomics (parameters may be
+// shared between chains).
+__device__ __noinline__ void chain_backward_one(const int32_t* __restrict__ ops, const int32_t* __restrict__ chain_begin,
+                                                int k, const float* __restrict__ values, const float* G,
+                                                float* __restrict__ g_values) {
+    const int b = chain_begin[k], e = chain_begin[k + 1], n = e - b;
+    if (n <= 0 || n > RRT_CHAIN_MAX_OPS) return;
+    Aff mats[RRT_CHAIN_MAX_OPS], pre[RRT_CHAIN_MAX_OPS + 1];
+    pre[0] = aff_identity();
+    for (int j = 0; j < n; j++) {
+        mats[j] = chain_op_matrix(ops + 4 * (b + j), values);
+        pre[j + 1] = aff_mul(pre[j], mats[j]);
+    }
+    Aff suf = aff_identity();                     // product of ops j+1..n-1
+    for (int j = n - 1; j >= 0; j--) {
+        // out = P . M_j . S  (affine).  T = G . S^T restricted to what reaches M_j's 3x4 block:
+        //   T[r][c] = sum_q G[r][q] S[c][q] (c<3: q over 0..3 with S[c][3]=b_c) ; T[r][3] = G[r][3]
+        float T[12];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                T[r * 4 + c] = G[r * 4 + 0] * suf.m[c * 4 + 0] + G[r * 4 + 1] * suf.m[c * 4 + 1] +
+                               G[r * 4 + 2] * suf.m[c * 4 + 2] + G[r * 4 + 3] * suf.m[c * 4 + 3];
+            T[r * 4 + 3] = G[r * 4 + 3];
+        }
+        // D = P_A^T . T   (gradient w.r.t. M_j's [A|b])
+        const Aff& Pm = pre[j];
+        float D[12];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                D[r * 4 + c] = Pm.m[0 * 4 + r] * T[0 * 4 + c] + Pm.m[1 * 4 + r] * T[1 * 4 + c] + Pm.m[2 * 4 + r] * T[2 * 4 + c];
+        const int32_t* op = ops + 4 * (b + j);
+        const int kind = op[0] & 0xff;
+        const bool inv = (op[0] & RRT_CHAIN_INVERT) != 0;
+        if (kind == RRT_CHAIN_TRANSLATE) {
+            const float sgn = inv ? -1.f : 1.f;
+            atomicAdd(&g_values[op[1] + 0], sgn * D[3]);
+            atomicAdd(&g_values[op[1] + 1], sgn * D[7]);
+            atomicAdd(&g_values[op[1] + 2], sgn * D[11]);
+        } else if (kind == RRT_CHAIN_SCALE) {
+            const float* v = values + op[1];
+#pragma unroll
+            for (int i = 0; i < 3; i++) atomicAdd(&g_values[op[1] + i], inv ? -D[i * 5] / (v[i] * v[i]) : D[i * 5]);
+        } else if (kind == RRT_CHAIN_ROTATE) {
+            const float ang = values[op[1]];
+            const float* a = values + op[2];
+            float s, c;
+            sincosf(ang * 0.017453292519943295f, &s, &c);
+            float Gr[9];                         // gradient w.r.t. the (non-transposed) rotation entries
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int cc = 0; cc < 3; cc++) Gr[r * 3 + cc] = inv ? D[cc * 4 + r] : D[r * 4 + cc];
+            const float dc = -s * 0.017453292519943295f, ds = c * 0.017453292519943295f, omc = 1.f - c;
+            float g_ang = Gr[0] * (1.f - a[0] * a[0]) * dc + Gr[4] * (1.f - a[1] * a[1]) * dc + Gr[8] * (1.f - a[2] * a[2]) * dc +
+                          Gr[1] * (-a[0] * a[1] * dc - a[2] * ds) + Gr[2] * (-a[0] * a[2] * dc + a[1] * ds) +
+                          Gr[3] * (-a[0] * a[1] * dc + a[2] * ds) + Gr[5] * (-a[1] * a[2] * dc - a[0] * ds) +
+                          Gr[6] * (-a[0] * a[2] * dc - a[1] * ds) + Gr[7] * (-a[1] * a[2] * dc + a[0] * ds);
+            float g_a0 = Gr[0] * 2.f * a[0] * omc + (Gr[1] + Gr[3]) * a[1] * omc + (Gr[2] + Gr[6]) * a[2] * omc + (Gr[7] - Gr[5]) * s;
+            float g_a1 = Gr[4] * 2.f * a[1] * omc + (Gr[1] + Gr[3]) * a[0] * omc + (Gr[5] + Gr[7]) * a[2] * omc + (Gr[2] - Gr[6]) * s;
+            float g_a2 = Gr[8] * 2.f * a[2] * omc + (Gr[2] + Gr[6]) * a[0] * omc + (Gr[5] + Gr[7]) * a[1] * omc + (Gr[3] - Gr[1]) * s;
+            atomicAdd(&g_values[op[1]], g_ang);
+            atomicAdd(&g_values[op[2] + 0], g_a0);
+            atomicAdd(&g_values[op[2] + 1], g_a1);
+            atomicAdd(&g_values[op[2] + 2], g_a2);
+        }
+        suf = aff_mul(mats[j], suf);
+    }
+}
+
+__global__ void chain_backward_kernel(const int32_t* __restrict__ ops, const int32_t* __restrict__ chain_begin,
+                                      int num_chains, const float* __restrict__ values,
+                                      const float* __restrict__ g_out, float* __restrict__ g_values) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= num_chains) return;
+    float G[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) G[i] = g_out[(size_t)k * 12 + i];
+    chain_backward_one(ops, chain_begin, k, values, G, g_values);
+}
+
 // ---------------------------------------------------------------- the small-scene kernel
 // Latency-oriented variant for the reference's own workloads (optimize_brightness.py,
 // match_mirror.py, test_balls.py, the orbit decoder: 32..128 pixels a side, 2..3 shapes).
@@ -1287,7 +1462,7 @@ constexpr int kSmallThreads = 128;
 constexpr long long kSmallDefaultMaxRays = 16 << 20;  // total rays of a call (all scenes) up to which it is used
                                                       // (orbit batch, 8.4 M rays: 258 us here vs 295 us on the general kernel)
 
-template <int MODE>
+template <int MODE, bool STEP = false>
 __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_small_kernel(const __grid_constant__ KParams P) {
     __shared__ float4 tab[kSmallMaxN * 4];
     __shared__ float mat_s[kSmallMaxN * RRT_MAT_STRIDE];
@@ -1326,7 +1501,12 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
     if (tid < N) {
         const float ct[3] = {__ldg(cam + 3), __ldg(cam + 7), __ldg(cam + 11)};
         Obj ob;
-        make_obj(w2o + (size_t)tid * RRT_W2O_STRIDE, sc.obj_type[tid], ct, ob);
+        if (STEP) {   // whole-step variant: the shape's w2o rows come straight from the parameter chain
+            const Aff M = chain_forward_one(P.step.ops, P.step.chain_begin, tid, P.step.values);
+            make_obj_rows(M.m, sc.obj_type[tid], ct, ob);
+        } else {
+            make_obj(w2o + (size_t)tid * RRT_W2O_STRIDE, sc.obj_type[tid], ct, ob);
+        }
         store_rec(tab + 4 * tid, ob);
     }
     for (int q = tid; q < N * RRT_MAT_STRIDE; q += kSmallThreads) mat_s[q] = __ldg(mats + q);
@@ -1522,6 +1702,50 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
             for (int w = 0; w < kSmallThreads / 32; w++) t += (double)loss_warp[w];
             if (t != 0.0) atomicAdd(&P.loss[scene], t);
         }
+        if (STEP) {
+            // ---- the rest of the optimise step, by the LAST CTA to get here (ticket): finalize the
+            // raw sums into d/d w2o, chain them back to the parameters (T.grad through
+            // translate/scale/rotate, transform.py:56-122), apply var <- var - lr*grad
+            // (optimize.py:26-27), publish the loss and re-zero the scratch for the next step.
+            __shared__ int is_last;
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) is_last = (atomicAdd(P.step.ticket, 1u) == gridDim.x - 1);
+            __syncthreads();
+            if (is_last) {
+                __threadfence();
+                const rrt_step& q = P.step;
+                if (tid < N) {
+                    float Mm[9], gb[3], G[12];
+#pragma unroll
+                    for (int v = 0; v < 9; v++) Mm[v] = __ldcg(gobj + (size_t)tid * RRT_OBJ_GRAD_STRIDE + v);
+#pragma unroll
+                    for (int v = 0; v < 3; v++) gb[v] = __ldcg(gobj + (size_t)tid * RRT_OBJ_GRAD_STRIDE + 9 + v);
+#pragma unroll
+                    for (int r = 0; r < 3; r++) {          // d/dA = M C^T + g_b ct^T ; d/db = g_b (finalize_grads)
+#pragma unroll
+                        for (int c = 0; c < 3; c++)
+                            G[r * 4 + c] = Mm[r * 3] * g.C[c * 3] + Mm[r * 3 + 1] * g.C[c * 3 + 1] + Mm[r * 3 + 2] * g.C[c * 3 + 2] +
+                                           gb[r] * g.ct[c];
+                        G[r * 4 + 3] = gb[r];
+                    }
+                    chain_backward_one(q.ops, q.chain_begin, tid, q.values, G, q.g_values);
+                }
+                __threadfence();
+                __syncthreads();
+                for (int p = tid; p < q.num_values; p += kSmallThreads) {
+                    const float gv = __ldcg(q.g_values + p);
+                    if (p >= q.param_begin) q.values[p] -= q.lr * gv;
+                    q.g_values[p] = 0.f;
+                }
+                for (int v = tid; v < (int)RRT_GRAD_SIZE(N); v += kSmallThreads) gobj[v] = 0.f;
+                if (tid == 0) {
+                    *q.loss_out = (float)__ldcg(P.loss);
+                    *P.loss = 0.0;
+                    *q.ticket = 0u;
+                }
+            }
+        }
     }
 }
 
@@ -1709,159 +1933,6 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(const float* __rest
         double sum = 0.0;
         for (int p = 0; p < world; p++) sum += __ldcg(local + (size_t)p * total + i);
         out[i] = timed_out ? __longlong_as_double(0x7ff8000000000000LL) : sum;
-    }
-}
-
-// ---------------------------------------------------------------- parameter -> matrix chain
-// Affine 3x4 matrices [A|b] (bottom row 0 0 0 1 implied).  See include/rrt_b200.h.
-struct Aff {
-    float m[12];
-};
-
-__device__ __forceinline__ Aff aff_identity() {
-    Aff r;
-#pragma unroll
-    for (int i = 0; i < 12; i++) r.m[i] = 0.f;
-    r.m[0] = r.m[5] = r.m[10] = 1.f;
-    return r;
-}
-
-// C = A . B   (transform.py:35-38); products with exact zeros stay exact zeros
-__device__ __forceinline__ Aff aff_mul(const Aff& A, const Aff& B) {
-    Aff C;
-#pragma unroll
-    for (int r = 0; r < 3; r++) {
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            float v = A.m[r * 4 + 0] * B.m[0 * 4 + c] + A.m[r * 4 + 1] * B.m[1 * 4 + c] + A.m[r * 4 + 2] * B.m[2 * 4 + c];
-            if (c == 3) v += A.m[r * 4 + 3];
-            C.m[r * 4 + c] = v;
-        }
-    }
-    return C;
-}
-
-// rotate(angle_deg, axis), transform.py:95-122 (Rodrigues form; axis assumed unit)
-__device__ __forceinline__ void rot_entries(float angle, const float* a, float* R) {
-    float s, c;
-    sincosf(angle * 0.017453292519943295f, &s, &c);
-    R[0] = a[0] * a[0] + (1.f - a[0] * a[0]) * c;
-    R[1] = a[0] * a[1] * (1.f - c) - a[2] * s;
-    R[2] = a[0] * a[2] * (1.f - c) + a[1] * s;
-    R[3] = a[0] * a[1] * (1.f - c) + a[2] * s;
-    R[4] = a[1] * a[1] + (1.f - a[1] * a[1]) * c;
-    R[5] = a[1] * a[2] * (1.f - c) - a[0] * s;
-    R[6] = a[0] * a[2] * (1.f - c) - a[1] * s;
-    R[7] = a[1] * a[2] * (1.f - c) + a[0] * s;
-    R[8] = a[2] * a[2] + (1.f - a[2] * a[2]) * c;
-}
-
-__device__ __forceinline__ Aff chain_op_matrix(const int32_t* op, const float* __restrict__ values) {
-    const int kind = op[0] & 0xff;
-    const bool inv = (op[0] & RRT_CHAIN_INVERT) != 0;
-    Aff M = aff_identity();
-    if (kind == RRT_CHAIN_TRANSLATE) {            // transform.py:60-75
-        const float* v = values + op[1];
-        M.m[3] = inv ? -v[0] : v[0]; M.m[7] = inv ? -v[1] : v[1]; M.m[11] = inv ? -v[2] : v[2];
-    } else if (kind == RRT_CHAIN_SCALE) {         // transform.py:78-93 (inverse is 1/x)
-        const float* v = values + op[1];
-        M.m[0] = inv ? 1.f / v[0] : v[0]; M.m[5] = inv ? 1.f / v[1] : v[1]; M.m[10] = inv ? 1.f / v[2] : v[2];
-    } else if (kind == RRT_CHAIN_ROTATE) {        // inverse = transpose
-        float R[9];
-        rot_entries(values[op[1]], values + op[2], R);
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-#pragma unroll
-            for (int c = 0; c < 3; c++) M.m[r * 4 + c] = inv ? R[c * 3 + r] : R[r * 3 + c];
-    }
-    return M;
-}
-
-__global__ void chain_forward_kernel(const int32_t* __restrict__ ops, const int32_t* __restrict__ chain_begin,
-                                     int num_chains, const float* __restrict__ values, float* __restrict__ out) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= num_chains) return;
-    Aff M = aff_identity();
-    for (int j = chain_begin[k]; j < chain_begin[k + 1]; j++) M = aff_mul(M, chain_op_matrix(ops + 4 * j, values));
-#pragma unroll
-    for (int i = 0; i < 12; i++) out[(size_t)k * 12 + i] = M.m[i];
-}
-
-// dL/d(op j) = P_{j-1}^T . G . S_{j+1}^T with P = prefix product, S = suffix product
-// (4x4 with the implied bottom row); then into the primitive's own parameters.
-__global__ void chain_backward_kernel(const int32_t* __restrict__ ops, const int32_t* __restrict__ chain_begin,
-                                      int num_chains, const float* __restrict__ values,
-                                      const float* __restrict__ g_out, float* __restrict__ g_values) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= num_chains) return;
-    const int b = chain_begin[k], e = chain_begin[k + 1], n = e - b;
-    if (n <= 0 || n > RRT_CHAIN_MAX_OPS) return;
-    Aff mats[RRT_CHAIN_MAX_OPS], pre[RRT_CHAIN_MAX_OPS + 1];
-    pre[0] = aff_identity();
-    for (int j = 0; j < n; j++) {
-        mats[j] = chain_op_matrix(ops + 4 * (b + j), values);
-        pre[j + 1] = aff_mul(pre[j], mats[j]);
-    }
-    float G[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) G[i] = g_out[(size_t)k * 12 + i];
-    Aff suf = aff_identity();                     // product of ops j+1..n-1
-    for (int j = n - 1; j >= 0; j--) {
-        // out = P . M_j . S  (affine).  T = G . S^T restricted to what reaches M_j's 3x4 block:
-        //   T[r][c] = sum_q G[r][q] S[c][q] (c<3: q over 0..3 with S[c][3]=b_c) ; T[r][3] = G[r][3]
-        float T[12];
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-                T[r * 4 + c] = G[r * 4 + 0] * suf.m[c * 4 + 0] + G[r * 4 + 1] * suf.m[c * 4 + 1] +
-                               G[r * 4 + 2] * suf.m[c * 4 + 2] + G[r * 4 + 3] * suf.m[c * 4 + 3];
-            T[r * 4 + 3] = G[r * 4 + 3];
-        }
-        // D = P_A^T . T   (gradient w.r.t. M_j's [A|b])
-        const Aff& Pm = pre[j];
-        float D[12];
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-#pragma unroll
-            for (int c = 0; c < 4; c++)
-                D[r * 4 + c] = Pm.m[0 * 4 + r] * T[0 * 4 + c] + Pm.m[1 * 4 + r] * T[1 * 4 + c] + Pm.m[2 * 4 + r] * T[2 * 4 + c];
-        const int32_t* op = ops + 4 * (b + j);
-        const int kind = op[0] & 0xff;
-        const bool inv = (op[0] & RRT_CHAIN_INVERT) != 0;
-        if (kind == RRT_CHAIN_TRANSLATE) {
-            const float sgn = inv ? -1.f : 1.f;
-            atomicAdd(&g_values[op[1] + 0], sgn * D[3]);
-            atomicAdd(&g_values[op[1] + 1], sgn * D[7]);
-            atomicAdd(&g_values[op[1] + 2], sgn * D[11]);
-        } else if (kind == RRT_CHAIN_SCALE) {
-            const float* v = values + op[1];
-#pragma unroll
-            for (int i = 0; i < 3; i++) atomicAdd(&g_values[op[1] + i], inv ? -D[i * 5] / (v[i] * v[i]) : D[i * 5]);
-        } else if (kind == RRT_CHAIN_ROTATE) {
-            const float ang = values[op[1]];
-            const float* a = values + op[2];
-            float s, c;
-            sincosf(ang * 0.017453292519943295f, &s, &c);
-            float Gr[9];                         // gradient w.r.t. the (non-transposed) rotation entries
-#pragma unroll
-            for (int r = 0; r < 3; r++)
-#pragma unroll
-                for (int cc = 0; cc < 3; cc++) Gr[r * 3 + cc] = inv ? D[cc * 4 + r] : D[r * 4 + cc];
-            const float dc = -s * 0.017453292519943295f, ds = c * 0.017453292519943295f, omc = 1.f - c;
-            float g_ang = Gr[0] * (1.f - a[0] * a[0]) * dc + Gr[4] * (1.f - a[1] * a[1]) * dc + Gr[8] * (1.f - a[2] * a[2]) * dc +
-                          Gr[1] * (-a[0] * a[1] * dc - a[2] * ds) + Gr[2] * (-a[0] * a[2] * dc + a[1] * ds) +
-                          Gr[3] * (-a[0] * a[1] * dc + a[2] * ds) + Gr[5] * (-a[1] * a[2] * dc - a[0] * ds) +
-                          Gr[6] * (-a[0] * a[2] * dc - a[1] * ds) + Gr[7] * (-a[1] * a[2] * dc + a[0] * ds);
-            float g_a0 = Gr[0] * 2.f * a[0] * omc + (Gr[1] + Gr[3]) * a[1] * omc + (Gr[2] + Gr[6]) * a[2] * omc + (Gr[7] - Gr[5]) * s;
-            float g_a1 = Gr[4] * 2.f * a[1] * omc + (Gr[1] + Gr[3]) * a[0] * omc + (Gr[5] + Gr[7]) * a[2] * omc + (Gr[2] - Gr[6]) * s;
-            float g_a2 = Gr[8] * 2.f * a[2] * omc + (Gr[2] + Gr[6]) * a[0] * omc + (Gr[5] + Gr[7]) * a[1] * omc + (Gr[3] - Gr[1]) * s;
-            atomicAdd(&g_values[op[1]], g_ang);
-            atomicAdd(&g_values[op[2] + 0], g_a0);
-            atomicAdd(&g_values[op[2] + 1], g_a1);
-            atomicAdd(&g_values[op[2] + 2], g_a2);
-        }
-        suf = aff_mul(mats[j], suf);
     }
 }
 
@@ -2119,6 +2190,43 @@ int rrt_chain_backward(const int32_t* ops, const int32_t* chain_begin, int num_c
     chain_backward_kernel<<<(num_chains + 63) / 64, 64, 0, st>>>(ops, chain_begin, num_chains, values, g_out, g_values);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "chain backward launch: %s", cudaGetErrorString(e));
+    return RRT_OK;
+}
+
+int rrt_small_step_mse(const rrt_scene* scene, const rrt_step* step, const float* target, const float* channel_weight,
+                       float* image, void* stream) {
+    KParams P;
+    memset(&P, 0, sizeof P);
+    int rc = check_scene(scene, &P.rows);
+    if (rc) return rc;
+    if (!step || !target) return fail(RRT_ERR_INVALID, "step and target are required");
+    if (!step->ops || !step->chain_begin || !step->values || !step->grad || !step->g_values || !step->loss_acc ||
+        !step->loss_out || !step->ticket)
+        return fail(RRT_ERR_INVALID, "rrt_step has a NULL field");
+    if (step->num_values <= 0 || step->param_begin < 0 || step->param_begin > step->num_values)
+        return fail(RRT_ERR_INVALID, "rrt_step: bad parameter range");
+    P.sc = *scene;
+    if (scene->num_scenes != 1 || scene->num_objects < 1) return fail(RRT_ERR_UNSUPPORTED, "whole-step kernel: one scene, >= 1 shape");
+    P.step = *step;
+    P.target = target;
+    P.cw[0] = channel_weight ? channel_weight[0] : 1.f;
+    P.cw[1] = channel_weight ? channel_weight[1] : 1.f;
+    P.cw[2] = channel_weight ? channel_weight[2] : 1.f;
+    P.image = image;
+    P.loss = step->loss_acc;
+    P.grad = step->grad;
+    if (!use_small_kernel(P))
+        return fail(RRT_ERR_UNSUPPORTED, "whole-step kernel needs a small scene (<= 32 shapes, power-of-two samples)");
+    const rrt_scene& sc = P.sc;
+    P.lin_step = sc.n > 1 ? 1.0 / (double)(sc.n - 1) : 0.0;
+    P.inv_s = 1.0f / (float)sc.samples;
+    P.inv_n = 1.0f / (float)sc.n;
+    P.pow2 = ((sc.samples & (sc.samples - 1)) == 0) && ((sc.n & (sc.n - 1)) == 0);
+    const long long rays_scene = (long long)P.rows * sc.n * sc.samples;
+    dim3 grid((unsigned)((rays_scene + kSmallThreads - 1) / kSmallThreads), 1);
+    render_small_kernel<MODE_FUSED, true><<<grid, kSmallThreads, 0, (cudaStream_t)stream>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "whole-step kernel launch: %s", cudaGetErrorString(e));
     return RRT_OK;
 }
 

@@ -21,6 +21,80 @@ import torch
 from .util import get_epsilon  # noqa: F401
 
 
+class _WholeStep(object):
+    """One kernel launch per optimise step (rrt_small_step_mse) for a `Scene.mse_cost` closure
+    whose variables are exactly the parameters of the shapes' transform chains.  Raises
+    ValueError when the scene does not qualify (the caller then takes the general path)."""
+
+    def __init__(self, spec, tVars):
+        import ctypes as C
+        from . import _native as nat, render as R
+        from .transform import as_tensor
+        scene = spec['scene']
+        if not torch.cuda.is_available():
+            raise ValueError('no CUDA device')
+        dev = scene.device()
+        if dev.type != 'cuda':
+            raise ValueError('scene is not on a CUDA device')
+        st = scene._static(dev)
+        prog, cam_prog = st['prog'], st['cam_prog']
+        if prog is None or not prog.dynamic or cam_prog is None or cam_prog.dynamic or scene.camera.look_at.requires_grad:
+            raise ValueError('needs chain-expressible shape transforms with parameters and a constant camera')
+        if st['mat'] is None or st['light_t'] is None:
+            raise ValueError('materials and light must be constants')
+        if {id(p) for p in prog.param_tensors} != {id(v) for v in tVars}:
+            raise ValueError('the optimised variables must be exactly the parameters of the shape transforms')
+        cfg = scene.config(spec['antialias_samples'], cull=False)
+        N, S = len(scene.shapes), cfg.samples
+        if N < 1 or N > 32 or S > 32 or (S & (S - 1)) or cfg.shadows or cfg.n * cfg.n * S > (16 << 20):
+            raise ValueError('not a small scene')
+        if any(p.dtype != torch.float32 or p.device != dev for p in prog.param_tensors):
+            raise ValueError('parameters must be float32 tensors on the scene device')
+        # parameters move INTO the chain's value buffer; the user's tensors become views of it
+        values = prog.values().detach().clone().contiguous()
+        off = int(prog.const_block.numel())
+        self.param_begin = off
+        for p in prog.param_tensors:
+            p.data = values[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        if off != values.numel():
+            raise ValueError('unexpected chain value layout')
+        obj_type, _, mat, light, cam = scene.pack(dev)
+        jit = scene._jitter_for(cfg.n, cfg.samples, spec['jitter'], spec['seed'], dev)
+        self.target = as_tensor(spec['target']).to(dev, torch.float32).contiguous()
+        if self.target.numel() != cfg.n * cfg.n * 3:
+            raise ValueError('target must be [n, n, 3]')
+        G = nat.grad_size(N)
+        z = lambda n, dt: torch.zeros(n, dtype=dt, device=dev)
+        self.keep = dict(values=values, w2o=z(N * 12, torch.float32).reshape(N, 12), grad=z(G, torch.float32),
+                         g_values=z(values.numel(), torch.float32), loss_acc=z(1, torch.float64),
+                         loss_out=z(1, torch.float32), ticket=z(1, torch.int32), prog=prog)
+        k = self.keep
+        self.tables = R._Tables(cfg, obj_type, k['w2o'], mat.detach(), light.detach(), cam.detach(), jit)
+        s = nat.RrtStep()
+        s.ops, s.chain_begin, s.values = prog.ops.data_ptr(), prog.chain_begin.data_ptr(), values.data_ptr()
+        s.num_values, s.param_begin = int(values.numel()), int(self.param_begin)
+        s.grad, s.g_values, s.loss_acc = k['grad'].data_ptr(), k['g_values'].data_ptr(), k['loss_acc'].data_ptr()
+        # the step's loss is written by the kernel straight into pinned (mapped) host memory: no copy node
+        self.host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        s.loss_out, s.ticket = self.host.data_ptr(), k['ticket'].data_ptr()
+        self.step = s
+        cw = spec['channel_weight']
+        self.cw = (C.c_float * 3)(*[float(v) for v in cw]) if cw is not None else None
+        self.device, self.C, self.nat = dev, C, nat
+
+    def __call__(self, lr):
+        C, nat = self.C, self.nat
+        self.step.lr = float(lr)
+        stream = torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            rc = nat.lib().rrt_small_step_mse(C.byref(self.tables.desc), C.byref(self.step), self.target.data_ptr(), self.cw,
+                                              None, C.c_void_p(stream.cuda_stream))
+        nat.check(rc, 'rrt_small_step_mse')
+        stream.synchronize()
+        return float(self.host[0])
+
+
 class GDOptimizer(object):
     """Gradient descent: var <- var - lr * dloss/dvar (optimize.py:11-29).
 
@@ -43,7 +117,13 @@ class GDOptimizer(object):
             v.requires_grad_(True)
         default_lr = lr
         use_graph = bool(graph) and all(v.is_cuda for v in tVars)
-        st = dict(calls=0, graph=None, value=None, lr=None, failed=False)
+        st = dict(calls=0, graph=None, value=None, lr=None, failed=False, whole_step=None)
+        spec = getattr(loss, 'fused_spec', None)
+        if spec is not None and use_graph:         # Scene.mse_cost: try the one-launch step
+            try:
+                st['whole_step'] = _WholeStep(spec, tVars)
+            except ValueError as e:
+                st['whole_step_refused'] = str(e)
 
         def step(step_lr):
             value = loss()
@@ -84,6 +164,8 @@ class GDOptimizer(object):
             if step_lr is None:
                 raise TypeError('learning rate missing: call train(lr)')
             st['calls'] += 1
+            if st['whole_step'] is not None:
+                return st['whole_step'](step_lr)
             if use_graph and st['graph'] is None and not st['failed'] and st['calls'] > 2:
                 try:
                     capture()

@@ -283,6 +283,20 @@ class Scene(object):
         return (loss, image) if want_image else loss
 
 
+    def mse_cost(self, target, antialias_samples=4, channel_weight=None, jitter=None, seed=None):
+        """The cost expression `((scene.build() - target) ** 2).sum()` (match_mirror.py:45) as a
+        closure for GDOptimizer.optimize: calling it renders through the fused kernel like
+        build_mse; GDOptimizer additionally recognises it and, when the optimised variables
+        are exactly the parameters of the shapes' transforms of a small scene, runs the WHOLE
+        step (chains, render, loss, reverse pass, update) as one kernel launch
+        (rrt_small_step_mse)."""
+        def cost():
+            return self.build_mse(target, antialias_samples, channel_weight, jitter, seed)
+        cost.fused_spec = dict(scene=self, target=target, antialias_samples=antialias_samples,
+                               channel_weight=channel_weight, jitter=jitter, seed=seed)
+        return cost
+
+
 class _FusedMSE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, w2o, mat, light, cam, cfg, obj_type, jit, target, channel_weight, want_image):

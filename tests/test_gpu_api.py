@@ -351,3 +351,43 @@ def test_example_generate_data(cuda, tmp_path):
         hit = (sc.build(seed=0).detach()[..., 0] > 0).cpu().numpy()
         # same silhouette up to anti-alias edge pixels (different jitter)
         assert np.mean(hit != (data[k] > 0)) < 0.06
+
+
+def test_whole_step_kernel_matches_general_path(cuda):
+    """Scene.mse_cost + GDOptimizer: the whole optimise step as ONE kernel launch
+    (rrt_small_step_mse: chains, render, loss, reverse pass, finalize, chain backward, update)
+    follows the same trajectory as the general path (build_mse closure, autograd, CUDA graph)."""
+    def make():
+        c1 = torch.tensor([-.5, -.5, 4.], device=cuda)
+        c2 = torch.tensor([.5, .5, 4.], device=cuda)
+        s2 = torch.tensor([1., 1.6, 1.3], device=cuda)
+        m1 = Material((0.2, 0.9, 0.4), 0.3, 0.7, 0.5, 50.)
+        m2 = Material((0.87, 0.1, 0.507), 0.3, 0.9, 0.4, 50.)
+        objs = [Sphere(translate(c1), m1), Sphere(translate(c2) * rotate(40, (0, 0, 1)) * scale(s2), m2),
+                Square(translate((0, 0, 3)) * rotate(50, [0., 1., 0.]), m2)]
+        sc = Scene(objs, [Light((-1., -1., 2.), (1., 0.87, 0.961))], Camera(64, 64), PhongShader())
+        return sc, [c1, c2, s2]
+    scA, pA = make()
+    scB, pB = make()
+    target = torch.flip(scA.build(seed=3).detach(), dims=[1])
+    trainA = GDOptimizer().optimize(pA, scA.mse_cost(target, seed=3), 2e-5)
+    assert trainA.state['whole_step'] is not None, trainA.state.get('whole_step_refused')
+    trainB = GDOptimizer().optimize(pB, lambda: scB.build_mse(target, seed=3), 2e-5)
+    la, lb = [], []
+    for i in range(12):
+        la.append(trainA())
+        lb.append(trainB())
+    np.testing.assert_allclose(la, lb, rtol=2e-4)
+    assert la[-1] < la[0]
+    for a, b in zip(pA, pB):
+        np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().cpu().numpy(), rtol=1e-4, atol=1e-5)
+    # the user's tensors are live views: a plain render sees the updated parameters
+    np.testing.assert_allclose(scA.build(seed=3).detach().cpu().numpy(), scB.build(seed=3).detach().cpu().numpy(), atol=2e-3)
+    # scenes that do not qualify fall back to the general path (here: a variable that is no chain parameter)
+    extra = torch.tensor([1.0], device=cuda)
+    scC, pC = make()
+    cost = scC.mse_cost(target, seed=3)
+    trainC = GDOptimizer().optimize(pC[:2], cost, 2e-5)          # s2 left out -> refused
+    assert trainC.state['whole_step'] is None and 'exactly' in trainC.state['whole_step_refused']
+    l0 = trainC()
+    assert np.isfinite(l0)

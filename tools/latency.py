@@ -48,7 +48,8 @@ def c3(fused):
     objs = [Sphere(translate(c1), m1), Sphere(translate(c2), m2), Square(translate((0, 0, 3)) * rotate(50, [0., 1., 0.]), m2)]
     sc = Scene(objs, [Light((-1., -1., 2.), (1., 0.87, 0.961))], Camera(128, 128), PhongShader())
     flipped = torch.flip(sc.build().detach(), dims=[1])
-    cost = (lambda: sc.build_mse(flipped)) if fused else (lambda: ((sc.build() - flipped) ** 2).sum())
+    cost = ((lambda: sc.build_mse(flipped)) if fused == 'graph' else sc.mse_cost(flipped)) if fused else \
+        (lambda: ((sc.build() - flipped) ** 2).sum())
     return GDOptimizer().optimize([c1, c2], cost, 0.000008, 0.1), sc
 
 
@@ -67,9 +68,9 @@ if __name__ == '__main__':
     train, sc = c1()
     print('C1 optimize_brightness step: %.1f us' % timeit(train))
     print('C1 render only (scene.build): %.1f us' % timeit(lambda: sc.build()))
-    for fused in (False, True):
+    for fused in (False, 'graph', True):
         train, sc = c3(fused)
-        print('C3 match_mirror step (fused=%s): %.1f us' % (fused, timeit(train)))
+        print('C3 match_mirror step (fused=%s%s): %.1f us' % (fused, ', whole-step kernel' if train.state.get('whole_step') else '', timeit(train)))
     fn, rays = c4()
     us = timeit(fn, iters=100)
     print('C4 orbit batch 256x2 fused fwd+mse+bwd: %.1f us  -> %.0f Mrays/s' % (us, rays / us))

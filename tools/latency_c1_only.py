@@ -4,5 +4,5 @@ import torch
 from tools.latency import c1, c3, timeit
 train, sc = c1()
 print('C1 step us', timeit(train, warm=5, iters=20))
-train, sc = c3(True)
+train, sc = c3('graph')
 print('C3 fused step us', timeit(train, warm=5, iters=20))

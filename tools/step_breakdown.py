@@ -47,4 +47,4 @@ if __name__ == '__main__':
     if which in ('all', 'c1'):
         breakdown('C1', c1()[0])
     if which in ('all', 'c3'):
-        breakdown('C3 fused', c3(True)[0])
+        breakdown('C3 fused', c3('graph')[0])
