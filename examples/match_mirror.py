@@ -29,8 +29,8 @@ def main(steps=90, out='output', dump=True, fused=False):
         os.makedirs(out, exist_ok=True)
         draw(os.path.join(out, '0.png'), first)
         draw(os.path.join(out, '0lr.png'), mirrored)
-    # match_mirror.py:45 -- as tensor algebra, or as the fused single-kernel cost
-    cost = (lambda: scene.build_mse(mirrored)) if fused else (lambda: ((scene.build() - mirrored) ** 2).sum())
+    # match_mirror.py:45 -- as tensor algebra, or as Scene.mse_cost (whole step = one kernel launch)
+    cost = scene.mse_cost(mirrored) if fused else (lambda: ((scene.build() - mirrored) ** 2).sum())
     train = GDOptimizer().optimize(params, cost, 0.000008, 0.1)
     losses = C.run(train, steps, lambda: scene.build().detach(), out if dump else None, draw)
     return losses, params[0], params[1]

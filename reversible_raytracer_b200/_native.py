@@ -48,9 +48,11 @@ class NativeError(RuntimeError):
 
 
 def build(force=False, verbose=False):
-    """Compile csrc/rrt_kernels.cu for sm_100a into librrt_b200.so (in-tree)."""
-    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= max(
-            os.path.getmtime(SRC), os.path.getmtime(os.path.join(INCLUDE, 'rrt_b200.h'))):
+    """Compile csrc/rrt_kernels.cu (+ its .cuh parts, one translation unit) for sm_100a into
+    librrt_b200.so (in-tree)."""
+    srcs = [os.path.join(os.path.dirname(SRC), f) for f in os.listdir(os.path.dirname(SRC))] + \
+           [os.path.join(INCLUDE, 'rrt_b200.h')]
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(f) for f in srcs):
         return LIB_PATH
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     cmd = [nvcc] + NVCC_FLAGS + ['-I', INCLUDE, '-o', LIB_PATH, SRC]

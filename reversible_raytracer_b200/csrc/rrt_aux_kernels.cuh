@@ -1,0 +1,238 @@
+// rrt_aux_kernels.cuh -- part of rrt_kernels.cu (one translation unit; included inside its anonymous namespace).
+// Small kernels: record table, primary-ray table, gradient finalisation, peer-memory exchange, FP32 peak.
+#pragma once
+
+// ---------------------------------------------------------------- sweep-record table (for TMA staging)
+// grid = (chunks of kObjChunk objects, scenes).  Writes the 64-byte records the render kernels
+// bulk-copy into shared memory; the chunk's class bits (squares / general spheres present) go
+// into the spare slot of its first record.
+__global__ void __launch_bounds__(128) build_records_kernel(const rrt_scene sc, float* __restrict__ records) {
+    __shared__ int cls_s;
+    const int scene = blockIdx.y, kb = blockIdx.x * kObjChunk, N = sc.num_objects;
+    const int cnt = min(kObjChunk, N - kb);
+    if (threadIdx.x == 0) cls_s = 0;
+    __syncthreads();
+    const float* cam = sc.camera + (size_t)scene * sc.camera_scene_stride;
+    const float ct[3] = {__ldg(cam + 3), __ldg(cam + 7), __ldg(cam + 11)};
+    const float* w2o = sc.w2o + (size_t)scene * sc.w2o_scene_stride;
+    float4* out = reinterpret_cast<float4*>(records + ((size_t)scene * N + kb) * RRT_RECORD_FLOATS);
+    int cls = 0;
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+        Obj ob;
+        make_obj(w2o + (size_t)(kb + k) * RRT_W2O_STRIDE, sc.obj_type[kb + k], ct, ob, true);
+        store_rec(out + 4 * k, ob);
+        cls |= ob.flags;
+    }
+    if (cls) atomicOr(&cls_s, cls);
+    __syncthreads();
+    if (threadIdx.x == 0 && cnt > 0) reinterpret_cast<float*>(out)[15] = __int_as_float(cls_s);
+}
+
+// ---------------------------------------------------------------- primary-ray grid table
+__global__ void primary_rays_kernel(int n, double step, float* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= n) return;
+    float x, y, z;
+    base_ray(n, step, i, j, x, y, z);
+    float* o = out + ((size_t)i * n + j) * 3;
+    o[0] = x; o[1] = y; o[2] = z;
+}
+
+// ---------------------------------------------------------------- gradient finalisation
+// One CTA per scene.  Converts the raw per-object sums [M, g_b] into d/d w2o and
+// folds the camera and light chains (see backward_ray).
+__global__ void finalize_grads(const __grid_constant__ KParams P) {
+    const rrt_scene& sc = P.sc;
+    const int N = sc.num_objects, scene = blockIdx.x, tid = threadIdx.x;
+    float* gobj = P.grad + (size_t)scene * RRT_GRAD_SIZE(N);
+    float* gglobal = gobj + (size_t)N * RRT_OBJ_GRAD_STRIDE;
+    const float* cam = sc.camera + (size_t)scene * sc.camera_scene_stride;
+    const float* w2o = sc.w2o + (size_t)scene * sc.w2o_scene_stride;
+    __shared__ float camg[12];
+    if (tid < 12) camg[tid] = 0.f;
+    __syncthreads();
+    float C[9], ct[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        C[r * 3] = cam[r * 4]; C[r * 3 + 1] = cam[r * 4 + 1]; C[r * 3 + 2] = cam[r * 4 + 2];
+        ct[r] = cam[r * 4 + 3];
+    }
+    float cg[12];
+#pragma unroll
+    for (int q = 0; q < 12; q++) cg[q] = 0.f;
+    for (int k = tid; k < N; k += blockDim.x) {
+        float* og = gobj + (size_t)k * RRT_OBJ_GRAD_STRIDE;
+        float M[9], gb[3], A[9];
+#pragma unroll
+        for (int q = 0; q < 9; q++) M[q] = og[q];
+#pragma unroll
+        for (int q = 0; q < 3; q++) gb[q] = og[9 + q];
+        const float* w = w2o + (size_t)k * RRT_W2O_STRIDE;
+#pragma unroll
+        for (int r = 0; r < 3; r++) { A[r * 3] = w[r * 4]; A[r * 3 + 1] = w[r * 4 + 1]; A[r * 3 + 2] = w[r * 4 + 2]; }
+        // d/dA = M C^T + g_b ct^T ;  d/db = g_b        (d' = A C r, o' = A ct + b)
+        float out[12];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                out[r * 4 + c] = M[r * 3] * C[c * 3] + M[r * 3 + 1] * C[c * 3 + 1] + M[r * 3 + 2] * C[c * 3 + 2] + gb[r] * ct[c];
+            out[r * 4 + 3] = gb[r];
+        }
+#pragma unroll
+        for (int q = 0; q < 12; q++) og[q] = out[q];
+        if (sc.camera_grad) {
+            // d/dC = sum_k A_k^T M_k ; d/dct = sum_k A_k^T g_b,k
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    cg[r * 4 + c] += A[0 * 3 + r] * M[0 * 3 + c] + A[1 * 3 + r] * M[1 * 3 + c] + A[2 * 3 + r] * M[2 * 3 + c];
+                cg[r * 4 + 3] += A[0 * 3 + r] * gb[0] + A[1 * 3 + r] * gb[1] + A[2 * 3 + r] * gb[2];
+            }
+        }
+    }
+    if (sc.camera_grad) {
+#pragma unroll
+        for (int q = 0; q < 12; q++) {
+            float x = warp_sum(cg[q]);
+            if ((tid & 31) == 0 && x != 0.f) atomicAdd(&camg[q], x);
+        }
+    }
+    __syncthreads();
+    if (tid < 12) gglobal[6 + tid] = camg[tid];
+    if (tid == 0) {
+        // Lhat = L/|L|  =>  g_L = (g_Lhat - Lhat (Lhat . g_Lhat)) / |L|    scene.py:83-86
+        const float* li = sc.light + (size_t)scene * sc.light_scene_stride;
+        float L0 = li[0], L1 = li[1], L2 = li[2];
+        float ln = sqrtf(L0 * L0 + L1 * L1 + L2 * L2);
+        float h0 = L0 / ln, h1 = L1 / ln, h2 = L2 / ln;
+        float g0 = gglobal[0], g1 = gglobal[1], g2 = gglobal[2];
+        float dot = h0 * g0 + h1 * g1 + h2 * g2;
+        gglobal[0] = (g0 - h0 * dot) / ln;
+        gglobal[1] = (g1 - h1 * dot) / ln;
+        gglobal[2] = (g2 - h2 * dot) / ln;
+    }
+}
+
+// ---------------------------------------------------------------- gradient exchange over peer memory
+// The one exchange step of the sharded path (row slabs / scene ranges per GPU): every rank holds
+// a small vector [gradient (float32) | loss (float64)] and all ranks need the sum.  Instead of
+// an NCCL allreduce (plus the two copy kernels that pack its buffer) ONE kernel per rank
+//   1. PUSHES its values, converted to float64, into slot[rank] of every peer's buffer with
+//      plain stores through the NVLink peer mapping,
+//   2. publishes a per-(CTA, source) flag on every peer (fence + release store) and waits for
+//      the same flags from all peers (acquire loads) -- CTA c only depends on CTA c of the
+//      peers, so no grid-wide barrier is needed,
+//   3. sums the `world` slots in RANK ORDER (every rank gets the same bits; deterministic).
+// Buffers alternate by epoch parity: a rank can only start epoch e+2 after every peer has
+// finished reading epoch e (it needs their epoch e+1 flags first), so two copies suffice.
+// Flags carry the epoch number, one per source, so a fast peer's next epoch cannot be
+// mistaken for a slow peer's current one.
+constexpr int kPeerCtas = 16;
+constexpr int kPeerMaxWorld = 16;
+constexpr int kPeerEpochOffset = kPeerCtas * kPeerMaxWorld;   // per-CTA epoch counters (local use only)
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) peer_allreduce_kernel(const float* __restrict__ grad, const double* __restrict__ loss,
+                                                             int n, int nloss, void* const* __restrict__ peer_buf,
+                                                             void* const* __restrict__ peer_sig, int rank, int world,
+                                                             double* __restrict__ out) {
+    const int cta = blockIdx.x, tid = threadIdx.x;
+    unsigned* sig_local = reinterpret_cast<unsigned*>(peer_sig[rank]);
+    __shared__ unsigned epoch_s;
+    __shared__ int timed_out;
+    if (tid == 0) {
+        timed_out = 0;
+        epoch_s = sig_local[kPeerEpochOffset + cta] + 1u;
+        sig_local[kPeerEpochOffset + cta] = epoch_s;
+    }
+    __syncthreads();
+    const unsigned epoch = epoch_s;
+    const int total = n + nloss;
+    const int per = (total + gridDim.x - 1) / gridDim.x;
+    const int lo = cta * per, hi = min(total, lo + per);
+    const size_t slot = ((size_t)(epoch & 1u) * world + rank) * (size_t)total;
+    // 1. push
+    for (int i = lo + tid; i < hi; i += blockDim.x) {
+        const double v = i < n ? (double)grad[i] : loss[i - n];
+        for (int p = 0; p < world; p++) reinterpret_cast<double*>(peer_buf[p])[slot + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    // 2. publish + wait
+    if (tid < world) {
+        st_release_sys(reinterpret_cast<unsigned*>(peer_sig[tid]) + cta * kPeerMaxWorld + rank, epoch);
+        const unsigned* mine = sig_local + cta * kPeerMaxWorld + tid;
+        // bounded wait (~10 s): a peer that died must not hang this GPU; the sums become NaN
+        long long spins = 0;
+        while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
+            if (++spins > (1LL << 26)) { timed_out = 1; break; }
+            if (spins > 1024) __nanosleep(128);
+        }
+    }
+    __syncthreads();
+    // 3. sum in rank order
+    const double* local = reinterpret_cast<const double*>(peer_buf[rank]) + (size_t)(epoch & 1u) * world * (size_t)total;
+    for (int i = lo + tid; i < hi; i += blockDim.x) {
+        double sum = 0.0;
+        for (int p = 0; p < world; p++) sum += __ldcg(local + (size_t)p * total + i);
+        out[i] = timed_out ? __longlong_as_double(0x7ff8000000000000LL) : sum;
+    }
+}
+
+// ---------------------------------------------------------------- FP32 peak micro-benchmarks
+template <int MODE>
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float seed) {
+    if (MODE == 0) {
+        float a[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) a[q] = seed + (float)(threadIdx.x + q);
+        float b = 1.0000001f, c = 1e-7f;
+#pragma unroll 1
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int rep = 0; rep < 8; rep++)
+#pragma unroll
+                for (int q = 0; q < 16; q++) a[q] = __fmaf_rn(a[q], b, c);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; q++) s += a[q];
+        if (s == 123.456f) out[0] = s;
+    } else {
+        // MODE 1: packed FFMA2 only.  MODE 2: + one ALU-pipe FMNMX3 per 4 FFMA2 (diagnostic:
+        // does a non-FMA instruction issue in the shadow of an FFMA2 or cost its own cycle?)
+        u64 a[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) a[q] = pk(seed + (float)(threadIdx.x + q), seed - (float)q);
+        u64 b = pk(1.0000001f, 0.9999999f), c = pk(1e-7f, -1e-7f);
+        float m = 0.f;
+#pragma unroll 1
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int rep = 0; rep < 8; rep++)
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    a[q] = fma2(a[q], b, c);
+                    if (MODE == 2 && (q & 3) == 3) {
+                        float lo, hi;
+                        upk(a[q - 3], lo, hi);
+                        m = fmaxf(m, fmaxf(lo, hi));
+                    }
+                }
+        }
+        float s = m;
+#pragma unroll
+        for (int q = 0; q < 16; q++) { float lo, hi; upk(a[q], lo, hi); s += lo + hi; }
+        if (s == 123.456f) out[0] = s;
+    }
+}

@@ -1,0 +1,189 @@
+// rrt_shade.cuh -- part of rrt_kernels.cu (one translation unit; included inside its anonymous namespace).
+// Hard shadows, shading (forward value) and the closed-form reverse pass of one winning ray.
+#pragma once
+
+// ---------------------------------------------------------------- hard shadows (RRT_FLAG_SHADOWS)
+// Sphere.shadow, shape.py:85-97, at the (commented-out) call site scene.py:41-45, in the
+// caster's object space and canonical float32 order -- bit-identical to orc_shadowed in
+// oracle/oracle_c.c.  `t` is the winner's ray parameter.
+__device__ __forceinline__ bool shadow_test(const float4* __restrict__ rec, float wx, float wy, float wz, float t,
+                                            const float* U) {
+    Obj ob;
+    load_rec(rec, ob);
+    if (ob.flags & 1) return false;            // Square has no shadow method: casts none
+    const float d0 = dot3_canon(ob.a[0], ob.a[1], ob.a[2], wx, wy, wz);
+    const float d1 = dot3_canon(ob.a[3], ob.a[4], ob.a[5], wx, wy, wz);
+    const float d2 = dot3_canon(ob.a[6], ob.a[7], ob.a[8], wx, wy, wz);
+    const float y0 = __fmaf_rn(t, d0, ob.o[0]), y1 = __fmaf_rn(t, d1, ob.o[1]), y2 = __fmaf_rn(t, d2, ob.o[2]);
+    const float x = dot3_canon(y0, y1, y2, U[0], U[1], U[2]);
+    const float yy = dot3_canon(y0, y1, y2, y0, y1, y2);
+    const float dec = __fadd_rn(__fmaf_rn(x, x, -yy), 1.0f);
+    return dec > 0.0f && __fsub_rn(-x, __fsqrt_rn(dec)) >= 0.0f;
+}
+
+// General kernel: tests the thread's winning rays against one staged chunk of objects.
+// Scalar and divergent on purpose -- shadows are an opt-in extension outside the
+// roofline-accountable sweep; out of line so that the hot loop's registers are untouched.
+__device__ __noinline__ unsigned shadow_chunk(const float4* __restrict__ tab, int cnt, int kbase, const float* dw,
+                                              const float* tmin, const int* idx, const float* U, unsigned shadowed) {
+#pragma unroll 1
+    for (int r = 0; r < kRays; r++) {
+        const int win = idx[r];
+        if (win < 0 || (shadowed >> r & 1u)) continue;
+        const float t = tmin[r], wx = dw[r], wy = dw[kRays + r], wz = dw[2 * kRays + r];
+#pragma unroll 1
+        for (int k = 0; k < cnt; k++) {
+            if (kbase + k == win) continue;
+            if (shadow_test(tab + 4 * k, wx, wy, wz, t, U)) { shadowed |= 1u << r; break; }
+        }
+    }
+    return shadowed;
+}
+
+// ---------------------------------------------------------------- shading (float32)
+// x ** y like C pow() (Theano's T.pow, shader.py:45): integer-valued exponents up to
+// 1024 (shininess = 50 in every reference script) take square-and-multiply -- a
+// negative base is fine there, as in pow(); everything else goes to powf.
+__device__ __noinline__ float powf_general(float x, float y) { return powf(x, y); }
+
+__device__ __forceinline__ float pow_shininess(float x, float y) {
+    const int e = (int)y;
+    if ((float)e == y && e >= 0 && e <= 1024) {
+        float r = 1.0f, b = x;
+        int k = e;
+#pragma unroll 1
+        while (k) {
+            if (k & 1) r *= b;
+            b *= b;
+            k >>= 1;
+        }
+        return r;
+    }
+    return powf_general(x, y);
+}
+
+
+struct ShadeRec {
+    float t, d[3], o[3], pn, nrm[3], ndl, rm[3], rv, pw, ph;
+    bool inside[3];
+};
+
+__device__ __forceinline__ void shade(int shader, float max_depth, const Obj& ob, const float* mat, const Globals& g,
+                                      const HitRec& h, ShadeRec& r, float rgb[3]) {
+    r.t = h.t;
+#pragma unroll
+    for (int c = 0; c < 3; c++) { r.d[c] = h.d[c]; r.o[c] = ob.o[c]; }
+    if (shader == RRT_SHADER_DEPTH) {  // shader.py:14-20
+        float v = 1.0f - r.t / max_depth;
+        rgb[0] = rgb[1] = rgb[2] = v;
+        return;
+    }
+    if (!(ob.flags & 1)) {  // Sphere.normals shape.py:134-137 (object-space normal)
+        float p0 = fmaf(r.t, r.d[0], r.o[0]), p1 = fmaf(r.t, r.d[1], r.o[1]), p2 = fmaf(r.t, r.d[2], r.o[2]);
+        const float pn2 = p0 * p0 + p1 * p1 + p2 * p2;
+        const float inv = rsqrtf(pn2);
+        r.pn = pn2 * inv;
+        r.nrm[0] = p0 * inv; r.nrm[1] = p1 * inv; r.nrm[2] = p2 * inv;
+    } else {                // Square.normals shape.py:55-68
+        r.nrm[0] = r.nrm[1] = 0.f;
+        r.nrm[2] = (ob.o[2] > 0.0f) ? 1.0f : -1.0f;
+        r.pn = 1.0f;
+    }
+    r.ndl = -(r.nrm[0] * g.Lh[0] + r.nrm[1] * g.Lh[1] + r.nrm[2] * g.Lh[2]);  // shader.py:40
+    r.ph = mat[0] + mat[1] * r.ndl;
+    r.rv = 0.f; r.pw = 0.f;
+    if (shader == RRT_SHADER_PHONG) {  // shader.py:43-45
+#pragma unroll
+        for (int c = 0; c < 3; c++) r.rm[c] = 2.0f * r.ndl * r.nrm[c] + g.Lh[c];
+        r.rv = r.rm[0] * g.look[0] + r.rm[1] * g.look[1] + r.rm[2] * g.look[2];
+        r.pw = pow_shininess(r.rv, mat[3]);
+        r.ph += mat[2] * r.pw;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {      // shader.py:50-51
+        float v = r.ph * mat[4 + c] * g.I[c];
+        r.inside[c] = (v >= 0.0f && v <= 1.0f);
+        rgb[c] = fminf(fmaxf(v, 0.0f), 1.0f);
+    }
+}
+
+// ---------------------------------------------------------------- reverse pass, one winning ray
+// Closed form of T.grad through the winner (masks constant).  og[19] receives
+// [M = sum g_d' r_cam^T (9), g_b = sum g_o' (3), d/d(ka,kd,ks,sh,r,g,b)];
+// gg[9] receives [d/d Lhat (3), d/d intensity (3), d/d look_at (3)].
+// The chain M -> d/dA, d/d camera and Lhat -> L is applied by finalize_grads.
+__device__ __forceinline__ void backward_ray(int shader, float max_depth, const Obj& ob, const float* mat,
+                                             const Globals& g, const HitRec& h, const ShadeRec& r, const float rc[3],
+                                             const float gc[3], float og[19], float gg[9]) {
+    float g_t = 0.f;
+    float g_o[3] = {0.f, 0.f, 0.f}, g_d[3] = {0.f, 0.f, 0.f};
+    const bool sphere = !(ob.flags & 1);
+    if (shader == RRT_SHADER_DEPTH) {
+        g_t = -(gc[0] + gc[1] + gc[2]) / max_depth;
+    } else {
+        float g_ph = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (!r.inside[c]) continue;
+            g_ph += gc[c] * mat[4 + c] * g.I[c];
+            og[16 + c] += gc[c] * r.ph * g.I[c];
+            gg[3 + c] += gc[c] * r.ph * mat[4 + c];
+        }
+        og[12] += g_ph;
+        og[13] += g_ph * r.ndl;
+        float g_ndl = g_ph * mat[1];
+        float g_n[3] = {0.f, 0.f, 0.f}, g_Lh[3] = {0.f, 0.f, 0.f};
+        if (shader == RRT_SHADER_PHONG) {
+            og[14] += g_ph * r.pw;
+            if (r.rv > 0.0f) og[15] += g_ph * mat[2] * r.pw * __logf(r.rv);
+            float dpw = (r.rv != 0.0f) ? __fdividef(r.pw, r.rv) : pow_shininess(r.rv, mat[3] - 1.0f);  // rv^(sh-1)
+            float g_rv = g_ph * mat[2] * mat[3] * dpw;
+            float g_rm[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                g_rm[c] = g_rv * g.look[c];
+                gg[6 + c] += g_rv * r.rm[c];
+            }
+            g_ndl += 2.0f * (g_rm[0] * r.nrm[0] + g_rm[1] * r.nrm[1] + g_rm[2] * r.nrm[2]);
+#pragma unroll
+            for (int c = 0; c < 3; c++) { g_n[c] += 2.0f * r.ndl * g_rm[c]; g_Lh[c] += g_rm[c]; }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) { g_n[c] -= g_ndl * g.Lh[c]; g_Lh[c] -= g_ndl * r.nrm[c]; }
+#pragma unroll
+        for (int c = 0; c < 3; c++) gg[c] += g_Lh[c];
+        if (sphere) {
+            float ndg = r.nrm[0] * g_n[0] + r.nrm[1] * g_n[1] + r.nrm[2] * g_n[2];
+            float inv = __frcp_rn(r.pn);
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                float gp = (g_n[c] - r.nrm[c] * ndg) * inv;
+                g_o[c] = gp;
+                g_t += gp * r.d[c];
+                g_d[c] = r.t * gp;
+            }
+        }
+    }
+    if (sphere) {
+        float ivn = __frcp_rn(h.vn);
+        float g_pd = -g_t * ivn, g_s = -g_t * ivn, g_vn = -g_t * r.t * ivn;
+        float g_det = g_s * 0.5f * rsqrtf(h.det);
+        g_pd += 2.0f * h.pd * g_det;
+        g_vn += ob.ncc * g_det;            // -cc * g_det
+        float g_cc = -h.vn * g_det;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            g_o[c] += 2.0f * r.o[c] * g_cc + r.d[c] * g_pd;
+            g_d[c] += r.o[c] * g_pd + 2.0f * r.d[c] * g_vn;
+        }
+    } else {  // t = -o'_z / d'_z
+        g_o[2] += -g_t / r.d[2];
+        g_d[2] += -g_t * r.t / r.d[2];
+    }
+#pragma unroll
+    for (int rr = 0; rr < 3; rr++) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) og[rr * 3 + c] += g_d[rr] * rc[c];
+        og[9 + rr] += g_o[rr];
+    }
+}

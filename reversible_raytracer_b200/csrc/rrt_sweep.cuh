@@ -1,0 +1,170 @@
+// rrt_sweep.cuh -- part of rrt_kernels.cu (one translation unit; included inside its anonymous namespace).
+// The packed nearest-hit sweep (hot loop), its rare path, and TMA staging of prebuilt records.
+#pragma once
+
+// ---------------------------------------------------------------- packed sweep
+template <bool GENERAL>
+__device__ __forceinline__ u64 pair_det(const float4& q0, const float4& q1, const float4& q2, const float4& q3,
+                                        u64 dx, u64 dy, u64 dz) {
+    u64 ex, ey, ez;
+    if (GENERAL) {
+        ex = fma2(bc(q2.y), dz, fma2(bc(q2.x), dy, mul2(bc(q0.x), dx)));
+        ey = fma2(bc(q2.w), dz, fma2(bc(q0.y), dy, mul2(bc(q2.z), dx)));
+        ez = fma2(bc(q0.z), dz, fma2(bc(q3.y), dy, mul2(bc(q3.x), dx)));
+    } else {
+        ex = mul2(bc(q0.x), dx);
+        ey = mul2(bc(q0.y), dy);
+        ez = mul2(bc(q0.z), dz);
+    }
+    u64 vn = fma2(ez, ez, fma2(ey, ey, mul2(ex, ex)));
+    u64 pd = fma2(ez, bc(q1.y), fma2(ey, bc(q1.x), mul2(ex, bc(q0.w))));
+    return fma2(pd, pd, mul2(vn, bc(q1.z)));
+}
+
+struct RayPack {
+    u64 dx[kRays / 2], dy[kRays / 2], dz[kRays / 2];
+};
+
+// Rare path of the sweep, out of line on purpose (keeps the hot loop's register and
+// code footprint small).  Re-tests `cnt` staged objects (chunk-local k0..k0+cnt-1,
+// global index kbase+k) against the thread's 8 rays, re-read from local memory
+// (SoA [x0..x7|y0..y7|z0..z7], 16-byte aligned): packed discriminants first, then
+// the scalar canonical-order routine only for the (ray, object) pairs with det > 0.
+// List order + strict '<' == scene.py:46-47 (the earlier shape wins ties).
+__device__ __noinline__ void rare_group(const float4* __restrict__ tab, int k0, int cnt, int kbase,
+                                        const float* dw, float* tmin, int* idx) {
+    const u64* dp = reinterpret_cast<const u64*>(dw);
+    u64 dx[kRays / 2], dy[kRays / 2], dz[kRays / 2];
+#pragma unroll
+    for (int p = 0; p < kRays / 2; p++) { dx[p] = dp[p]; dy[p] = dp[kRays / 2 + p]; dz[p] = dp[kRays + p]; }
+#pragma unroll 1
+    for (int j = 0; j < cnt; j++) {
+        const float4* rec = tab + 4 * (k0 + j);
+        const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2], q3 = rec[3];
+        const bool square = __float_as_int(q1.w) & 1;
+        float det[kRays];
+#pragma unroll
+        for (int p = 0; p < kRays / 2; p++) upk(pair_det<true>(q0, q1, q2, q3, dx[p], dy[p], dz[p]), det[2 * p], det[2 * p + 1]);
+        unsigned hits = 0;
+#pragma unroll
+        for (int r = 0; r < kRays; r++) hits |= ((square || det[r] > 0.0f) ? 1u : 0u) << r;
+        if (!hits) continue;
+        Obj ob;
+        load_rec(rec, ob);
+#pragma unroll 1
+        while (hits) {
+            const int r = __ffs(hits) - 1;
+            hits &= hits - 1;
+            HitRec h;
+            const float t = obj_test(ob, dw[r], dw[kRays + r], dw[2 * kRays + r], h);
+            if (t < tmin[r]) { tmin[r] = t; idx[r] = kbase + k0 + j; }
+        }
+    }
+}
+
+constexpr int kGroup = RRT_GROUP;  // objects per branch in the hot loop
+
+// max over the 8 dets of one object, folded into the running group max (FMNMX3 chain;
+// fmaxf drops NaN, and NaN is a miss: shape.py:124-125)
+// LDS.128 from a 32-bit shared-window address: keeps the hot loop free of the
+// generic->shared address arithmetic (S2UR/ULEA per iteration) a float4* would cost.
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+
+// ---------------------------------------------------------------- TMA staging of precomputed records
+// One elected thread arms an mbarrier with the chunk's byte count and issues ONE bulk copy
+// global -> shared (cp.async.bulk, SASS UBLKCP); every thread then waits on the barrier's
+// phase.  Replaces ~90 instructions per object and thread of in-CTA record building.
+__device__ __forceinline__ void mbar_init(uint32_t mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_bulk_load(uint32_t dst, const void* src, unsigned bytes, uint32_t mbar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, unsigned phase) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(mbar), "r"(phase) : "memory");
+    } while (!ok);
+}
+
+// Out of line on purpose, like rare_group: keeps the render kernel's register allocation
+// around the hot loop exactly as it is without the record table.  The barrier's phase lives in
+// shared memory (flipped by thread 0 after the CTA-wide barrier that follows every staging).
+__device__ __noinline__ void stage_records_tma(float4* smem_tab, const float* src, int cnt, unsigned long long* bar,
+                                               const unsigned* phase_s, int* chunk_class, int tid) {
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(bar);
+    const unsigned phase = *phase_s;
+    if (tid == 0) tma_bulk_load((uint32_t)__cvta_generic_to_shared(smem_tab), src, (unsigned)cnt * 64u, mbar);
+    mbar_wait(mbar, phase);
+    // rrt_build_records left the chunk's class bits in the spare slot of its first record
+    if (tid == 0 && chunk_class) *chunk_class |= __float_as_int(smem_tab[3].w);
+}
+
+template <bool GENERAL>
+__device__ __forceinline__ float object_max_det(uint32_t rec, const RayPack& rp, float gmax) {
+    float4 q0 = lds128(rec), q1 = lds128(rec + 16);
+    float4 q2 = q0, q3 = q0;
+    if (GENERAL) { q2 = lds128(rec + 32); q3 = lds128(rec + 48); }
+#pragma unroll
+    for (int p = 0; p < kRays / 2; p++) {
+        float lo, hi;
+        upk(pair_det<GENERAL>(q0, q1, q2, q3, rp.dx[p], rp.dy[p], rp.dz[p]), lo, hi);
+        gmax = fmaxf(gmax, fmaxf(lo, hi));
+    }
+    return gmax;
+}
+
+// Sweep `count` staged SPHERES over the thread's 8 rays.  The hot loop is branch-free
+// over groups of kGroup objects: packed FFMA2 discriminants, a running max, ONE
+// compare-and-branch per group; a group with any det > 0 (rare: ~1e-3 per object and
+// warp) is re-evaluated by the scalar canonical routine.  GENERAL=false is the
+// diagonal fast path (translate*scale objects): exact-zero off-diagonals make it
+// bit-identical to the general form.
+template <bool GENERAL>
+__device__ __forceinline__ void sweep_spheres(const float4* __restrict__ tab, int count, int kbase, const RayPack& rp,
+                                              const float* dw, float* tmin, int* idx) {
+    // one induction variable (the shared-window address) and a warp-uniform branch keep the
+    // loop control at compare+branch; the object index is only reconstructed on the rare path
+    constexpr int kUnroll = RRT_SWEEP_UNROLL;   // groups per loop trip (loop control amortised over kUnroll*kGroup objects)
+    uint32_t rec0 = (uint32_t)__cvta_generic_to_shared(tab);
+    uint32_t rec_end = rec0 + 64u * (uint32_t)(count - count % (kGroup * kUnroll));
+    // launder both through an opaque move: otherwise ptxas rematerialises the shared-window
+    // arithmetic (S2UR/ULEA) inside the loop instead of keeping two registers live
+    asm volatile("mov.u32 %0, %0;" : "+r"(rec0));
+    asm volatile("mov.u32 %0, %0;" : "+r"(rec_end));
+    uint32_t rec = rec0;
+#pragma unroll 1
+    for (; rec != rec_end; rec += 64 * kGroup * kUnroll) {
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            float gmax = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kGroup; j++) gmax = object_max_det<GENERAL>(rec + 64 * (u * kGroup + j), rp, gmax);
+            if (__builtin_expect(__any_sync(0xffffffffu, gmax > 0.0f), 0))
+                rare_group(tab, (int)((rec - rec0) >> 6) + u * kGroup, kGroup, kbase, dw, tmin, idx);
+        }
+    }
+    const int k = count - count % (kGroup * kUnroll);
+    if (k < count) rare_group(tab, k, count - k, kbase, dw, tmin, idx);
+}
+
+// Chunks that contain squares: spheres get the packed pre-test one by one, squares
+// always take the scalar routine.
+__device__ __forceinline__ void sweep_mixed(const float4* __restrict__ tab, int count, int kbase, const RayPack& rp,
+                                            const float* dw, float* tmin, int* idx) {
+#pragma unroll 1
+    for (int k = 0; k < count; k++) {
+        const int flags = __float_as_int(tab[4 * k + 1].w);
+        float gmax = 1.0f;
+        if (!(flags & 1)) gmax = object_max_det<true>((uint32_t)__cvta_generic_to_shared(tab + 4 * k), rp, 0.0f);
+        if (gmax > 0.0f) rare_group(tab, k, 1, kbase, dw, tmin, idx);
+    }
+}
