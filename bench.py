@@ -192,6 +192,25 @@ def other_configs(dev):
     return out
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs next to its GPU BEFORE any pinned host buffer is touched
+    (first-touch NUMA placement): with 8 ranks moving image slabs over PCIe every step, remote
+    host memory is what the copies wait for.  Best effort; returns the CPU count or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        cpus = {i * 64 + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:       # noqa: BLE001
+        pass
+    return None
+
+
 # ------------------------------------------------------------------ GPU leg
 def run_b200(args):
     import torch
@@ -203,6 +222,7 @@ def run_b200(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device: there is no CPU fallback for the product path')
+    numa_cpus = bind_to_gpu_numa_node(local) if world > 1 else None
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
@@ -445,6 +465,7 @@ def run_b200(args):
                                n=n, samples=S, objects=N, sharding='row slabs, %d rows per GPU' % rows_per,
                                collective=collective,
                                l2='256 MiB flush write between timed iterations (outside the timed intervals)',
+                               host_cpus_bound_to_gpu_numa_node=numa_cpus,
                                jitter='in-kernel counter RNG, seed 4321'),
                    e2e=dict(value=e2e_streamed_value, unit='Mrays/s', h2d_bytes_per_step=h2d + full_bytes,
                             d2h_bytes_per_step=d2h + full_bytes,

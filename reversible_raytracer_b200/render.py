@@ -223,9 +223,10 @@ class StreamedFusedMSE:
     def __init__(self, cfg, num_objects, device, slabs=None, want_image=True):
         self.cfg, self.N, self.device = cfg, int(num_objects), torch.device(device)
         if slabs is None:
-            # measured on C5 (4096 rows): 4 / 8 / 16 / 24 / 32 slabs -> 26.9 / 25.6 / 24.9 / 24.7 / 24.9 ms
-            # against 24.3 ms with everything resident; keep slabs >= ~160 rows (several grid waves)
-            slabs = max(1, min(32, cfg.rows // 160))
+            # measured on C5 (tools/streamed_probe.py): 4096 rows: 16 / 24 / 32 slabs -> 24.89 / 24.67 /
+            # 24.62 ms against 24.28 ms resident; a 512-row slab (one of 8 GPUs): 3 / 6 / 12 / 16 slabs ->
+            # 3.53 / 3.35 / 3.31 / 3.35 ms against 3.14 ms.  => slabs of >= ~44 rows, at most 32 of them
+            slabs = max(1, min(32, cfg.rows // 44))
         rows, slabs = cfg.rows, max(1, min(int(slabs), cfg.rows))
         per = (rows + slabs - 1) // slabs
         per = (per + 3) // 4 * 4                      # whole CTAs (4 rows each) per slab
