@@ -90,6 +90,9 @@ extern "C" {
  * RRT_HIT_SHADOWED or-ed in, so the shadow mask is observable and testable bit for bit. */
 #define RRT_FLAG_SHADOWS 4
 #define RRT_HIT_SHADOWED 0x40000000
+/* Diagnostic: run the shadow pass of the general kernel with the scalar routine only (the
+ * packed FFMA2 filter in front of it is exact, so results are identical; A/B and tests). */
+#define RRT_FLAG_SCALAR_SHADOWS 8
 
 #define RRT_OK 0
 #define RRT_ERR_INVALID (-1)   /* bad argument (message in rrt_last_error)            */

@@ -117,7 +117,7 @@ EXPORTS = ['rrt_version', 'rrt_last_error', 'rrt_render_forward', 'rrt_render_ba
            'rrt_peer_allreduce', 'rrt_peer_buffer_bytes', 'rrt_peer_signal_bytes', 'rrt_build_records',
            'rrt_small_step_mse']
 
-FLAG_CULL, FLAG_NO_SMALL, FLAG_SHADOWS = 1, 2, 4
+FLAG_CULL, FLAG_NO_SMALL, FLAG_SHADOWS, FLAG_SCALAR_SHADOWS = 1, 2, 4, 8
 HIT_SHADOWED = 0x40000000
 CHAIN_TRANSLATE, CHAIN_SCALE, CHAIN_ROTATE, CHAIN_INVERT, CHAIN_MAX_OPS = 1, 2, 3, 0x100, 8
 

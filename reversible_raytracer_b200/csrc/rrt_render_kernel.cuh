@@ -328,7 +328,9 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                     __syncthreads();
                     if (sc.obj_records && tid == 0) tma_phase ^= 1u;
                 }
-                shadowed = shadow_chunk(smem_tab, cnt, kb, l_dw, l_tmin, l_idx, g.U, shadowed);
+                shadowed = (sc.flags & RRT_FLAG_SCALAR_SHADOWS)
+                               ? shadow_chunk(smem_tab, cnt, kb, l_dw, l_tmin, l_idx, g.U, shadowed)
+                               : shadow_chunk_packed(smem_tab, cnt, kb, l_dw, l_tmin, l_idx, g.U, shadowed);
             }
         }
 

@@ -40,6 +40,87 @@ __device__ __noinline__ unsigned shadow_chunk(const float4* __restrict__ tab, in
     return shadowed;
 }
 
+// Packed form of the same pass for chunks of spheres: the decider of 8 rays against one object
+// as FFMA2/FMUL2 (bit-identical to shadow_test's scalar arithmetic, so it is an EXACT filter),
+// folded into a running max; only (ray, object) pairs with dec > 0 -- the ray's own winner and
+// real occluder candidates -- take the scalar routine, which makes the decision.
+__device__ __forceinline__ u64 neg2(u64 v) { return v ^ 0x8000000080000000ULL; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+template <bool GENERAL>
+__device__ __forceinline__ u64 pair_dec(const float4& q0, const float4& q1, const float4& q2, const float4& q3,
+                                        u64 dx, u64 dy, u64 dz, u64 t2, float U0, float U1, float U2) {
+    u64 ex, ey, ez;
+    if (GENERAL) {
+        ex = fma2(bc(q2.y), dz, fma2(bc(q2.x), dy, mul2(bc(q0.x), dx)));
+        ey = fma2(bc(q2.w), dz, fma2(bc(q0.y), dy, mul2(bc(q2.z), dx)));
+        ez = fma2(bc(q0.z), dz, fma2(bc(q3.y), dy, mul2(bc(q3.x), dx)));
+    } else {
+        ex = mul2(bc(q0.x), dx);
+        ey = mul2(bc(q0.y), dy);
+        ez = mul2(bc(q0.z), dz);
+    }
+    const u64 y0 = fma2(t2, ex, bc(q0.w)), y1 = fma2(t2, ey, bc(q1.x)), y2 = fma2(t2, ez, bc(q1.y));
+    const u64 x = fma2(y2, bc(U2), fma2(y1, bc(U1), mul2(y0, bc(U0))));
+    const u64 yy = fma2(y2, y2, fma2(y1, y1, mul2(y0, y0)));
+    return add2(fma2(x, x, neg2(yy)), bc(1.0f));
+}
+
+__device__ __noinline__ unsigned shadow_chunk_packed(const float4* __restrict__ tab, int cnt, int kbase, const float* dw,
+                                                     const float* tmin, const int* idx, const float* U, unsigned shadowed) {
+    const u64* dp = reinterpret_cast<const u64*>(dw);
+    u64 dx[kRays / 2], dy[kRays / 2], dz[kRays / 2], tp[kRays / 2];
+    const float nan = __int_as_float(0x7fc00000);
+#pragma unroll
+    for (int p = 0; p < kRays / 2; p++) {
+        dx[p] = dp[p]; dy[p] = dp[kRays / 2 + p]; dz[p] = dp[kRays + p];
+        // rays without a (still lit) winner carry t = NaN: their decider is NaN, never > 0
+        const float t0 = (idx[2 * p] >= 0 && !(shadowed >> (2 * p) & 1u)) ? tmin[2 * p] : nan;
+        const float t1 = (idx[2 * p + 1] >= 0 && !(shadowed >> (2 * p + 1) & 1u)) ? tmin[2 * p + 1] : nan;
+        tp[p] = pk(t0, t1);
+    }
+    const float U0 = U[0], U1 = U[1], U2 = U[2];
+#pragma unroll 1
+    for (int k = 0; k < cnt; k++) {
+        const float4* rec = tab + 4 * k;
+        const float4 q0 = rec[0], q1 = rec[1];
+        const int flags = __float_as_int(q1.w);
+        if (flags & 1) continue;                           // squares cast no shadow
+        float dec[kRays];
+        float gmax = 0.0f;
+        if (flags & 2) {
+            const float4 q2 = rec[2], q3 = rec[3];
+#pragma unroll
+            for (int p = 0; p < kRays / 2; p++) {
+                upk(pair_dec<true>(q0, q1, q2, q3, dx[p], dy[p], dz[p], tp[p], U0, U1, U2), dec[2 * p], dec[2 * p + 1]);
+                gmax = fmaxf(gmax, fmaxf(dec[2 * p], dec[2 * p + 1]));
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < kRays / 2; p++) {
+                upk(pair_dec<false>(q0, q1, q0, q0, dx[p], dy[p], dz[p], tp[p], U0, U1, U2), dec[2 * p], dec[2 * p + 1]);
+                gmax = fmaxf(gmax, fmaxf(dec[2 * p], dec[2 * p + 1]));
+            }
+        }
+        if (!(gmax > 0.0f)) continue;
+#pragma unroll
+        for (int r = 0; r < kRays; r++) {
+            if (dec[r] > 0.0f && kbase + k != idx[r] &&
+                shadow_test(rec, dw[r], dw[kRays + r], dw[2 * kRays + r], tmin[r], U)) {
+                shadowed |= 1u << r;
+                float lo, hi;
+                upk(tp[r / 2], lo, hi);
+                tp[r / 2] = (r & 1) ? pk(lo, nan) : pk(nan, hi);
+            }
+        }
+    }
+    return shadowed;
+}
+
 // ---------------------------------------------------------------- shading (float32)
 // x ** y like C pow() (Theano's T.pow, shader.py:45): integer-valued exponents up to
 // 1024 (shininess = 50 in every reference script) take square-and-multiply -- a

@@ -32,7 +32,8 @@ class RenderConfig:
     cull: int = 0                       # 1: conservative per-tile object culling (bit-identical results, less work)
     no_small: int = 0                   # 1: never take the small-scene (one ray per thread) kernel (A/B, tests)
     use_records: int = 1                # 0: never precompute / TMA-stage the sweep records (A/B, tests)
-    shadows: int = 0                    # 1: hard shadows (scene.py:41-45 + shape.py:85-97; include/rrt_b200.h)
+    shadows: int = 0                    # 1: hard shadows (scene.py:41-45 + shape.py:85-97; include/rrt_b200.h);
+                                        # 2: same, scalar pass only in the general kernel (A/B, tests)
 
     @property
     def rows(self):
@@ -109,7 +110,7 @@ class _Tables:
         d.row_begin, d.row_count = cfg.row_begin, cfg.row_count
         d.scene_begin = cfg.scene_begin
         d.flags = ((nat.FLAG_CULL if cfg.cull else 0) | (nat.FLAG_NO_SMALL if cfg.no_small else 0) |
-                   (nat.FLAG_SHADOWS if cfg.shadows else 0))
+                   (nat.FLAG_SHADOWS if cfg.shadows else 0) | (nat.FLAG_SCALAR_SHADOWS if cfg.shadows == 2 else 0))
         d.max_depth, d.camera_grad, d.seed = cfg.max_depth, cfg.camera_grad, cfg.seed & 0xFFFFFFFFFFFFFFFF
         d.obj_type, d.w2o, d.material = self.obj_type.data_ptr(), self.w2o.data_ptr(), self.material.data_ptr()
         d.light, d.camera = self.light.data_ptr(), self.camera.data_ptr()

@@ -502,6 +502,11 @@ def test_shadows_parity(case, cuda):
     np.testing.assert_allclose(image.cpu().numpy().reshape(image_o.shape), image_o, rtol=PIX_RTOL, atol=PIX_ATOL)
     np.testing.assert_allclose(float(loss), loss_o[0], rtol=1e-4)
     compare_grads(grad.cpu().numpy().astype(np.float64), grad_o[0], ps.N)
+    # general kernel: packed (FFMA2) filter + scalar decision == scalar pass only (RRT_FLAG_SCALAR_SHADOWS)
+    from dataclasses import replace
+    for mode in (1, 2):
+        h2 = R.render_forward(replace(cfg, no_small=1, shadows=mode), ot, w2o, mat, light, cam, jit, want_hit=True)[1]
+        assert np.array_equal(h2.cpu().numpy().reshape(hit_o.shape), hit_o), mode
     dl = rng.normal(0, 1, img_o.shape).astype(np.float32)
     gb_o = oc.render_backward(ps, dl, hit_o)
     for stored in (True, False):

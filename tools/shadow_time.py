@@ -12,9 +12,9 @@ for n, N in ((1024, 256), (4096, 1024)):
     args = (t(tb['obj_type']), t(tb['w2o']), t(tb['material']), t(tb['light']), t(tb['camera']))
     cfg = R.RenderConfig(n=n, samples=4, shader=nat.SHADER_PHONG, transpose=1, seed=4321)
     target = R.render_forward(cfg, args[0], t(tt['w2o']), *args[2:], None, want_hit=False)[0]
-    for sh in (0, 1):
+    for sh in (0, 2, 1):
         c = replace(cfg, shadows=sh)
         ms = timeit(lambda: R.render_fused_mse(c, *args, target, want_image=True), warm=1, iters=3) / 1e3
         _, hit, _ = R.render_forward(c, *args, None, want_hit=True)
         frac = float(((hit >= 0) & ((hit & nat.HIT_SHADOWED) != 0)).sum()) / max(1.0, float((hit >= 0).sum()))
-        print('n=%d N=%d shadows=%d: fused %.2f ms, shadowed winners %.1f%%' % (n, N, sh, ms, 100 * frac))
+        print('n=%d N=%d shadows=%d (2 = scalar pass only): fused %.2f ms, shadowed winners %.1f%%' % (n, N, sh, ms, 100 * frac))
