@@ -477,7 +477,10 @@ def run_b200(args):
                                 value=e2e_value, unit='Mrays/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                                 note='target stays resident like the reference\'s compiled-in constant '
                                      '(match_mirror.py:45); only the parameter tables go up and loss + gradients come back')),
-                   gpu_launches=(2 + (1 if peer is not None else 0)) * args.steps, clocks=sampler.summary())
+                   # per step: rrt_build_records (>= 64 objects), the fused render kernel, finalize_grads,
+                   # and at N > 1 the peer-memory exchange kernel
+                   gpu_launches=(2 + (1 if N >= R.RECORDS_MIN_N else 0) + (1 if peer is not None else 0)) * args.steps,
+                   clocks=sampler.summary())
         if kernel_ms is not None:
             out['rank0_step_ms'] = [round(a.elapsed_time(b), 3) for a, b in evs]
             out['per_rank_render_ms'] = kernel_ms     # fused kernel + finalize per rank, before the allreduce
