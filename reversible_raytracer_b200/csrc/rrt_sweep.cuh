@@ -21,6 +21,25 @@ __device__ __forceinline__ u64 pair_det(const float4& q0, const float4& q1, cons
     return fma2(pd, pd, mul2(vn, bc(q1.z)));
 }
 
+// same arithmetic, also returning vn and pd (the rare path finishes t from them)
+template <bool GENERAL>
+__device__ __forceinline__ u64 pair_det_full(const float4& q0, const float4& q1, const float4& q2, const float4& q3,
+                                             u64 dx, u64 dy, u64 dz, u64& vn, u64& pd) {
+    u64 ex, ey, ez;
+    if (GENERAL) {
+        ex = fma2(bc(q2.y), dz, fma2(bc(q2.x), dy, mul2(bc(q0.x), dx)));
+        ey = fma2(bc(q2.w), dz, fma2(bc(q0.y), dy, mul2(bc(q2.z), dx)));
+        ez = fma2(bc(q0.z), dz, fma2(bc(q3.y), dy, mul2(bc(q3.x), dx)));
+    } else {
+        ex = mul2(bc(q0.x), dx);
+        ey = mul2(bc(q0.y), dy);
+        ez = mul2(bc(q0.z), dz);
+    }
+    vn = fma2(ez, ez, fma2(ey, ey, mul2(ex, ex)));
+    pd = fma2(ez, bc(q1.y), fma2(ey, bc(q1.x), mul2(ex, bc(q0.w))));
+    return fma2(pd, pd, mul2(vn, bc(q1.z)));
+}
+
 struct RayPack {
     u64 dx[kRays / 2], dy[kRays / 2], dz[kRays / 2];
 };
@@ -40,24 +59,47 @@ __device__ __noinline__ void rare_group(const float4* __restrict__ tab, int k0, 
 #pragma unroll 1
     for (int j = 0; j < cnt; j++) {
         const float4* rec = tab + 4 * (k0 + j);
-        const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2], q3 = rec[3];
-        const bool square = __float_as_int(q1.w) & 1;
-        float det[kRays];
-#pragma unroll
-        for (int p = 0; p < kRays / 2; p++) upk(pair_det<true>(q0, q1, q2, q3, dx[p], dy[p], dz[p]), det[2 * p], det[2 * p + 1]);
-        unsigned hits = 0;
-#pragma unroll
-        for (int r = 0; r < kRays; r++) hits |= ((square || det[r] > 0.0f) ? 1u : 0u) << r;
-        if (!hits) continue;
-        Obj ob;
-        load_rec(rec, ob);
+        const float4 q0 = rec[0], q1 = rec[1];
+        const int flags = __float_as_int(q1.w);
+        if (flags & 1) {                                   // square: the scalar routine for every ray
+            Obj ob;
+            load_rec(rec, ob);
 #pragma unroll 1
-        while (hits) {
-            const int r = __ffs(hits) - 1;
-            hits &= hits - 1;
-            HitRec h;
-            const float t = obj_test(ob, dw[r], dw[kRays + r], dw[2 * kRays + r], h);
-            if (t < tmin[r]) { tmin[r] = t; idx[r] = kbase + k0 + j; }
+            for (int r = 0; r < kRays; r++) {
+                HitRec h;
+                const float t = obj_test(ob, dw[r], dw[kRays + r], dw[2 * kRays + r], h);
+                if (t < tmin[r]) { tmin[r] = t; idx[r] = kbase + k0 + j; }
+            }
+            continue;
+        }
+        // sphere: the packed pass yields det, vn and pd with the bits of the scalar routine
+        // (IEEE fma per lane; the diagonal form differs only in the sign of a zero, which neither
+        // vn, pd nor -pd - sqrt(det) can see), so a hit only needs the sqrt and the divide
+        float det[kRays], vn[kRays], pd[kRays];
+        if (flags & 2) {
+            const float4 q2 = rec[2], q3 = rec[3];
+#pragma unroll
+            for (int p = 0; p < kRays / 2; p++) {
+                u64 v2, p2;
+                upk(pair_det_full<true>(q0, q1, q2, q3, dx[p], dy[p], dz[p], v2, p2), det[2 * p], det[2 * p + 1]);
+                upk(v2, vn[2 * p], vn[2 * p + 1]);
+                upk(p2, pd[2 * p], pd[2 * p + 1]);
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < kRays / 2; p++) {
+                u64 v2, p2;
+                upk(pair_det_full<false>(q0, q1, q0, q0, dx[p], dy[p], dz[p], v2, p2), det[2 * p], det[2 * p + 1]);
+                upk(v2, vn[2 * p], vn[2 * p + 1]);
+                upk(p2, pd[2 * p], pd[2 * p + 1]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kRays; r++) {
+            if (det[r] > 0.0f) {                           // shape.py:121-125, first root
+                const float t = __fdiv_rn(__fsub_rn(-pd[r], __fsqrt_rn(det[r])), vn[r]);
+                if (t < tmin[r]) { tmin[r] = t; idx[r] = kbase + k0 + j; }
+            }
         }
     }
 }
