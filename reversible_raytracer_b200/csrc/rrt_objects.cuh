@@ -116,3 +116,25 @@ __device__ __forceinline__ float obj_test(const Obj& ob, float dwx, float dwy, f
         return h.t = m ? t : inf;
     }
 }
+
+// The hit record of a ray whose winner AND ray parameter t are already known from the sweep:
+// same d', vn, pd, det as obj_test (same operations), but no second sqrt / divide.
+template <bool NEED_QUADRATIC>
+__device__ __forceinline__ void hit_record(const Obj& ob, float dwx, float dwy, float dwz, float t, HitRec& h) {
+    if (!(ob.flags & 2)) {
+        h.d[0] = __fmul_rn(ob.a[0], dwx);
+        h.d[1] = __fmul_rn(ob.a[4], dwy);
+        h.d[2] = __fmul_rn(ob.a[8], dwz);
+    } else {
+        h.d[0] = dot3_canon(ob.a[0], ob.a[1], ob.a[2], dwx, dwy, dwz);
+        h.d[1] = dot3_canon(ob.a[3], ob.a[4], ob.a[5], dwx, dwy, dwz);
+        h.d[2] = dot3_canon(ob.a[6], ob.a[7], ob.a[8], dwx, dwy, dwz);
+    }
+    h.t = t;
+    h.vn = h.pd = h.det = 0.f;
+    if (NEED_QUADRATIC && !(ob.flags & 1)) {
+        h.vn = dot3_canon(h.d[0], h.d[1], h.d[2], h.d[0], h.d[1], h.d[2]);
+        h.pd = dot3_canon(h.d[0], h.d[1], h.d[2], ob.o[0], ob.o[1], ob.o[2]);
+        h.det = __fmaf_rn(h.pd, h.pd, __fmul_rn(h.vn, ob.ncc));
+    }
+}

@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                 }
                 const float dwx = l_dw[r], dwy = l_dw[kRays + r], dwz = l_dw[2 * kRays + r];
                 HitRec h;
-                obj_test(ob, dwx, dwy, dwz, h);
+                hit_record<false>(ob, dwx, dwy, dwz, l_tmin[r], h);   // t is known from the sweep
                 ShadeRec sr;
                 float rgb[3];
                 shade(sc.shader, sc.max_depth, ob, m7, g, h, sr, rgb);
@@ -486,8 +486,12 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                         k_loaded = k;
                     }
                     dwx = l_dw[r]; dwy = l_dw[kRays + r]; dwz = l_dw[2 * kRays + r];
-                    obj_test(ob, dwx, dwy, dwz, h);
-                    if (!(h.t < __int_as_float(0x7f800000))) k = -1;  // stale stored winner
+                    if (use_stored) {
+                        obj_test(ob, dwx, dwy, dwz, h);
+                        if (!(h.t < __int_as_float(0x7f800000))) k = -1;  // stale stored winner
+                    } else {
+                        hit_record<true>(ob, dwx, dwy, dwz, l_tmin[r], h);   // t is known from the sweep
+                    }
                 }
                 // flush the running per-object accumulator when some lane changes object
                 const bool change = fin ? (acc_key >= 0) : ((k >= 0) && (acc_key >= 0) && (k != acc_key));
