@@ -171,8 +171,12 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
     if (MODE == MODE_BWD && gc[0] == 0.f && gc[1] == 0.f && gc[2] == 0.f) idx = -1;
     if (idx >= 0) {
         load_rec(tab + 4 * idx, ob);
-        obj_test<true>(ob, wx, wy, wz, h);
-        if (!(h.t < inf)) idx = -1;                      // stale stored winner
+        if (use_stored) {
+            obj_test<true>(ob, wx, wy, wz, h);
+            if (!(h.t < inf)) idx = -1;                  // stale stored winner
+        } else {
+            hit_record<MODE != MODE_FWD>(ob, wx, wy, wz, tmin, h);   // t is known from the sweep
+        }
     }
     if (idx >= 0) {
 #pragma unroll
