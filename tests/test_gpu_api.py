@@ -391,3 +391,35 @@ def test_whole_step_kernel_matches_general_path(cuda):
     assert trainC.state['whole_step'] is None and 'exactly' in trainC.state['whole_step_refused']
     l0 = trainC()
     assert np.isfinite(l0)
+
+
+def test_c_abi_demo(cuda, tmp_path):
+    """examples/c_abi_demo.c: the C ABI driven from plain C (cudaMalloc'ed buffers, no Python /
+    torch in the process) reproduces the oracle on match_mirror.py's scene: exact hit counts per
+    shape, loss and centre gradients within tolerance."""
+    import re, shutil, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which('gcc') is None or not os.path.exists('/usr/local/cuda/include/cuda_runtime_api.h'):
+        pytest.skip('needs gcc and the CUDA runtime headers')
+    exe = str(tmp_path / 'c_abi_demo')
+    libdir = os.path.join(root, 'reversible_raytracer_b200')
+    subprocess.check_call(['gcc', '-O2', '-I', os.path.join(root, 'include'), '-I', '/usr/local/cuda/include',
+                           os.path.join(root, 'examples', 'c_abi_demo.c'), '-o', exe, '-L', libdir, '-lrrt_b200',
+                           '-L', '/usr/local/cuda/lib64', '-lcudart', '-lm', '-Wl,-rpath,' + libdir])
+    out = subprocess.run([exe, str(tmp_path / 'frame0.ppm')], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    m = re.search(r'loss ([\d.]+)\s+hits sphere0 (\d+) sphere1 (\d+) square (\d+) background (\d+)', out.stdout)
+    g = re.search(r'dcentre0 = \(([-\d.]+), ([-\d.]+), ([-\d.]+)\)\s+dloss/dcentre1 = \(([-\d.]+), ([-\d.]+), ([-\d.]+)\)', out.stdout)
+    assert m and g, out.stdout
+    ps = oc.PackedScene.from_spec(scenes.match_mirror(n=128, samples=4), camera_grad=0, use_rng_seed=3)
+    img_o, hit_o, _ = oc.render_forward(ps)
+    target = np.ascontiguousarray(img_o[0][:, ::-1, :])
+    _, _, loss_o, grad_o = oc.render_fused_mse(ps, target)
+    counts = [int((hit_o == k).sum()) for k in (0, 1, 2)] + [int((hit_o < 0).sum())]
+    assert [int(m.group(i)) for i in (2, 3, 4, 5)] == counts
+    np.testing.assert_allclose(float(m.group(1)), loss_o[0], rtol=1e-4)
+    go = oc.split_grad(grad_o[0], 3)['w2o']
+    ref = np.concatenate([-go[0][:, 3], -go[1][:, 3]])
+    got = np.array([float(g.group(i)) for i in range(1, 7)])
+    assert np.max(np.abs(got - ref)) <= 2e-3 * np.max(np.abs(ref)) + 1e-4
+    assert os.path.getsize(str(tmp_path / 'frame0.ppm')) > 128 * 128 * 3
