@@ -331,6 +331,28 @@ def run_b200(args):
     rays = float(n) * n * S
     value = rays * args.steps / (total_ms * 1e-3) / 1e6
 
+    # ---- forward only (BASELINE.json asks for forward AND forward+backward at every N): the same
+    # slab rendered by rrt_render_forward, no exchange needed; max over ranks
+    def fwd_step():
+        return R.render_forward(cfg, obj_type, d['w2o'], d['material'], d['light'], d['camera'], None, want_hit=False)
+    fwd_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    f_ms_total, nfwd = 0.0, min(args.steps, 5)
+    for k in range(nfwd):
+        flush.fill_(k & 0xff)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fwd_step()
+        b.record()
+        torch.cuda.synchronize()
+        f_ms_total += a.elapsed_time(b)
+    fwd_t = torch.tensor([f_ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(fwd_t, op=dist.ReduceOp.MAX)
+    fwd_ms = float(fwd_t) / nfwd
+
     # ---- end-to-end through the public functional API with HOST buffers: every step
     # uploads the scene-parameter tables from pinned memory and reads back loss + gradient
     pin_grad = torch.empty(G, dtype=torch.float32).pin_memory()
@@ -481,11 +503,16 @@ def run_b200(args):
                    # and at N > 1 the peer-memory exchange kernel
                    gpu_launches=(2 + (1 if N >= R.RECORDS_MIN_N else 0) + (1 if peer is not None else 0)) * args.steps,
                    clocks=sampler.summary())
+        out['forward_only'] = dict(ms_per_step=fwd_ms, value=float(n) * n * S / (fwd_ms * 1e-3) / 1e6, unit='Mrays/s',
+                                   frac_fp32_peak=None)
         if kernel_ms is not None:
             out['rank0_step_ms'] = [round(a.elapsed_time(b), 3) for a, b in evs]
             out['per_rank_render_ms'] = kernel_ms     # fused kernel + finalize per rank, before the allreduce
         if roof is not None:
             out['roofline'] = roof
+            # forward credits the sweep + 64 nominal flops per winning ray
+            f_flops = rays * N * (28.0 if args.general else 16.0) + float(hit_rays) * 64.0
+            out['forward_only']['frac_fp32_peak'] = f_flops / (fwd_ms * 1e-3) / 1e12 / roof['peak']
         if world == 1 and not args.no_extras:
             try:
                 oc_ = other_configs(dev)
