@@ -78,6 +78,49 @@ def test_lazy_transform_tracks_inplace_updates_and_autograd():
     np.testing.assert_allclose(s.w2o.m[:3, 3].detach().numpy(), [0.0, -0.5, -1.0])   # re-evaluated
 
 
+def _random_chain(rng, depth):
+    """A random translate / scale / rotate product, in the product's algebra and the oracle's."""
+    prod, ref, flat = None, None, []
+    for _ in range(depth):
+        kind = rng.randint(3)
+        if kind == 0:
+            v = rng.uniform(-3, 3, 3)
+            a, b = T.translate(tuple(v)), on.translate(v)
+        elif kind == 1:
+            v = rng.uniform(0.2, 3, 3)
+            a, b = T.scale(tuple(v)), on.scale(v)
+        else:
+            ang = rng.uniform(-180, 180)
+            ax = rng.normal(size=3)
+            ax /= np.linalg.norm(ax)
+            a, b = T.rotate(float(ang), tuple(ax)), on.rotate(ang, ax)
+        prod = a if prod is None else prod * a
+        ref = b if ref is None else on.compose(ref, b)
+    return prod, ref
+
+
+@pytest.mark.parametrize('seed', range(12))
+def test_random_transform_chains_match_oracle_algebra(seed):
+    """Transform.__mul__ / inverse (transform.py:32-38) on random chains: m and mInv equal the
+    oracle's, m.mInv = I, and the inverse of the product is the reversed product of inverses --
+    the analytic inverse the renderer consumes (shape.py:74-75), no numeric inversion."""
+    rng = np.random.RandomState(900 + seed)
+    prod, ref = _random_chain(rng, 1 + seed % 5)
+    np.testing.assert_allclose(prod.m.numpy(), ref[0], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(prod.mInv.numpy(), ref[1], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose((prod.m.double() @ prod.mInv.double()).numpy(), np.eye(4), atol=5e-5)
+    inv = prod.inverse()
+    np.testing.assert_allclose(inv.m.numpy(), prod.mInv.numpy(), rtol=0, atol=0)
+    np.testing.assert_allclose(inv.mInv.numpy(), prod.m.numpy(), rtol=0, atol=0)
+    # Transform.__call__ on a ray field: origin through the full matrix, directions through the
+    # 3x3 block, spatial transpose (transform.py:40-47)
+    rays = rng.normal(size=(3, 5, 3)).astype(np.float32)
+    rf = prod(T.RayField([0.5, -1.0, 2.0], torch.from_numpy(rays)))
+    o_ref, r_ref = on.apply_rayfield(ref[0], np.array([0.5, -1.0, 2.0], dtype=np.float32), rays)
+    np.testing.assert_allclose(rf.origin.numpy(), o_ref, rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(rf.rays.numpy(), r_ref, rtol=2e-5, atol=2e-5)
+
+
 # ---- packed tables == the oracle's scene specs
 def _scene_c3():
     m1 = Material((0.2, 0.9, 0.4), 0.3, 0.7, 0.5, 50.)
