@@ -423,3 +423,30 @@ def test_c_abi_demo(cuda, tmp_path):
     got = np.array([float(g.group(i)) for i in range(1, 7)])
     assert np.max(np.abs(got - ref)) <= 2e-3 * np.max(np.abs(ref)) + 1e-4
     assert os.path.getsize(str(tmp_path / 'frame0.ppm')) > 128 * 128 * 3
+
+
+def test_whole_step_kernel_depth_shader_channel_weights(cuda):
+    """Whole-step kernel on the C2 shape of problem (test_balls.py:22-44): two spheres
+    translate(p[:3]) * scale(p[3:]) with all six numbers trainable, DepthMapShader, cost on
+    channel 0 only -- same trajectory as the general path."""
+    def make():
+        p1 = torch.tensor([0.3, -0.2, 3.0], device=cuda)
+        s1 = torch.tensor([0.5, 0.6, 0.5], device=cuda)
+        p2 = torch.tensor([-0.4, 0.3, 3.5], device=cuda)
+        s2 = torch.tensor([0.7, 0.5, 0.6], device=cuda)
+        m = Material((0.2, 0.9, 0.4), 0.3, 0.7, 0.5, 50.)
+        sc = Scene([Sphere(translate(p1) * scale(s1), m), Sphere(translate(p2) * scale(s2), m)],
+                   [Light((-1., -1., 2.), (0.961, 1., 0.87))], Camera(32, 32), DepthMapShader(6.1))
+        return sc, [p1, s1, p2, s2]
+    scA, pA = make()
+    scB, pB = make()
+    target = torch.rand((32, 32, 3), device=cuda)
+    cw = (1.0, 0.0, 0.0)
+    trainA = GDOptimizer().optimize(pA, scA.mse_cost(target, channel_weight=cw, seed=9), 1e-4)
+    assert trainA.state['whole_step'] is not None, trainA.state.get('whole_step_refused')
+    trainB = GDOptimizer().optimize(pB, lambda: scB.build_mse(target, channel_weight=cw, seed=9), 1e-4)
+    la = [trainA() for _ in range(10)]
+    lb = [trainB() for _ in range(10)]
+    np.testing.assert_allclose(la, lb, rtol=2e-4)
+    for a, b in zip(pA, pB):
+        np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().cpu().numpy(), rtol=2e-4, atol=1e-5)
