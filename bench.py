@@ -45,6 +45,10 @@ def parse():
     ap.add_argument('--no-extras', action='store_true', help='skip the other BASELINE configs (C1/C3 step latency, C4, C5g)')
     ap.add_argument('--miss', action='store_true', help='diagnostic: move every sphere out of view (pure sweep, no hits)')
     ap.add_argument('--cpu-seconds', type=float, default=20.0)
+    ap.add_argument('--workload', default='c5', choices=['c5', 'c4'],
+                    help="c5 (default): the headline stress scene; c4: BASELINE config 4, the orbit autoencoder's "
+                         "decoder batch (256 scenes x 2 views, 64x64, S=4), scene ranges sharded across ranks")
+    ap.add_argument('--scenes', type=int, default=256)
     return ap.parse_args()
 
 
@@ -531,10 +535,67 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_c4(args):
+    """BASELINE config 4 (test_optimization.py:17-44, autoencoder_2ly.py:82-91 scaled to a batch):
+    `--scenes` orbit scenes x 2 camera views, 64x64, S=4, fused forward + squared error + reverse
+    pass.  Scene ranges are sharded across ranks (sharding.scene_range); per-scene gradients stay
+    on their rank (they feed the local encoder backward), so the render path has no collective."""
+    import torch
+    import torch.distributed as dist
+    from reversible_raytracer_b200 import render as R, workloads as W, sharding as Sh, _native as nat
+    world, rank = int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    nat.lib()
+    tb, tt = W.orbit_tables(args.scenes), W.orbit_tables(args.scenes, centre_noise=0.5)
+    first, count = Sh.scene_range(args.scenes, world, rank)
+    sl = slice(2 * first, 2 * (first + count))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    cfg = R.RenderConfig(n=64, samples=4, shader=tb['shader'], transpose=0, seed=7, scene_begin=2 * first)
+    obj_type, mat, light, cam = t(tb['obj_type']), t(tb['material']), t(tb['light']), t(tb['camera'][sl])
+    w2o = t(tb['w2o'][sl])
+    target, _, _ = R.render_forward(cfg, obj_type, t(tt['w2o'][sl]), mat, light, cam, None, want_hit=False)
+    step = lambda: R.render_fused_mse(cfg, obj_type, w2o, mat, light, cam, target)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    rays = 2.0 * args.scenes * 64 * 64 * 4
+    if rank == 0:
+        print(json.dumps(dict(
+            metric='Mrays/s fwd+bwd', value=rays * args.steps / (float(ms) * 1e-3) / 1e6, unit='Mrays/s', n_gpus=world,
+            steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=float(ms) / args.steps, higher_is_better=True,
+            scaling='strong', vs_baseline=None, dtype='f32', data='synthetic',
+            config=dict(workload='C4 orbit autoencoder decoder batch: %d scenes x 2 views, 64x64, S=4, 2 spheres, '
+                                 'fused fwd+mse+bwd' % args.scenes, sharding='%d scenes per GPU' % count,
+                        collective='none on the render path (per-scene gradients stay local)',
+                        l2='working set (%.0f MB per rank) is L2-resident by nature of the workload' % (2 * count * 64 * 64 * 3 * 4 * 2 / 1e6)),
+            gpu_launches=2 * args.steps)))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload == 'c4':
+        run_c4(args)
     else:
         run_b200(args)
 
