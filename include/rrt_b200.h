@@ -16,7 +16,7 @@
  *     cross the ABI.
  *   - Every buffer is DEVICE memory owned by the caller (except where a parameter
  *     is documented as host).  The library never allocates, frees or synchronises
- *     (rrt_measure_fp32_peak is the one documented exception: it is a benchmark).
+ *     (measurement helpers that do live in a separate library, include/rrt_b200_bench.h).
  *   - All work is enqueued on the caller's CUDA stream (`stream` is a
  *     cudaStream_t passed as void*; NULL = legacy default stream).
  *   - No global mutable state: re-entrant from several host threads, one process
@@ -287,14 +287,6 @@ size_t rrt_peer_buffer_bytes(int n, int nloss, int world);
 size_t rrt_peer_signal_bytes(void);
 int rrt_peer_allreduce(const float* grad, const double* loss, int n, int nloss, void* const* peer_buf,
                        void* const* peer_sig, int rank, int world, double* out, void* stream);
-
-/*
- * FP32 pipe micro-benchmark used as the roofline denominator (MEASURED_PEAKS.json
- * has no FP32 entry).  mode 0 = scalar FFMA, 1 = packed FFMA2 (fma.rn.f32x2),
- * 2 = FFMA2 + one ALU-pipe FMNMX3 per 4 (diagnostic: shows FFMA2 does not dual-issue).
- * Synchronises the stream.  tflops is a HOST pointer.
- */
-int rrt_measure_fp32_peak(int mode, int iters, double* tflops, double* ms, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,6 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
 LIB_PATH = os.environ.get('RRT_B200_LIB') or os.path.join(HERE, 'librrt_b200.so')   # env override: A/B kernel variants
 SRC = os.path.join(HERE, 'csrc', 'rrt_kernels.cu')
+BENCH_LIB_PATH = os.path.join(HERE, 'librrt_b200_bench.so')       # measurement helpers (include/rrt_b200_bench.h)
+BENCH_SRC = os.path.join(HERE, 'csrc', 'rrt_bench_kernels.cu')
 INCLUDE = os.path.join(REPO, 'include')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
@@ -51,14 +53,16 @@ def build(force=False, verbose=False):
     """Compile csrc/rrt_kernels.cu (+ its .cuh parts, one translation unit) for sm_100a into
     librrt_b200.so (in-tree)."""
     srcs = [os.path.join(os.path.dirname(SRC), f) for f in os.listdir(os.path.dirname(SRC))] + \
-           [os.path.join(INCLUDE, 'rrt_b200.h')]
-    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(f) for f in srcs):
-        return LIB_PATH
+           [os.path.join(INCLUDE, 'rrt_b200.h'), os.path.join(INCLUDE, 'rrt_b200_bench.h')]
+    newest = max(os.path.getmtime(f) for f in srcs)
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + ['-I', INCLUDE, '-o', LIB_PATH, SRC]
-    if verbose:
-        cmd.insert(1, '-Xptxas=-v')
-    subprocess.check_call(cmd)
+    for out, src in ((LIB_PATH, SRC), (BENCH_LIB_PATH, BENCH_SRC)):
+        if not force and os.path.exists(out) and os.path.getmtime(out) >= newest:
+            continue
+        cmd = [nvcc] + NVCC_FLAGS + ['-I', INCLUDE, '-o', out, src]
+        if verbose:
+            cmd.insert(1, '-Xptxas=-v')
+        subprocess.check_call(cmd)
     return LIB_PATH
 
 
@@ -92,7 +96,6 @@ def lib():
         L.rrt_primary_rays.argtypes = [C.c_int, P, P]
         L.rrt_chain_forward.argtypes = [P, P, C.c_int, P, P, P]
         L.rrt_chain_backward.argtypes = [P, P, C.c_int, P, P, P, C.c_int, P]
-        L.rrt_measure_fp32_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), P]
         if hasattr(L, 'rrt_small_step_mse'):
             L.rrt_small_step_mse.argtypes = [C.POINTER(RrtScene), C.POINTER(RrtStep), P, C.POINTER(C.c_float), P, P]
             L.rrt_small_step_mse.restype = C.c_int
@@ -105,15 +108,33 @@ def lib():
         L.rrt_peer_signal_bytes.restype = C.c_size_t
         L.rrt_peer_allreduce.argtypes = [P, P, C.c_int, C.c_int, P, P, C.c_int, C.c_int, P, P]
         L.rrt_peer_allreduce.restype = C.c_int
-        for f in (L.rrt_render_forward, L.rrt_render_backward, L.rrt_render_fused_mse, L.rrt_measure_fp32_peak,
+        for f in (L.rrt_render_forward, L.rrt_render_backward, L.rrt_render_fused_mse,
                   L.rrt_chain_forward, L.rrt_chain_backward, L.rrt_primary_rays):
             f.restype = C.c_int
         _lib = L
     return _lib
 
 
+_bench = None
+
+
+def bench_lib():
+    """librrt_b200_bench.so: measurement helpers (FP32 peak micro-benchmarks), used by bench.py only."""
+    global _bench
+    if _bench is None:
+        if not os.path.exists(BENCH_LIB_PATH):
+            raise NativeError('librrt_b200_bench.so is not built (run __graft_entry__.build())')
+        L = C.CDLL(BENCH_LIB_PATH)
+        L.rrt_bench_fp32_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p]
+        L.rrt_bench_fp32_peak.restype = C.c_int
+        _bench = L
+    return _bench
+
+
+BENCH_EXPORTS = ['rrt_bench_fp32_peak']
+
 EXPORTS = ['rrt_version', 'rrt_last_error', 'rrt_render_forward', 'rrt_render_backward',
-           'rrt_render_fused_mse', 'rrt_measure_fp32_peak', 'rrt_chain_forward', 'rrt_chain_backward', 'rrt_primary_rays',
+           'rrt_render_fused_mse', 'rrt_chain_forward', 'rrt_chain_backward', 'rrt_primary_rays',
            'rrt_peer_allreduce', 'rrt_peer_buffer_bytes', 'rrt_peer_signal_bytes', 'rrt_build_records',
            'rrt_small_step_mse']
 

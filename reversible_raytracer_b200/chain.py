@@ -23,7 +23,8 @@ from . import _native as nat
 
 def flatten(transform, inverted=False):
     """Transform expression -> list of (kind, inverted, args) whose left-to-right matrix
-    product equals transform.m (or .mInv when inverted).  None if not expressible."""
+    product equals transform.m (or .mInv when inverted); args are transform._Arg objects.
+    None if not expressible."""
     e = transform._expr
     if e is None:
         return None
@@ -31,9 +32,9 @@ def flatten(transform, inverted=False):
     if tag == 'I':
         return []
     if tag in ('T', 'S'):
-        return [(tag, inverted, (e[1],), e[2])]
+        return [(tag, inverted, (e[1],))]
     if tag == 'R':
-        return [('R', inverted, (e[1], e[2]), e[3])]
+        return [('R', inverted, (e[1], e[2]))]
     if tag == 'inv':
         return flatten(e[1], not inverted)
     if tag == 'mul':
@@ -44,8 +45,42 @@ def flatten(transform, inverted=False):
     return None
 
 
+class _Structure(object):
+    """Device-side op table of a list of chains.  Depends only on the STRUCTURE of the
+    expressions (op kinds, constant values, which live parameters are shared between ops),
+    not on the identity of the parameter tensors, so it is cached: a loss closure that rebuilds
+    its shapes on every call (the reference's decoders do) compiles -- and uploads -- it once."""
+
+    def __init__(self, key, device):
+        chains, n_const, n_values = key
+        kind_id = {'T': nat.CHAIN_TRANSLATE, 'S': nat.CHAIN_SCALE, 'R': nat.CHAIN_ROTATE}
+        ops, begin, consts = [], [0], np.zeros(n_const, dtype=np.float32)
+        for chain in chains:
+            for kind, inv, args in chain:
+                offs = []
+                for tag, off, payload in args:
+                    offs.append(off)
+                    if tag == 'c':
+                        v = np.frombuffer(payload, dtype=np.float32)
+                        consts[off:off + v.size] = v
+                ops.append([kind_id[kind] | (nat.CHAIN_INVERT if inv else 0), offs[0], offs[1] if len(offs) > 1 else 0, 0])
+            begin.append(len(ops))
+        if not ops:                                # identity-only chains: keep the table non-empty (non-NULL)
+            ops = [[0, 0, 0, 0]]
+        self.ops = torch.tensor(np.asarray(ops, dtype=np.int32).reshape(-1, 4), device=device)
+        self.chain_begin = torch.tensor(np.asarray(begin, dtype=np.int32), device=device)
+        self.const_block = torch.tensor(consts, dtype=torch.float32, device=device)
+        self.num_values = max(n_values, 1)
+        self.zero1 = torch.zeros(1, dtype=torch.float32, device=device)
+
+
+_STRUCTURES = {}
+_STRUCTURES_MAX = 256
+
+
 class ChainProgram(object):
-    """Compiled op table for a list of Transforms (one output row of 12 floats each)."""
+    """Compiled op table for a list of Transforms (one output row of 12 floats each), bound to the
+    CURRENT live parameter tensors of those transforms."""
 
     def __init__(self, transforms, device):
         chains = [flatten(t) for t in transforms]
@@ -53,58 +88,52 @@ class ChainProgram(object):
             raise ValueError('transform not expressible as a chain of translate/scale/rotate')
         self.device = device
         self.num_chains = len(chains)
-        consts, self.param_tensors, slot_of = [], [], {}
+        # pass 1: constants get fixed offsets in the constant block (in order of appearance)
         n_const = 0
-        # first pass: constants get fixed offsets in the constant block
         plan = []
         for chain in chains:
             row = []
-            for kind, inv, args, is_param in chain:
+            for kind, inv, args in chain:
                 offs = []
                 for a in args:
-                    if is_param:
-                        offs.append(('p', a))
+                    if a.param:
+                        offs.append(['p', a, None])
                     else:
-                        v = a.detach().reshape(-1).to(torch.float32).cpu().numpy()
-                        offs.append(('c', n_const))
-                        consts.append(v)
-                        n_const += v.size
+                        offs.append(['c', n_const, a.host.tobytes()])
+                        n_const += a.host.size
                 row.append((kind, inv, offs))
             plan.append(row)
-        # parameters follow the constant block, each distinct tensor once
-        p_off = n_const
+        # pass 2: live parameters follow the constant block, each distinct tensor once
+        self.param_tensors, slot_of, p_off = [], {}, n_const
         for row in plan:
             for kind, inv, offs in row:
-                for j, (tag, a) in enumerate(offs):
-                    if tag == 'p':
-                        key = id(a)
-                        if key not in slot_of:
-                            slot_of[key] = p_off
-                            self.param_tensors.append(a)
-                            p_off += a.numel()
-                        offs[j] = ('c', slot_of[key])
-        self.num_values = max(p_off, 1)
-        kind_id = {'T': nat.CHAIN_TRANSLATE, 'S': nat.CHAIN_SCALE, 'R': nat.CHAIN_ROTATE}
-        ops, begin = [], [0]
-        for row in plan:
-            for kind, inv, offs in row:
-                ops.append([kind_id[kind] | (nat.CHAIN_INVERT if inv else 0), offs[0][1],
-                            offs[1][1] if len(offs) > 1 else 0, 0])
-            begin.append(len(ops))
-        if not ops:                                # identity-only chains: keep the table non-empty (non-NULL)
-            ops = [[0, 0, 0, 0]]
-        self.ops = torch.tensor(np.asarray(ops, dtype=np.int32).reshape(-1, 4), device=device)
-        self.chain_begin = torch.tensor(np.asarray(begin, dtype=np.int32), device=device)
-        self.const_block = torch.tensor(np.concatenate(consts) if consts else np.zeros(0, dtype=np.float32),
-                                        dtype=torch.float32, device=device)
+                for o in offs:
+                    if o[0] == 'p':
+                        src = o[1].src
+                        if id(src) not in slot_of:
+                            slot_of[id(src)] = p_off
+                            self.param_tensors.append(src)
+                            p_off += src.numel()
+                        o[1], o[2] = slot_of[id(src)], src.numel()
+        key = (tuple(tuple((kind, inv, tuple(tuple(o) for o in offs)) for kind, inv, offs in row) for row in plan),
+               n_const, p_off)
+        st = _STRUCTURES.get((key, str(device)))
+        if st is None:
+            if len(_STRUCTURES) >= _STRUCTURES_MAX:
+                _STRUCTURES.clear()
+            st = _STRUCTURES[(key, str(device))] = _Structure(key, device)
+        self.structure = st
+        self.ops, self.chain_begin, self.const_block, self.num_values = st.ops, st.chain_begin, st.const_block, st.num_values
         self.dynamic = len(self.param_tensors) > 0
         self._static_out = None
 
     def values(self):
+        """cat(constants, live parameters) as float32 on the program's device (the cast is done
+        here, at evaluation time, so in-place updates of non-float32 parameters are seen)."""
         parts = [self.const_block] + [p.reshape(-1).to(self.device, torch.float32) for p in self.param_tensors]
         v = torch.cat(parts) if len(parts) > 1 else self.const_block
         if v.numel() == 0:
-            v = torch.zeros(1, dtype=torch.float32, device=self.device)
+            v = self.structure.zero1
         return v
 
     def evaluate(self):

@@ -1,5 +1,5 @@
 // rrt_aux_kernels.cuh -- part of rrt_kernels.cu (one translation unit; included inside its anonymous namespace).
-// Small kernels: record table, primary-ray table, gradient finalisation, peer-memory exchange, FP32 peak.
+// Small kernels: record table, primary-ray table, gradient finalisation, peer-memory exchange.
 #pragma once
 
 // ---------------------------------------------------------------- sweep-record table (for TMA staging)
@@ -186,53 +186,5 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(const float* __rest
         double sum = 0.0;
         for (int p = 0; p < world; p++) sum += __ldcg(local + (size_t)p * total + i);
         out[i] = timed_out ? __longlong_as_double(0x7ff8000000000000LL) : sum;
-    }
-}
-
-// ---------------------------------------------------------------- FP32 peak micro-benchmarks
-template <int MODE>
-__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float seed) {
-    if (MODE == 0) {
-        float a[16];
-#pragma unroll
-        for (int q = 0; q < 16; q++) a[q] = seed + (float)(threadIdx.x + q);
-        float b = 1.0000001f, c = 1e-7f;
-#pragma unroll 1
-        for (int it = 0; it < iters; it++) {
-#pragma unroll
-            for (int rep = 0; rep < 8; rep++)
-#pragma unroll
-                for (int q = 0; q < 16; q++) a[q] = __fmaf_rn(a[q], b, c);
-        }
-        float s = 0.f;
-#pragma unroll
-        for (int q = 0; q < 16; q++) s += a[q];
-        if (s == 123.456f) out[0] = s;
-    } else {
-        // MODE 1: packed FFMA2 only.  MODE 2: + one ALU-pipe FMNMX3 per 4 FFMA2 (diagnostic:
-        // does a non-FMA instruction issue in the shadow of an FFMA2 or cost its own cycle?)
-        u64 a[16];
-#pragma unroll
-        for (int q = 0; q < 16; q++) a[q] = pk(seed + (float)(threadIdx.x + q), seed - (float)q);
-        u64 b = pk(1.0000001f, 0.9999999f), c = pk(1e-7f, -1e-7f);
-        float m = 0.f;
-#pragma unroll 1
-        for (int it = 0; it < iters; it++) {
-#pragma unroll
-            for (int rep = 0; rep < 8; rep++)
-#pragma unroll
-                for (int q = 0; q < 16; q++) {
-                    a[q] = fma2(a[q], b, c);
-                    if (MODE == 2 && (q & 3) == 3) {
-                        float lo, hi;
-                        upk(a[q - 3], lo, hi);
-                        m = fmaxf(m, fmaxf(lo, hi));
-                    }
-                }
-        }
-        float s = m;
-#pragma unroll
-        for (int q = 0; q < 16; q++) { float lo, hi; upk(a[q], lo, hi); s += lo + hi; }
-        if (s == 123.456f) out[0] = s;
     }
 }

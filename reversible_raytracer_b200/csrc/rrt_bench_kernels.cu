@@ -1,0 +1,159 @@
+// rrt_bench_kernels.cu -- librrt_b200_bench.so: FP32-pipe micro-benchmarks (measurement only, see
+// include/rrt_b200_bench.h).  Separate from the product library on purpose: it allocates,
+// synchronises and times.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rrt_b200_bench.h"
+
+namespace {
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+    u64 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void upk(u64 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+
+__constant__ float4 c_tab[256];
+
+template <int MODE>
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float seed) {
+    __shared__ float4 tab[256];
+    tab[threadIdx.x] = make_float4(1.0000001f, 1e-7f, 0.9999999f, -1e-7f);
+    __syncthreads();
+    if (MODE == 0) {
+        float a[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) a[q] = seed + (float)(threadIdx.x + q);
+        float b = 1.0000001f, c = 1e-7f;
+#pragma unroll 1
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int rep = 0; rep < 8; rep++)
+#pragma unroll
+                for (int q = 0; q < 16; q++) a[q] = __fmaf_rn(a[q], b, c);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; q++) s += a[q];
+        if (s == 123.456f) out[0] = s;
+    } else {
+    u64 a[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) a[q] = pk(seed + (float)(threadIdx.x + q), seed - (float)q);
+    u64 b = pk(1.0000001f, 0.9999999f), c = pk(1e-7f, -1e-7f);
+    float m = 0.f;
+    uint32_t sbase = (uint32_t)__cvta_generic_to_shared(tab);
+    asm volatile("mov.u32 %0, %0;" : "+r"(sbase));
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+        const uint32_t row = sbase + 16u * (uint32_t)(it & 127);       // warp-uniform: a broadcast load
+#pragma unroll
+        for (int rep = 0; rep < 8; rep++) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                a[q] = fma2(a[q], b, c);
+                if (MODE == 2 && (q & 3) == 3) {
+                    float lo, hi;
+                    upk(a[q - 3], lo, hi);
+                    m = fmaxf(m, fmaxf(lo, hi));
+                }
+                if (MODE == 3 && (q & 7) == 7) {
+                    const float4 v = lds128(row + 16u * (uint32_t)(rep * 2 + (q >> 3)));
+                    b = pk(v.x, v.z);
+                    c = pk(v.y, v.w);
+                }
+                if (MODE == 4 && (q & 7) == 7) {
+                    const float4 v = c_tab[(it + rep * 2 + (q >> 3)) & 255];
+                    b = pk(1.0000001f + v.x, 0.9999999f + v.z);
+                    c = pk(1e-7f + v.y, -1e-7f + v.w);
+                }
+                if (MODE == 5) {
+                    // per 24 FFMA2: 4 FMNMX3 and 1.5 LDS.128  =>  per 48: 8 and 3 (trip = 128 = 2.67 x 48)
+                    const int n = rep * 16 + q;
+                    if (n % 6 == 5) {
+                        float lo, hi;
+                        upk(a[(q + 11) & 15], lo, hi);
+                        m = fmaxf(m, fmaxf(lo, hi));
+                    }
+                    if (n % 16 == 15) {
+                        const float4 v = lds128(row + 16u * (uint32_t)rep);
+                        b = pk(v.x, v.z);
+                        c = pk(v.y, v.w);
+                    }
+                }
+            }
+        }
+    }
+    float s = m;
+#pragma unroll
+    for (int q = 0; q < 16; q++) { float lo, hi; upk(a[q], lo, hi); s += lo + hi; }
+    if (s == 123.456f) out[0] = s;
+    }
+}
+
+template <int MODE>
+void launch(int blocks, float* out, int iters, cudaStream_t st) {
+    fp32_peak_kernel<MODE><<<blocks, 256, 0, st>>>(out, iters, 0.5f);
+}
+
+}  // namespace
+
+extern "C" int rrt_bench_fp32_peak(int mode, int iters, double* tflops, double* ms, void* stream) {
+    if (!tflops || iters <= 0 || mode < 0 || mode > 5) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return -2;
+    float* out = nullptr;
+    if (cudaMalloc(&out, 4) != cudaSuccess) return -2;
+    float4 h[256];
+    for (int i = 0; i < 256; i++) h[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    cudaMemcpyToSymbolAsync(c_tab, h, sizeof h, 0, cudaMemcpyHostToDevice, st);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int blocks = sms * 8, threads = 256;     // 8 resident CTAs of 256 threads per SM: one full wave
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0, st);
+        switch (mode) {
+            case 0: launch<0>(blocks, out, iters, st); break;
+            case 1: launch<1>(blocks, out, iters, st); break;
+            case 2: launch<2>(blocks, out, iters, st); break;
+            case 3: launch<3>(blocks, out, iters, st); break;
+            case 4: launch<4>(blocks, out, iters, st); break;
+            default: launch<5>(blocks, out, iters, st); break;
+        }
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, e0, e1);
+        if (rep > 0 && t < best) best = t;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    if (e != cudaSuccess) return -2;
+    // per thread per iteration: 8*16 FMA instructions, x2 lanes when packed, 2 flops each
+    const double flops = (double)blocks * threads * (double)iters * 8.0 * 16.0 * (mode >= 1 ? 2.0 : 1.0) * 2.0;
+    *tflops = flops / ((double)best * 1e-3) / 1e12;
+    if (ms) *ms = best;
+    return 0;
+}

@@ -128,18 +128,14 @@ int check_scene(const rrt_scene* sc, int* rows_out) {
     return RRT_OK;
 }
 
-// Small scenes (few objects, few rays) take the one-ray-per-thread kernel.  The ray limit
-// can be overridden for A/B measurements: RRT_SMALL_MAX_RAYS=<count> (0 disables the kernel).
+// Small scenes (few objects, few rays) take the one-ray-per-thread kernel (RRT_FLAG_NO_SMALL
+// forces the general one).  Pure function of the descriptor: no environment, no static state.
 bool use_small_kernel(const KParams& P) {
     const rrt_scene& sc = P.sc;
     const int S = sc.samples;
     if (sc.num_objects > kSmallMaxN || S > 32 || (S & (S - 1)) || (sc.flags & (RRT_FLAG_CULL | RRT_FLAG_NO_SMALL)))
         return false;
-    static long long limit = -1;
-    if (limit < 0) {
-        const char* e = getenv("RRT_SMALL_MAX_RAYS");
-        limit = e ? atoll(e) : kSmallDefaultMaxRays;
-    }
+    const long long limit = kSmallDefaultMaxRays;
     const long long rays_scene = (long long)P.rows * sc.n * S;
     if (rays_scene >= 0x7fffffffLL - kSmallThreads) return false;    // 32-bit ray index in the kernel
     return rays_scene * sc.num_scenes <= limit;
@@ -162,8 +158,6 @@ int launch(KParams& P, cudaStream_t st) {
         if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "small-scene kernel launch: %s", cudaGetErrorString(e));
         return RRT_OK;
     }
-    if (MODE == MODE_FUSED && S > kRays)   // one thread must own all samples of its pixels (single sample chunk)
-        return fail(RRT_ERR_UNSUPPORTED, "fused kernel supports samples <= 8 beyond the small-scene limits; use forward + backward");
     int pix;
     if (S == 1) pix = kRays; else if (S == 2) pix = kRays / 2; else if (S == 4) pix = kRays / 4; else pix = 1;
     // block height: keep the grid >= ~2 waves of 148 SMs when the image is small
@@ -362,39 +356,6 @@ int rrt_peer_allreduce(const float* grad, const double* loss, int n, int nloss, 
     peer_allreduce_kernel<<<kPeerCtas, 256, 0, (cudaStream_t)stream>>>(grad, loss, n, nloss, peer_buf, peer_sig, rank, world, out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "peer allreduce launch: %s", cudaGetErrorString(e));
-    return RRT_OK;
-}
-
-int rrt_measure_fp32_peak(int mode, int iters, double* tflops, double* ms, void* stream) {
-    if (!tflops || iters <= 0 || mode < 0 || mode > 2) return fail(RRT_ERR_INVALID, "bad arguments");
-    cudaStream_t st = (cudaStream_t)stream;
-    float* out = nullptr;
-    if (cudaMalloc(&out, 4) != cudaSuccess) return fail(RRT_ERR_CUDA, "cudaMalloc failed");
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0);
-    cudaEventCreate(&e1);
-    const int blocks = 148 * 8, threads = 256;
-    float best = 1e30f;
-    for (int rep = 0; rep < 5; rep++) {
-        cudaEventRecord(e0, st);
-        if (mode == 0) fp32_peak_kernel<0><<<blocks, threads, 0, st>>>(out, iters, 0.5f);
-        else if (mode == 1) fp32_peak_kernel<1><<<blocks, threads, 0, st>>>(out, iters, 0.5f);
-        else fp32_peak_kernel<2><<<blocks, threads, 0, st>>>(out, iters, 0.5f);
-        cudaEventRecord(e1, st);
-        cudaEventSynchronize(e1);
-        float t = 0.f;
-        cudaEventElapsedTime(&t, e0, e1);
-        if (rep > 0 && t < best) best = t;
-    }
-    cudaError_t e = cudaGetLastError();
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(out);
-    if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "peak kernel: %s", cudaGetErrorString(e));
-    // per thread per iteration: 8*16 FMA instructions, x2 lanes when packed, 2 flops each
-    double flops = (double)blocks * threads * (double)iters * 8.0 * 16.0 * (mode >= 1 ? 2.0 : 1.0) * 2.0;
-    *tflops = flops / ((double)best * 1e-3) / 1e12;
-    if (ms) *ms = best;
     return RRT_OK;
 }
 

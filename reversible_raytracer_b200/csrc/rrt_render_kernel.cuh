@@ -130,8 +130,17 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
     float loss_part = 0.f;
 
     const int nchunks_s = (S + SPT - 1) / SPT;
+    // Fused mode with more samples than one thread holds (generic instantiation only, S > 8): the
+    // upstream gradient of a pixel is known only after ALL its samples are shaded, so the chunk
+    // loop runs twice -- pass 0 sweeps + shades, pass 1 sweeps again + runs the reverse pass
+    // (hit records are recomputed, never stored).  Compile-time false wherever S == SPT.
+    const bool two_pass = (MODE == MODE_FUSED) && (PIX == 1) && nchunks_s > 1;
+    const int ntrips = two_pass ? 2 * nchunks_s : nchunks_s;
 #pragma unroll 1
-    for (int sc0 = 0; sc0 < nchunks_s; sc0++) {
+    for (int trip = 0; trip < ntrips; trip++) {
+        const int sc0 = two_pass ? (trip >= nchunks_s ? trip - nchunks_s : trip) : trip;
+        const bool do_fwd = (MODE != MODE_BWD) && (!two_pass || trip < nchunks_s);
+        const bool do_bwd = (MODE != MODE_FWD) && (!two_pass || trip >= nchunks_s);
         // ---- build the 8 rays of this sample chunk.  Per-ray state lives in (L1-resident)
         // local memory: it is read by the rare path of the sweep and by the rolled shading /
         // reverse-pass loops below; only the packed world directions stay in registers.
@@ -207,7 +216,7 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                     lo3[c] = fminf(lo3[c], __shfl_xor_sync(0xffffffffu, lo3[c], o));
                     hi3[c] = fmaxf(hi3[c], __shfl_xor_sync(0xffffffffu, hi3[c], o));
                 }
-            if (sc0 > 0) __syncthreads();          // previous use of cone_red / tcone is over
+            if (trip > 0) __syncthreads();         // previous use of cone_red / tcone is over
             if (lane == 0) {
 #pragma unroll
                 for (int c = 0; c < 3; c++) { cone_red[warp][c] = lo3[c]; cone_red[warp][3 + c] = hi3[c]; }
@@ -261,9 +270,9 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
 #pragma unroll 1
             for (int kb = 0; kb < N; kb += kObjChunk) {
                 const int cnt = min(kObjChunk, N - kb);
-                if (kb > 0 || sc0 > 0) __syncthreads();   // previous chunk fully consumed
+                if (kb > 0 || trip > 0) __syncthreads();  // previous chunk fully consumed
                 bool staged_by_tma = false;
-                if (N > kObjChunk || sc0 == 0) {
+                if (N > kObjChunk || trip == 0) {
                     if (sc.obj_records) {                  // precomputed records: one TMA bulk copy
                         stage_records_tma(smem_tab, sc.obj_records + ((size_t)scene * N + kb) * RRT_RECORD_FLOATS, cnt,
                                           &tma_bar, &tma_phase, &chunk_class, tid);
@@ -335,7 +344,7 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
         }
 
         // ---- outputs of the sweep
-        if (MODE != MODE_BWD && (P.hit_out || P.tmin_out)) {
+        if (do_fwd && (P.hit_out || P.tmin_out)) {
 #pragma unroll 1
             for (int r = 0; r < kRays; r++) {
                 const int px = r / SPT, s = sc0 * SPT + r % SPT, b = b0 + px;
@@ -353,7 +362,7 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
         }
 
         // ---- shade the winners (forward value)
-        if (MODE != MODE_BWD) {
+        if (do_fwd) {
             // a thread's rays (samples of one pixel, neighbouring pixels) mostly share their
             // winner: the object record and material are re-fetched only when it changes
             Obj ob;
@@ -388,7 +397,7 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
         // (32*PIX pixels = 96*PIX contiguous floats per warp) moves through a per-warp
         // shared-memory stage so that global traffic is coalesced 16-byte vectors
         // (LDG.128 / STG.128, streaming); ragged tiles use scalar accesses.
-        if (MODE != MODE_BWD && last_chunk) {
+        if (do_fwd && last_chunk) {
             const float inv = 1.0f / (float)S;
             const bool vec = P.vec_ok && row_ok && (blockIdx.x * 32 + 32) * PIX <= n;   // warp-uniform
             const size_t row_off = (((size_t)scene * P.rows + al) * n + (size_t)blockIdx.x * 32 * PIX) * 3;
@@ -454,7 +463,7 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
         }
 
         // ---- reverse pass over the winners
-        if (MODE != MODE_FWD) {
+        if (do_bwd) {
             // one extra (sentinel) trip after the last ray of the last sample chunk flushes the
             // running accumulator, so the warp-level flush code exists exactly once
             Obj ob;

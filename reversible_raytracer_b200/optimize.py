@@ -9,10 +9,22 @@ returns a scalar tensor, e.g.
                                    lambda: -scene.build()[90, 85].sum() - scene.build()[50, 90].sum())
     for i in range(90): print(train(0.0008))
 
-Both call shapes found in the reference are accepted:
-    optimize(tVars, loss, momentum=0) -> fn(lr)            optimize.py:19-29 (HEAD)
+Both call shapes found in the reference are accepted, told apart by the number of positional
+arguments exactly as the reference's two signatures would bind them:
+    optimize(tVars, loss[, momentum]) -> fn(lr)            optimize.py:19-29 (HEAD; momentum is
+                                                           accepted and unused there, too)
     optimize(tVars, loss, lr, momentum) -> fn()            optimize_brightness.py:50-52,
                                                            match_mirror.py:48 (stale form)
+`lr=` / `momentum=` may also be given by keyword.
+
+CUDA-graph capture (graph='auto', the default) -- what it freezes.  The reference's compiled
+function is symbolic; a captured closure is a RECORDING: only device-side state is live on replay.
+Anything the closure reads on the HOST per call is frozen at capture time: Python scalars, a
+changing `seed=` / `jitter=`, a data index, `setTransform`-style scene mutations, a new Material.
+Guards: (1) right after capture the graph is replayed once with lr = 0 and its loss is compared
+with an eager evaluation -- a mismatch drops the graph with a warning and stepping stays eager;
+(2) `train.recapture()` invalidates the graph after you changed host-side state on purpose;
+(3) `graph=False` never captures.
 """
 import warnings
 
@@ -108,7 +120,13 @@ class GDOptimizer(object):
     def __init__(self):
         pass
 
-    def optimize(self, tVars, loss, lr=None, momentum=0, graph='auto'):
+    def optimize(self, tVars, loss, *args, graph='auto', **kw):
+        if len(args) > 2 or set(kw) - {'lr', 'momentum'}:
+            raise TypeError('optimize(tVars, loss[, momentum]) or optimize(tVars, loss, lr, momentum)')
+        lr = kw.get('lr')
+        if len(args) == 2:                         # stale 4-argument form: (lr, momentum)
+            lr = args[0]
+        # len(args) == 1 is HEAD's `momentum`, which the reference never uses either (optimize.py:19-29)
         if not callable(loss):
             raise TypeError('loss must be a callable returning a scalar tensor (eager re-host of the '
                             'symbolic loss expression of optimize.py:19)')
@@ -154,10 +172,20 @@ class GDOptimizer(object):
                 st['value'] = step(st['lr'])
                 # the loss read-back is part of the graph: a copy node into pinned host memory
                 st['host'].copy_(st['value'].detach().to(torch.float32), non_blocking=True)
+            # validate the recording once: replay with lr = 0 (no update) against an eager evaluation
+            g.replay()
+            torch.cuda.current_stream(dev).synchronize()
+            replayed = float(st['host'])
+            with torch.no_grad():
+                eager = float(loss().detach())
             with torch.no_grad():                  # lr was 0 during warm-up/capture; restore exactly anyway
                 for v, s0 in zip(tVars, saved):
                     v.copy_(s0)
+            if not abs(replayed - eager) <= 1e-3 * max(1.0, abs(eager)):
+                raise RuntimeError('replayed loss %r != eager loss %r: the closure reads host-side state '
+                                   'that a CUDA graph cannot see' % (replayed, eager))
             st['graph'] = g
+            st['lr_value'] = None
 
         def train(step_lr=None):
             step_lr = default_lr if step_lr is None else step_lr
@@ -183,7 +211,14 @@ class GDOptimizer(object):
                 return float(st['host'])
             return float(step(step_lr).detach())
 
+        def recapture():
+            """Forget the captured graph (call after changing host-side state the loss closure
+            reads: seeds, data indices, scene structure); the next train() captures again."""
+            st['graph'], st['failed'], st['lr_value'] = None, False, None
+            st['calls'] = max(st['calls'], 2)
+
         train.state = st
+        train.recapture = recapture
         return train
 
 

@@ -243,7 +243,8 @@ class StreamedFusedMSE:
             self.e_in = [torch.cuda.Event() for _ in range(K)]
             self.e_k = [torch.cuda.Event() for _ in range(K)]
             self.e_fork, self.e_out = torch.cuda.Event(), torch.cuda.Event()
-        self.launches_per_call = 2 * K                # fused kernel + finalize per slab
+        # fused kernel + finalize per slab, + one rrt_build_records per call from RECORDS_MIN_N objects
+        self.launches_per_call = 2 * K + (1 if self.N >= RECORDS_MIN_N and cfg.use_records else 0)
 
     def __call__(self, obj_type, w2o, material, light, camera, target_host, image_host=None, channel_weight=None):
         cfg, dev = self.cfg, self.device
@@ -259,22 +260,26 @@ class StreamedFusedMSE:
         cw = (C.c_float * 3)(*[float(v) for v in channel_weight]) if channel_weight is not None else None
         L = nat.lib()
         cur = torch.cuda.current_stream(dev)
-        self.e_fork.record(cur)                       # parameter tables are ready from here on
+        # Parameter tables (dtype / layout copies) and the sweep-record table are built ONCE per
+        # call, on the caller's stream, BEFORE the fork event: the record table does not depend on
+        # the slab, and the side streams that TMA-load it are ordered after it by e_fork.
+        T = _Tables(cfg, obj_type, w2o, material, light, camera, None)
+        if T.B != 1:
+            raise ValueError('StreamedFusedMSE renders one scene (use render_fused_mse for scene batches)')
+        self._tables = T                              # keeps the tables alive while the side streams run
+        self.e_fork.record(cur)                       # parameter + record tables are ready from here on
         for s in (self.s_in, self.s_out, *self.s_k):
             s.wait_event(self.e_fork)
-        keep = []
         for k, (r0, rc) in enumerate(self.bounds):
             with torch.cuda.stream(self.s_in):
                 self.dev_target[r0:r0 + rc].copy_(target_host[r0:r0 + rc], non_blocking=True)
                 self.e_in[k].record(self.s_in)
             sk = self.s_k[k & 1]
-            T = _Tables(cfg.slab(cfg.row_begin + r0, rc), obj_type, w2o, material, light, camera, None)
-            keep.append(T)
-            if T.B != 1:
-                raise ValueError('StreamedFusedMSE renders one scene (use render_fused_mse for scene batches)')
+            desc = nat.RrtScene.from_buffer_copy(T.desc)          # same tables, this slab's rows
+            desc.row_begin, desc.row_count = cfg.row_begin + r0, rc
             sk.wait_event(self.e_in[k])
             with torch.cuda.device(dev):
-                rc_ = L.rrt_render_fused_mse(C.byref(T.desc), self.dev_target[r0:r0 + rc].data_ptr(), cw,
+                rc_ = L.rrt_render_fused_mse(C.byref(desc), self.dev_target[r0:r0 + rc].data_ptr(), cw,
                                              self.dev_image[r0:r0 + rc].data_ptr() if self.dev_image is not None else None,
                                              None, self.losses[k:k + 1].data_ptr(), self.grads[k].data_ptr(),
                                              C.c_void_p(sk.cuda_stream))
@@ -376,9 +381,11 @@ class _FusedLossFn(torch.autograd.Function):
 
 
 def measure_fp32_peak(mode=1, iters=4096):
-    """FP32 pipe micro-benchmark (TFLOP/s): mode 0 scalar FFMA, 1 packed FFMA2."""
+    """FP32 pipe micro-benchmark (TFLOP/s) from the separate measurement library
+    (include/rrt_b200_bench.h): mode 0 scalar FFMA, 1 packed FFMA2, 2..5 instruction mixes."""
     tf, ms = C.c_double(0), C.c_double(0)
-    rc = nat.lib().rrt_measure_fp32_peak(mode, iters, C.byref(tf), C.byref(ms),
-                                         C.c_void_p(torch.cuda.current_stream().cuda_stream))
-    nat.check(rc, 'rrt_measure_fp32_peak')
+    rc = nat.bench_lib().rrt_bench_fp32_peak(mode, iters, C.byref(tf), C.byref(ms),
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc != 0:
+        raise nat.NativeError('rrt_bench_fp32_peak failed (%d)' % rc)
     return tf.value, ms.value

@@ -29,6 +29,23 @@ from .util import *  # noqa: F401,F403
 from .transform import *  # noqa: F401,F403
 
 
+# Module-level caches of host-generated constants, so that a loss closure which rebuilds its
+# Scene on every call (orbit_experiments/test_optimization.py:17-44 does) performs no
+# host->device copy in steady state and can be captured into a CUDA graph.
+_SEEDED_JITTER = {}      # (n, S, seed, transposed, device) -> (jx, jy) device tensors
+_OBJ_TYPES = {}          # (kinds, device) -> int32 device tensor
+
+
+def _obj_type_tensor(kinds, device):
+    key = (tuple(int(k) for k in kinds), str(device))
+    t = _OBJ_TYPES.get(key)
+    if t is None:
+        if len(_OBJ_TYPES) > 1024:
+            _OBJ_TYPES.clear()
+        t = _OBJ_TYPES[key] = torch.tensor(list(key[0]), dtype=torch.int32, device=device)
+    return t
+
+
 class Material(object):
     """scene.py:89-101"""
 
@@ -142,29 +159,36 @@ class Scene(object):
         (scene.py:24-25) in RAY index space; the root variant shades pixel (a,b) with
         ray [b,a], hence the transpose."""
         key = (n, S)
+        transposed = not self.camera.has_transform
         if jitter is not None:
             jx, jy = (np.asarray(j, dtype=np.float32) for j in jitter)
-        elif seed is not None and (n, S, int(seed)) in self._jitter:
-            # seeded draws are reproducible: upload once, reuse (also keeps a loss closure that
-            # passes seed= free of host->device copies, i.e. capturable into a CUDA graph)
-            self._jitter[key] = self._jitter[(n, S, int(seed))]
-            return self._jitter[key]
         elif seed is not None:
-            rng = np.random.RandomState(seed)
-            jx = np.asarray(rng.random_sample((n, n, S)), dtype=np.float32)
-            jy = np.asarray(rng.random_sample((n, n, S)), dtype=np.float32)
+            # seeded draws are reproducible: generated and uploaded once per process (module-level
+            # cache, so even a Scene rebuilt inside a loss closure stays free of host->device copies)
+            gkey = (n, S, int(seed), transposed, str(device))
+            out = _SEEDED_JITTER.get(gkey)
+            if out is None:
+                rng = np.random.RandomState(seed)
+                jx = np.asarray(rng.random_sample((n, n, S)), dtype=np.float32)
+                jy = np.asarray(rng.random_sample((n, n, S)), dtype=np.float32)
+                if transposed:
+                    jx, jy = jx.transpose(1, 0, 2), jy.transpose(1, 0, 2)
+                if len(_SEEDED_JITTER) > 64:
+                    _SEEDED_JITTER.clear()
+                out = _SEEDED_JITTER[gkey] = (torch.from_numpy(np.ascontiguousarray(jx)).to(device),
+                                              torch.from_numpy(np.ascontiguousarray(jy)).to(device))
+            self._jitter[key] = out
+            return out
         elif key in self._jitter:
             return self._jitter[key]
         else:
             jx = np.asarray(np.random.random((n, n, S)), dtype=np.float32)
             jy = np.asarray(np.random.random((n, n, S)), dtype=np.float32)
-        if not self.camera.has_transform:
+        if transposed:
             jx, jy = jx.transpose(1, 0, 2), jy.transpose(1, 0, 2)
         out = (torch.from_numpy(np.ascontiguousarray(jx)).to(device),
                torch.from_numpy(np.ascontiguousarray(jy)).to(device))
         self._jitter[key] = out
-        if jitter is None and seed is not None:
-            self._jitter[(n, S, int(seed))] = out
         return out
 
     def reset_jitter(self):
@@ -187,14 +211,21 @@ class Scene(object):
         (chain.py), obj_type, and the packed tables of constant materials / light / camera."""
         st = self._cache
         shapes = list(self.shapes)
-        if (st is not None and st['device'] == device and len(st['shapes']) == len(shapes)
-                and all(a is b for a, b in zip(st['shapes'], shapes))
-                and all(a is b.w2o for a, b in zip(st['w2o'], shapes))
-                and st['camera'] is self.camera and st['light'] is self.lights[0]):
+        light = self.lights[0]
+        # everything the cached tables were packed from, by identity: shapes, their transforms and
+        # materials (and the constant materials' field tensors), the light's fields, the camera
+        sig = (device, tuple(id(s) for s in shapes), tuple(id(s.w2o) for s in shapes),
+               tuple((id(s.material),) + tuple(id(getattr(s.material, f)) for f in ('ka', 'kd', 'ks', 'shininess', 'color'))
+                     for s in shapes),
+               id(light), id(light.direction), id(light.intensity),
+               id(self.camera), id(self.camera.o2w), id(self.camera.look_at))
+        if st is not None and st['sig'] == sig:
             return st
         from .chain import ChainProgram
-        st = dict(device=device, shapes=shapes, w2o=[s.w2o for s in shapes], camera=self.camera, light=self.lights[0])
-        st['obj_type'] = torch.tensor([s.kind for s in shapes], dtype=torch.int32, device=device)
+        # (the objects themselves are kept alive in the cache entry, so the ids in `sig` stay unique)
+        st = dict(sig=sig, device=device, shapes=shapes, w2o=[s.w2o for s in shapes], camera=self.camera, light=light,
+                  materials=[s.material for s in shapes])
+        st['obj_type'] = _obj_type_tensor([s.kind for s in shapes], device)
         # two programs, so that the shapes' rows ARE the renderer's w2o table (no slicing of a
         # joint output and no scatter of its gradient), and a constant camera is evaluated once
         st['prog'] = st['cam_prog'] = None
@@ -260,35 +291,37 @@ class Scene(object):
                               shadows=int(self.shadows))
 
     # -- rendering ------------------------------------------------------------------
-    def build(self, antialias_samples=4, jitter=None, seed=None, cull=None):
-        """Render the scene (scene.py:18-52) -> image (x_dims, y_dims, 3) float32 on the
-        GPU, differentiable w.r.t. shape transforms, materials, the light and (orbit
-        variant) the camera transform."""
+    def _prepare(self, antialias_samples, jitter, seed, cull):
+        """Shared prologue of build() / build_mse(): device, config, packed tables, jitter and the
+        camera's last-sample bookkeeping (scene.py:30-32 leaves the last RayField on the camera)."""
         if not torch.cuda.is_available():
             raise nat.NativeError('Scene.build needs a CUDA device (B200); there is no CPU fallback')
         device = self.device()
         if device.type != 'cuda':
             device = torch.device('cuda', torch.cuda.current_device())
         cfg = self.config(antialias_samples, cull)     # culling never changes a bit of the result
-        obj_type, w2o, mat, light, cam = self.pack(device)
+        tables = self.pack(device)
         jit = self._jitter_for(cfg.n, cfg.samples, jitter, seed, device)
         self.camera._rays, self.camera._last_sample = None, ('lazy', jit, cfg.samples, not self.camera.has_transform)
+        return device, cfg, tables, jit
+
+    def build(self, antialias_samples=4, jitter=None, seed=None, cull=None):
+        """Render the scene (scene.py:18-52) -> image (x_dims, y_dims, 3) float32 on the
+        GPU, differentiable w.r.t. shape transforms, materials, the light and (orbit
+        variant) the camera transform."""
+        device, cfg, (obj_type, w2o, mat, light, cam), jit = self._prepare(antialias_samples, jitter, seed, cull)
         return R.render(cfg, obj_type, w2o, mat, light, cam, jit)
 
     def build_mse(self, target, antialias_samples=4, channel_weight=None, jitter=None, seed=None,
-                  want_image=False):
+                  want_image=False, cull=None):
         """Fused forward + sum((image-target)^2) + reverse pass in ONE kernel (the cost of
         match_mirror.py:45 and of every autoencoder, autoencoder.py:76).  Returns a
         differentiable scalar loss (float32) -- call .backward() on it -- and, if asked,
         the detached image."""
-        device = self.device()
-        cfg = self.config(antialias_samples)
-        obj_type, w2o, mat, light, cam = self.pack(device)
-        jit = self._jitter_for(cfg.n, cfg.samples, jitter, seed, device)
+        device, cfg, (obj_type, w2o, mat, light, cam), jit = self._prepare(antialias_samples, jitter, seed, cull)
         loss, image = _FusedMSE.apply(w2o, mat, light, cam, cfg, obj_type, jit,
                                       as_tensor(target).to(device), channel_weight, want_image)
         return (loss, image) if want_image else loss
-
 
     def mse_cost(self, target, antialias_samples=4, channel_weight=None, jitter=None, seed=None):
         """The cost expression `((scene.build() - target) ** 2).sum()` (match_mirror.py:45) as a

@@ -33,12 +33,57 @@ def set_default_device(device):
     _DEFAULT_DEVICE = torch.device(device)
 
 
+_CONST_CACHE = {}
+_CONST_CACHE_MAX = 4096
+
+
 def as_tensor(x, device=None):
-    """T.as_tensor_variable equivalent: tensors pass through (keeping autograd),
-    everything else becomes a float32 constant on the default device."""
+    """T.as_tensor_variable equivalent: tensors pass through (keeping autograd; non-float32
+    tensors are cast), everything else becomes a float32 constant on the default device.
+    Constants are cached BY VALUE: a loss closure that rebuilds its scene on every call, the way
+    the reference's decoders do (orbit_experiments/test_optimization.py:17-44:
+    `translate(center2) * scale((6, 6, 6))`, `Material((0.9, 0, 0), ...)` inside `scene()`),
+    uploads each constant once and can then be captured into a CUDA graph (no host->device
+    copy on the steady-state path).  The cached tensors are shared: never modify them in place."""
     if isinstance(x, torch.Tensor):
         return x if x.dtype == torch.float32 else x.float()
-    return torch.as_tensor(np.asarray(x, dtype=np.float32), device=device or default_device())
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+    dev = torch.device(device) if device is not None else default_device()
+    if a.size > 64:                       # images / targets: not worth hashing, not constants of the algebra
+        return torch.as_tensor(a, device=dev)
+    key = (a.tobytes(), a.shape, str(dev))
+    t = _CONST_CACHE.get(key)
+    if t is None:
+        if len(_CONST_CACHE) >= _CONST_CACHE_MAX:
+            _CONST_CACHE.clear()
+        t = _CONST_CACHE[key] = torch.as_tensor(a, device=dev)
+    return t
+
+
+class _Arg(object):
+    """One argument of a primitive transform: a LIVE parameter (any torch tensor handed in by the
+    user -- re-read on every evaluation, cast to float32 lazily so that in-place optimiser updates of
+    a float64 / half parameter are seen, like a theano.shared variable) or a constant (host value
+    kept for the chain compiler, device tensor from the by-value cache)."""
+    __slots__ = ('src', 'host', 'param')
+
+    def __init__(self, x, device=None):
+        self.param = isinstance(x, torch.Tensor)
+        if self.param:
+            self.src, self.host = x, None
+        else:
+            self.host = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+            self.src = as_tensor(self.host, device=device)
+
+    @property
+    def t(self):
+        """float32 view of the current value"""
+        x = self.src
+        return x if x.dtype == torch.float32 else x.float()
+
+    @property
+    def device(self):
+        return self.src.device
 
 
 class RayField(object):
@@ -66,7 +111,7 @@ class Transform(object):
         self._fm, self._fmInv = _fm, _fmInv
         self._dynamic = _dynamic
         # structure of the expression, for the native parameter->matrix chain (chain.py):
-        #   ('T'|'S', tensor, is_parameter) | ('R', angle, axis, is_parameter) | ('mul', A, B) | ('inv', A)
+        #   ('T'|'S', _Arg) | ('R', _Arg angle, _Arg axis) | ('mul', A, B) | ('inv', A)
         #   | ('I',) | None (explicit matrices: not expressible, torch path only)
         self._expr = _expr
 
@@ -147,30 +192,37 @@ def _place(device, entries):
 
 def translate(x):
     """transform.py:60-75"""
-    dyn = isinstance(x, torch.Tensor)
-    x = as_tensor(x)
-    return Transform(_fm=lambda: _place(x.device, {(0, 3): x[0], (1, 3): x[1], (2, 3): x[2]}),
-                     _fmInv=lambda: _place(x.device, {(0, 3): -x[0], (1, 3): -x[1], (2, 3): -x[2]}),
-                     _dynamic=dyn, _expr=('T', x, dyn))
+    a = _Arg(x)
+    return Transform(_fm=lambda: _translation(a.t, 1.0), _fmInv=lambda: _translation(a.t, -1.0),
+                     _dynamic=a.param, _expr=('T', a))
+
+
+def _translation(x, sign):
+    if sign < 0:
+        x = -x
+    return _place(x.device, {(0, 3): x[0], (1, 3): x[1], (2, 3): x[2]})
 
 
 def scale(x):
     """transform.py:78-93 (inverse is 1/x)"""
-    dyn = isinstance(x, torch.Tensor)
-    x = as_tensor(x)
-    return Transform(_fm=lambda: _place(x.device, {(0, 0): x[0], (1, 1): x[1], (2, 2): x[2]}),
-                     _fmInv=lambda: _place(x.device, {(0, 0): 1. / x[0], (1, 1): 1. / x[1], (2, 2): 1. / x[2]}),
-                     _dynamic=dyn, _expr=('S', x, dyn))
+    a = _Arg(x)
+    return Transform(_fm=lambda: _scaling(a.t, False), _fmInv=lambda: _scaling(a.t, True),
+                     _dynamic=a.param, _expr=('S', a))
+
+
+def _scaling(x, inverse):
+    if inverse:
+        return _place(x.device, {(0, 0): 1. / x[0], (1, 1): 1. / x[1], (2, 2): 1. / x[2]})
+    return _place(x.device, {(0, 0): x[0], (1, 1): x[1], (2, 2): x[2]})
 
 
 def rotate(angle, axis):
     """transform.py:95-122: angle in DEGREES about an (assumed unit) axis; the
     inverse is the transpose."""
-    dyn = isinstance(angle, torch.Tensor) or isinstance(axis, torch.Tensor)
-    axis_t = as_tensor(axis)
-    angle_t = as_tensor(angle, device=axis_t.device)
-    return Transform(_fm=lambda: _rotation(angle_t, axis_t), _fmInv=lambda: _rotation(angle_t, axis_t).t(),
-                     _dynamic=dyn, _expr=('R', angle_t, axis_t, dyn))
+    ax = _Arg(axis)
+    an = _Arg(angle, device=ax.device)
+    return Transform(_fm=lambda: _rotation(an.t, ax.t.to(an.device)), _fmInv=lambda: _rotation(an.t, ax.t.to(an.device)).t(),
+                     _dynamic=an.param or ax.param, _expr=('R', an, ax))
 
 
 def _rotation(angle, a):

@@ -27,6 +27,6 @@ def _extension_built():
     library is never rebuilt behind the tests' back.  (The product itself still fails loudly
     when the library is absent: _native.lib() raises NativeError.)"""
     from reversible_raytracer_b200 import _native as nat
-    if not os.path.exists(nat.LIB_PATH):
+    if not os.path.exists(nat.LIB_PATH) or not os.path.exists(nat.BENCH_LIB_PATH):
         nat.build(force=True)
     yield

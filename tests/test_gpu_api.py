@@ -156,8 +156,10 @@ def test_fit_golden_orbit_renders(cuda):
         m2 = Material((0.9, 0.0, 0.0), 0.3, 0.9, 0.4, 50.)
         cams = [Camera(64, 64, translate((0, y, 0)), np.asarray([0, 0, 1], dtype='float32')) for y in (2.5, -2.5)]
 
+        z32 = torch.tensor(32.0, device=cuda)      # created OUTSIDE the closure: no host->device copy per call
+
         def centre():
-            return torch.stack([9 * torch.cos(theta), 9 * torch.sin(theta), torch.tensor(32.0, device=cuda)])
+            return torch.stack([9 * torch.cos(theta), 9 * torch.sin(theta), z32])
 
         scs = []
         for cam in cams:
@@ -173,6 +175,7 @@ def test_fit_golden_orbit_renders(cuda):
         train = GDOptimizer().optimize([theta], cost)
         for _ in range(25):
             train(2e-5)
+        assert train.state['graph'] is not None and not train.state['failed']     # steps 3.. are graph replays
         with torch.no_grad():
             c = centre()
             for v, sc in enumerate(scs):
@@ -231,6 +234,61 @@ def test_graph_captured_optimizer_matches_eager(cuda):
     np.testing.assert_allclose(v_g, v_e, rtol=1e-5)
     np.testing.assert_allclose(a_g, a_e, rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(b_g, b_e, rtol=1e-5, atol=1e-6)
+
+
+def test_graph_capture_survives_reference_closure_style(cuda):
+    """The reference's decoders rebuild materials, transforms, shapes, light, camera and Scene on
+    EVERY call (orbit_experiments/test_optimization.py:17-44).  Constants are cached by value, the
+    chain op table by structure, seeded jitter per process -- so such a closure performs no
+    host<->device copy in steady state and GDOptimizer captures it into a CUDA graph (round 1 fell
+    back to eager stepping with a warning here)."""
+    import warnings
+    target = torch.rand((2, 64, 64, 3), device=cuda)
+
+    def scene(obj_param, cam_y, seed):
+        material1 = Material((0.0, 0.9, 0.0), 0.3, 0.7, 0.5, 50.)
+        material2 = Material((0.9, 0.0, 0.0), 0.3, 0.9, 0.4, 50.)
+        center2 = np.asarray([0, 0, 48], dtype='float32')
+        shapes = [Sphere(translate(obj_param) * scale((4, 4, 4)), material1),
+                  Sphere(translate(center2) * scale((6, 6, 6)), material2)]
+        light = Light((-0., -0., 1), (1., 1., 1.))
+        camera = Camera(64, 64, translate((0, cam_y, 0)), np.asarray([0, 0, 1], dtype='float32'))
+        return Scene(shapes, [light], camera, PhongShader(specular=False)).build(seed=seed)
+
+    def run(graph):
+        c = torch.tensor([3.0, -8.0, 32.0], device=cuda)
+
+        def cost():
+            return ((scene(c, 2.5, 5) - target[0]) ** 2).sum() + ((scene(c, -2.5, 6) - target[1]) ** 2).sum()
+        train = GDOptimizer().optimize([c], cost, graph=graph)
+        with warnings.catch_warnings():
+            warnings.simplefilter('error')         # a failed capture warns: make it fail the test
+            vals = [train(1e-4) for _ in range(6)]
+        return vals, c.detach().cpu().numpy(), train.state
+    v_e, c_e, _ = run(False)
+    v_g, c_g, st = run('auto')
+    assert st['graph'] is not None and not st['failed']
+    np.testing.assert_allclose(v_g, v_e, rtol=1e-5)
+    np.testing.assert_allclose(c_g, c_e, rtol=1e-5, atol=1e-6)
+
+
+def test_graph_capture_validation_catches_host_state(cuda):
+    """A closure that reads host-side state which changes per call (here: the jitter seed) cannot be
+    replayed faithfully; the post-capture validation (replay with lr = 0 vs an eager evaluation)
+    must drop the graph with a warning instead of silently freezing the state."""
+    sc, c1, c2 = _c1(cuda)
+    calls = [0]
+
+    def loss():
+        calls[0] += 1
+        return sc.build(seed=calls[0]).sum()       # a different jitter on every call
+    train = GDOptimizer().optimize([c1, c2], loss)
+    with pytest.warns(UserWarning, match='capture'):
+        for _ in range(4):
+            train(1e-6)
+    assert train.state['graph'] is None and train.state['failed']
+    train.recapture()
+    assert not train.state['failed']
 
 
 def test_batched_autoencoder_decoder_trains(cuda):
@@ -370,9 +428,9 @@ def test_whole_step_kernel_matches_general_path(cuda):
     scA, pA = make()
     scB, pB = make()
     target = torch.flip(scA.build(seed=3).detach(), dims=[1])
-    trainA = GDOptimizer().optimize(pA, scA.mse_cost(target, seed=3), 2e-5)
+    trainA = GDOptimizer().optimize(pA, scA.mse_cost(target, seed=3), lr=2e-5)
     assert trainA.state['whole_step'] is not None, trainA.state.get('whole_step_refused')
-    trainB = GDOptimizer().optimize(pB, lambda: scB.build_mse(target, seed=3), 2e-5)
+    trainB = GDOptimizer().optimize(pB, lambda: scB.build_mse(target, seed=3), lr=2e-5)
     la, lb = [], []
     for i in range(12):
         la.append(trainA())
@@ -387,7 +445,7 @@ def test_whole_step_kernel_matches_general_path(cuda):
     extra = torch.tensor([1.0], device=cuda)
     scC, pC = make()
     cost = scC.mse_cost(target, seed=3)
-    trainC = GDOptimizer().optimize(pC[:2], cost, 2e-5)          # s2 left out -> refused
+    trainC = GDOptimizer().optimize(pC[:2], cost, lr=2e-5)          # s2 left out -> refused
     assert trainC.state['whole_step'] is None and 'exactly' in trainC.state['whole_step_refused']
     l0 = trainC()
     assert np.isfinite(l0)
@@ -442,9 +500,9 @@ def test_whole_step_kernel_depth_shader_channel_weights(cuda):
     scB, pB = make()
     target = torch.rand((32, 32, 3), device=cuda)
     cw = (1.0, 0.0, 0.0)
-    trainA = GDOptimizer().optimize(pA, scA.mse_cost(target, channel_weight=cw, seed=9), 1e-4)
+    trainA = GDOptimizer().optimize(pA, scA.mse_cost(target, channel_weight=cw, seed=9), lr=1e-4)
     assert trainA.state['whole_step'] is not None, trainA.state.get('whole_step_refused')
-    trainB = GDOptimizer().optimize(pB, lambda: scB.build_mse(target, channel_weight=cw, seed=9), 1e-4)
+    trainB = GDOptimizer().optimize(pB, lambda: scB.build_mse(target, channel_weight=cw, seed=9), lr=1e-4)
     la = [trainA() for _ in range(10)]
     lb = [trainB() for _ in range(10)]
     np.testing.assert_allclose(la, lb, rtol=2e-4)

@@ -394,28 +394,37 @@ def test_culling_full_size_slab(cuda):
             assert torch.equal(x, y)
 
 
-def test_streamed_host_buffers_equal_single_launch(cuda):
+@pytest.mark.parametrize('num_objects', [40, 100, 600])
+def test_streamed_host_buffers_equal_single_launch(num_objects, cuda):
     """render.StreamedFusedMSE (row slabs pipelined over copy-in / kernel / copy-out streams,
     target and image in pinned HOST memory) == one whole-image launch: image bit-identical,
-    loss / gradients up to the summation order; and against the oracle."""
-    spec = scenes.stress(n=96, num_objects=40, samples=4, seed=11)
+    loss / gradients up to the summation order.  40 objects: records built per CTA; 100: the
+    record table built once per call + TMA staging on the side streams (what bench.py's e2e leg
+    runs); 600: two TMA chunks.  The scene CHANGES between calls, so a record table that is stale
+    or read before it is rebuilt shows up as a different image."""
+    spec = scenes.stress(n=96, num_objects=num_objects, samples=4, seed=11)
     ps = oc.PackedScene.from_spec(spec, camera_grad=0)
     cfg, ot, w2o, mat, light, cam, _ = to_device(ps, cuda, with_jitter=False)
-    cfg = R.RenderConfig(n=cfg.n, samples=cfg.samples, shader=cfg.shader, transpose=cfg.transpose, seed=77)
+    cfg = R.RenderConfig(n=cfg.n, samples=cfg.samples, shader=cfg.shader, transpose=cfg.transpose, seed=77,
+                         no_small=cfg.no_small, use_records=cfg.use_records)
+    w2o_b = w2o.clone()
+    w2o_b[:, 3] += 0.37 * w2o_b[:, 0]             # every centre moves: another image
     target = torch.rand((cfg.n, cfg.n, 3), device=cuda)
-    loss0, grad0, img0, _ = R.render_fused_mse(cfg, ot, w2o, mat, light, cam, target, want_image=True)
+    ref = [R.render_fused_mse(cfg, ot, w, mat, light, cam, target, want_image=True) for w in (w2o, w2o_b)]
+    assert not torch.equal(ref[0][2], ref[1][2])
     pin_t = target.cpu().pin_memory()
     pin_i = torch.empty_like(pin_t).pin_memory()
     for slabs in (1, 3, 5):
         st = R.StreamedFusedMSE(cfg, w2o.shape[0], cuda, slabs=slabs)
-        for rep in range(2):                     # second call reuses buffers / events
+        for rep in range(4):                     # later calls reuse buffers / events, scene alternates
+            loss0, grad0, img0, _ = ref[rep & 1]
             pin_i.zero_()
-            loss, grad = st(ot, w2o, mat, light, cam, pin_t, pin_i)
+            loss, grad = st(ot, (w2o, w2o_b)[rep & 1], mat, light, cam, pin_t, pin_i)
             torch.cuda.synchronize()
             assert torch.equal(pin_i, img0.cpu())
             np.testing.assert_allclose(float(loss), float(loss0), rtol=1e-6)
-            s = float(grad0.abs().max())
-            assert float((grad - grad0).abs().max()) <= 1e-4 * s
+            s_ = float(grad0.abs().max())
+            assert float((grad - grad0).abs().max()) <= 1e-4 * s_
     with pytest.raises(ValueError):
         st(ot, w2o, mat, light, cam, target.cpu(), pin_i)       # not pinned
 
@@ -456,17 +465,17 @@ def test_small_and_general_kernels_agree(name, cuda):
     assert float((g1 - g0).abs().max()) <= 1e-4 * float(g0.abs().max())
 
 
-def test_fused_many_samples_small_scene(cuda):
-    """S = 16 fused: beyond the general fused kernel's 8 samples, served by the small-scene kernel."""
-    ps = oc.PackedScene.from_spec(scenes.stress(n=20, num_objects=9, samples=16), camera_grad=1)
+@pytest.mark.parametrize('samples,num_objects', [(16, 9), (16, 100), (12, 40), (32, 600)])
+def test_fused_many_samples(samples, num_objects, cuda):
+    """Fused mode beyond the 8 samples one thread of the general kernel holds: small scenes take the
+    small-scene kernel (power-of-two S), everything else the general kernel's two-pass chunk loop
+    (pass 0 sweeps + shades, pass 1 sweeps again + reverse pass) -- S = 16 with 100 shapes used to
+    be refused with RRT_ERR_UNSUPPORTED."""
+    ps = oc.PackedScene.from_spec(scenes.stress(n=20, num_objects=num_objects, samples=samples), camera_grad=1)
     img_o, _, _ = oc.render_forward(ps, want_aux=False)
     target = np.clip(img_o + 0.1, 0, 1).astype(np.float32)
     image_o, hit_o, loss_o, grad_o = oc.render_fused_mse(ps, target)
     cfg, ot, w2o, mat, light, cam, jit = to_device(ps, cuda)
-    if cfg.no_small:
-        with pytest.raises(Exception):
-            R.render_fused_mse(cfg, ot, w2o, mat, light, cam, torch.from_numpy(target).to(cuda), None, jit)
-        return
     loss, grad, image, hit = R.render_fused_mse(cfg, ot, w2o, mat, light, cam, torch.from_numpy(target).to(cuda),
                                                 None, jit, want_image=True, want_hit=True)
     assert np.array_equal(hit.cpu().numpy().reshape(hit_o.shape), hit_o)

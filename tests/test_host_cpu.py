@@ -66,6 +66,35 @@ def test_inverse_and_exact_zeros():
     assert torch.count_nonzero(off) == 0          # diagonal fast path keys on exact zeros
 
 
+def test_constants_are_cached_by_value_and_nonfloat32_parameters_stay_live():
+    """as_tensor caches constants by value (a closure that rebuilds its scene uploads nothing in
+    steady state); a float64 parameter is cast lazily, so in-place updates are seen (a
+    theano.shared stays live in the reference, transform.py:60-75)."""
+    from reversible_raytracer_b200.transform import as_tensor
+    from reversible_raytracer_b200.chain import ChainProgram, flatten
+    assert as_tensor((0, 0, 48)) is as_tensor([0., 0., 48.])
+    assert T.translate((0, 0, 48))._expr[1].src is T.translate((0, 0, 48))._expr[1].src
+    p = torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64)
+    t = T.translate(p) * T.scale((2, 2, 2))
+    assert float(t.m[0, 3]) == 1.0
+    p[0] = 5.0
+    assert float(t.m[0, 3]) == 5.0 and t.m.dtype == torch.float32
+    assert flatten(t)[0][2][0].src is p            # the chain compiler sees the ORIGINAL tensor
+
+
+def test_chain_structure_is_cached_across_rebuilt_expressions():
+    """The reference's decoders rebuild `T.translate(c) * T.scale((4,4,4))` on every call
+    (orbit_experiments/test_optimization.py:17-44); the compiled op table is keyed by structure."""
+    from reversible_raytracer_b200.chain import ChainProgram
+    dev = torch.device('cpu')
+    a = ChainProgram([(T.translate(torch.zeros(3)) * T.scale((4, 4, 4))).inverse(), T.translate((0, 0, 48)).inverse()], dev)
+    b = ChainProgram([(T.translate(torch.ones(3)) * T.scale((4, 4, 4))).inverse(), T.translate((0, 0, 48)).inverse()], dev)
+    c = ChainProgram([(T.translate(torch.ones(3)) * T.scale((5, 4, 4))).inverse(), T.translate((0, 0, 48)).inverse()], dev)
+    assert a.structure is b.structure and a.structure is not c.structure
+    assert a.param_tensors[0] is not b.param_tensors[0]
+    np.testing.assert_array_equal(b.values().numpy(), [4, 4, 4, 0, 0, 48, 1, 1, 1])   # constants, then parameters
+
+
 def test_lazy_transform_tracks_inplace_updates_and_autograd():
     c = torch.tensor([1., 2., 3.], requires_grad=True)
     s = Sphere(T.translate(c) * T.scale((2, 2, 2)), Material((1, 1, 1), .3, .7, .5, 50.))
@@ -200,6 +229,12 @@ def test_cabi_exports_and_struct_layout(tmp_path):
     for name in declared:
         assert hasattr(L, name), name
     assert L.rrt_version() == 100
+    # the measurement helpers live in their own library / header (never in the product ABI)
+    bh = open(os.path.join(ROOT, 'include', 'rrt_b200_bench.h')).read()
+    bdecl = sorted(set(re.findall(r'\b(rrt_[a-z0-9_]+)\s*\(', bh)))
+    assert set(bdecl) == set(nat.BENCH_EXPORTS) and not set(bdecl) & set(declared)
+    for name in bdecl:
+        assert hasattr(nat.bench_lib(), name), name
     # struct layout: ctypes mirror == what the C compiler sees
     src = tmp_path / 'sz.c'
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rrt_b200.h"\nint main(){printf("%zu %zu %zu %zu", sizeof(rrt_scene), '
@@ -244,6 +279,16 @@ def test_gdoptimizer_both_call_shapes():
     np.testing.assert_allclose(x.detach().numpy(), [0.0, 0.0], atol=1e-6)
     with pytest.raises(TypeError):
         GDOptimizer().optimize([x], loss)()
+    # HEAD's third positional argument is `momentum` (optimize.py:19), unused there and here
+    x3 = torch.tensor([1.0])
+    train3 = GDOptimizer().optimize([x3], lambda: (x3 ** 2).sum(), 0.9)
+    train3(0.25)
+    np.testing.assert_allclose(x3.detach().numpy(), [0.5], rtol=1e-6)
+    train4 = GDOptimizer().optimize([x3], lambda: (x3 ** 2).sum(), lr=0.5)
+    train4()
+    np.testing.assert_allclose(x3.detach().numpy(), [0.0], atol=1e-7)
+    with pytest.raises(TypeError):
+        GDOptimizer().optimize([x3], loss, 1, 2, 3)
     assert abs(get_epsilon(1e-4, 200, 100) - 1e-4 / 1.5) < 1e-12
 
 
