@@ -93,6 +93,12 @@ extern "C" {
 /* Diagnostic: run the shadow pass of the general kernel with the scalar routine only (the
  * packed FFMA2 filter in front of it is exact, so results are identical; A/B and tests). */
 #define RRT_FLAG_SCALAR_SHADOWS 8
+/* Reverse pass produces d/d w2o (and, with camera_grad, d/d camera.o2w) only: the material, light
+ * and look_at entries of the gradient vector are left ZERO and their sums are not computed.  For
+ * callers that chain only through the transforms -- every autoencoder decoder of the reference
+ * (autoencoder.py:57-71, orbit_experiments/autoencoder_2ly.py:82-91: materials, light and camera
+ * direction are constants there). */
+#define RRT_FLAG_NO_MATERIAL_GRAD 16
 
 #define RRT_OK 0
 #define RRT_ERR_INVALID (-1)   /* bad argument (message in rrt_last_error)            */
@@ -156,6 +162,14 @@ typedef struct rrt_scene {
      * rebuilding the records in every CTA.  NULL => the kernels build the records themselves.
      * Same bits either way.  Must be rebuilt whenever w2o or the camera changes.               */
     const float* obj_records;
+
+    /* Optional scratch, uint32 [num_scenes] in device memory: ZERO before its first use, left zero
+     * by every call (the kernels reset what they used), never touched by the host afterwards.
+     * With it the reverse-pass entry points are ONE launch: the last CTA to finish a scene
+     * (device-side ticket + __threadfence) finalises that scene's gradient (d/dA = M C^T + g_b ct^T,
+     * camera and light chains) inside the render kernel instead of a second launch.  Calls that
+     * may run concurrently (different streams) need different scratch.  NULL => separate launch. */
+    uint32_t* ticket;
 } rrt_scene;
 
 #define RRT_RECORD_FLOATS 16

@@ -42,6 +42,7 @@ class RrtScene(C.Structure):
         ('light_scene_stride', C.c_int64), ('camera_scene_stride', C.c_int64),
         ('jitter_scene_stride', C.c_int64), ('base_rays', C.c_void_p),
         ('scene_begin', C.c_int32), ('flags', C.c_int32), ('obj_records', C.c_void_p),
+        ('ticket', C.c_void_p),
     ]
 
 
@@ -138,7 +139,7 @@ EXPORTS = ['rrt_version', 'rrt_last_error', 'rrt_render_forward', 'rrt_render_ba
            'rrt_peer_allreduce', 'rrt_peer_buffer_bytes', 'rrt_peer_signal_bytes', 'rrt_build_records',
            'rrt_small_step_mse']
 
-FLAG_CULL, FLAG_NO_SMALL, FLAG_SHADOWS, FLAG_SCALAR_SHADOWS = 1, 2, 4, 8
+FLAG_CULL, FLAG_NO_SMALL, FLAG_SHADOWS, FLAG_SCALAR_SHADOWS, FLAG_NO_MATERIAL_GRAD = 1, 2, 4, 8, 16
 HIT_SHADOWED = 0x40000000
 CHAIN_TRANSLATE, CHAIN_SCALE, CHAIN_ROTATE, CHAIN_INVERT, CHAIN_MAX_OPS = 1, 2, 3, 0x100, 8
 

@@ -39,80 +39,11 @@ __global__ void primary_rays_kernel(int n, double step, float* __restrict__ out)
 }
 
 // ---------------------------------------------------------------- gradient finalisation
-// One CTA per scene.  Converts the raw per-object sums [M, g_b] into d/d w2o and
-// folds the camera and light chains (see backward_ray).
-__global__ void finalize_grads(const __grid_constant__ KParams P) {
-    const rrt_scene& sc = P.sc;
-    const int N = sc.num_objects, scene = blockIdx.x, tid = threadIdx.x;
-    float* gobj = P.grad + (size_t)scene * RRT_GRAD_SIZE(N);
-    float* gglobal = gobj + (size_t)N * RRT_OBJ_GRAD_STRIDE;
-    const float* cam = sc.camera + (size_t)scene * sc.camera_scene_stride;
-    const float* w2o = sc.w2o + (size_t)scene * sc.w2o_scene_stride;
+// One CTA per scene (the separate-launch form; with rrt_scene.ticket the render kernels call
+// finalize_scene themselves from the last CTA of each scene).
+__global__ void __launch_bounds__(128) finalize_grads(const __grid_constant__ KParams P) {
     __shared__ float camg[12];
-    if (tid < 12) camg[tid] = 0.f;
-    __syncthreads();
-    float C[9], ct[3];
-#pragma unroll
-    for (int r = 0; r < 3; r++) {
-        C[r * 3] = cam[r * 4]; C[r * 3 + 1] = cam[r * 4 + 1]; C[r * 3 + 2] = cam[r * 4 + 2];
-        ct[r] = cam[r * 4 + 3];
-    }
-    float cg[12];
-#pragma unroll
-    for (int q = 0; q < 12; q++) cg[q] = 0.f;
-    for (int k = tid; k < N; k += blockDim.x) {
-        float* og = gobj + (size_t)k * RRT_OBJ_GRAD_STRIDE;
-        float M[9], gb[3], A[9];
-#pragma unroll
-        for (int q = 0; q < 9; q++) M[q] = og[q];
-#pragma unroll
-        for (int q = 0; q < 3; q++) gb[q] = og[9 + q];
-        const float* w = w2o + (size_t)k * RRT_W2O_STRIDE;
-#pragma unroll
-        for (int r = 0; r < 3; r++) { A[r * 3] = w[r * 4]; A[r * 3 + 1] = w[r * 4 + 1]; A[r * 3 + 2] = w[r * 4 + 2]; }
-        // d/dA = M C^T + g_b ct^T ;  d/db = g_b        (d' = A C r, o' = A ct + b)
-        float out[12];
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-                out[r * 4 + c] = M[r * 3] * C[c * 3] + M[r * 3 + 1] * C[c * 3 + 1] + M[r * 3 + 2] * C[c * 3 + 2] + gb[r] * ct[c];
-            out[r * 4 + 3] = gb[r];
-        }
-#pragma unroll
-        for (int q = 0; q < 12; q++) og[q] = out[q];
-        if (sc.camera_grad) {
-            // d/dC = sum_k A_k^T M_k ; d/dct = sum_k A_k^T g_b,k
-#pragma unroll
-            for (int r = 0; r < 3; r++) {
-#pragma unroll
-                for (int c = 0; c < 3; c++)
-                    cg[r * 4 + c] += A[0 * 3 + r] * M[0 * 3 + c] + A[1 * 3 + r] * M[1 * 3 + c] + A[2 * 3 + r] * M[2 * 3 + c];
-                cg[r * 4 + 3] += A[0 * 3 + r] * gb[0] + A[1 * 3 + r] * gb[1] + A[2 * 3 + r] * gb[2];
-            }
-        }
-    }
-    if (sc.camera_grad) {
-#pragma unroll
-        for (int q = 0; q < 12; q++) {
-            float x = warp_sum(cg[q]);
-            if ((tid & 31) == 0 && x != 0.f) atomicAdd(&camg[q], x);
-        }
-    }
-    __syncthreads();
-    if (tid < 12) gglobal[6 + tid] = camg[tid];
-    if (tid == 0) {
-        // Lhat = L/|L|  =>  g_L = (g_Lhat - Lhat (Lhat . g_Lhat)) / |L|    scene.py:83-86
-        const float* li = sc.light + (size_t)scene * sc.light_scene_stride;
-        float L0 = li[0], L1 = li[1], L2 = li[2];
-        float ln = sqrtf(L0 * L0 + L1 * L1 + L2 * L2);
-        float h0 = L0 / ln, h1 = L1 / ln, h2 = L2 / ln;
-        float g0 = gglobal[0], g1 = gglobal[1], g2 = gglobal[2];
-        float dot = h0 * g0 + h1 * g1 + h2 * g2;
-        gglobal[0] = (g0 - h0 * dot) / ln;
-        gglobal[1] = (g1 - h1 * dot) / ln;
-        gglobal[2] = (g2 - h2 * dot) / ln;
-    }
+    finalize_scene(P, blockIdx.x, threadIdx.x, blockDim.x, camg);
 }
 
 // ---------------------------------------------------------------- gradient exchange over peer memory

@@ -57,6 +57,9 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, f
 #pragma unroll
     for (int q = 0; q < 16; q++) a[q] = pk(seed + (float)(threadIdx.x + q), seed - (float)q);
     u64 b = pk(1.0000001f, 0.9999999f), c = pk(1e-7f, -1e-7f);
+    // loaded operands are consumed one load LATER (bn/cn -> b/c), like the software-pipelined
+    // object loop of the render kernel: the load latency is off the FMA dependency chains
+    u64 bn = b, cn = c;
     float m = 0.f;
     uint32_t sbase = (uint32_t)__cvta_generic_to_shared(tab);
     asm volatile("mov.u32 %0, %0;" : "+r"(sbase));
@@ -75,13 +78,15 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, f
                 }
                 if (MODE == 3 && (q & 7) == 7) {
                     const float4 v = lds128(row + 16u * (uint32_t)(rep * 2 + (q >> 3)));
-                    b = pk(v.x, v.z);
-                    c = pk(v.y, v.w);
+                    b = bn; c = cn;
+                    bn = pk(v.x, v.z);
+                    cn = pk(v.y, v.w);
                 }
                 if (MODE == 4 && (q & 7) == 7) {
                     const float4 v = c_tab[(it + rep * 2 + (q >> 3)) & 255];
-                    b = pk(1.0000001f + v.x, 0.9999999f + v.z);
-                    c = pk(1e-7f + v.y, -1e-7f + v.w);
+                    b = bn; c = cn;
+                    bn = pk(1.0000001f + v.x, 0.9999999f + v.z);
+                    cn = pk(1e-7f + v.y, -1e-7f + v.w);
                 }
                 if (MODE == 5) {
                     // per 24 FFMA2: 4 FMNMX3 and 1.5 LDS.128  =>  per 48: 8 and 3 (trip = 128 = 2.67 x 48)
@@ -93,8 +98,9 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, f
                     }
                     if (n % 16 == 15) {
                         const float4 v = lds128(row + 16u * (uint32_t)rep);
-                        b = pk(v.x, v.z);
-                        c = pk(v.y, v.w);
+                        b = bn; c = cn;
+                        bn = pk(v.x, v.z);
+                        cn = pk(v.y, v.w);
                     }
                 }
             }

@@ -87,6 +87,8 @@ struct KParams {
     int pow2;          // 1: (u+s)/S/n may be evaluated as exact multiplications
     int vec_ok;        // 1: image/target rows are 16-byte aligned (n % 4 == 0, aligned base pointers)
     rrt_step step;     // rrt_small_step_mse only (whole optimise step in one launch)
+    int small_per;     // render_small_kernel: work items (blocks of kSmallThreads rays) per persistent CTA
+    int n_shift;       // log2(n) when n is a power of two, else -1
 };
 
 // The device code lives in the .cuh parts below, in dependency order (single translation unit).
@@ -141,8 +143,33 @@ bool use_small_kernel(const KParams& P) {
     return rays_scene * sc.num_scenes <= limit;
 }
 
+int sm_count() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+        sms = 148;      // B200
+    return sms;
+}
+
+// Persistent grid of the small-scene kernel: at most one resident wave, every CTA >= 1 work item.
+unsigned small_grid(KParams& P) {
+    const rrt_scene& sc = P.sc;
+    const long long rays_scene = (long long)P.rows * sc.n * sc.samples;
+    const long long total = ((rays_scene + kSmallThreads - 1) / kSmallThreads) * sc.num_scenes;
+    const long long cap = (long long)sm_count() * RRT_SMALL_MIN_BLOCKS;
+    long long per = (total + cap - 1) / cap;
+    if (per < 1) per = 1;
+    P.small_per = (int)per;
+    P.n_shift = -1;
+    if ((sc.n & (sc.n - 1)) == 0)
+        for (int q = 0; q < 31; q++)
+            if ((1 << q) == sc.n) P.n_shift = q;
+    return (unsigned)((total + per - 1) / per);
+}
+
+// *finalized is set when the kernel itself finalised the gradients (rrt_scene.ticket given and
+// supported by the kernel taken); otherwise the caller launches finalize_grads.
 template <int MODE>
-int launch(KParams& P, cudaStream_t st) {
+int launch(KParams& P, cudaStream_t st, bool* finalized = nullptr) {
     const rrt_scene& sc = P.sc;
     P.lin_step = sc.n > 1 ? 1.0 / (double)(sc.n - 1) : 0.0;
     P.inv_s = 1.0f / (float)sc.samples;
@@ -150,12 +177,16 @@ int launch(KParams& P, cudaStream_t st) {
     P.pow2 = ((sc.samples & (sc.samples - 1)) == 0) && ((sc.n & (sc.n - 1)) == 0);
     P.vec_ok = (sc.n % 4 == 0) && (((uintptr_t)P.image & 15) == 0) && (((uintptr_t)P.target & 15) == 0);
     const int S = sc.samples;
+    if (finalized) *finalized = false;
     if (use_small_kernel(P)) {
-        const long long rays_scene = (long long)P.rows * sc.n * S;
-        dim3 grid((unsigned)((rays_scene + kSmallThreads - 1) / kSmallThreads), sc.num_scenes);
-        render_small_kernel<MODE><<<grid, kSmallThreads, 0, st>>>(P);
+        const unsigned grid = small_grid(P);
+        if (MODE != MODE_FWD && (sc.flags & RRT_FLAG_NO_MATERIAL_GRAD))
+            render_small_kernel<MODE, false, true><<<grid, kSmallThreads, 0, st>>>(P);
+        else
+            render_small_kernel<MODE><<<grid, kSmallThreads, 0, st>>>(P);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "small-scene kernel launch: %s", cudaGetErrorString(e));
+        if (finalized) *finalized = (MODE != MODE_FWD) && sc.ticket != nullptr;
         return RRT_OK;
     }
     int pix;
@@ -224,9 +255,10 @@ int rrt_render_backward(const rrt_scene* scene, const float* dl_dimage, const in
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(grad, 0, sizeof(float) * RRT_GRAD_SIZE(scene->num_objects) * scene->num_scenes, st);
     if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "memset grad: %s", cudaGetErrorString(e));
-    rc = launch<MODE_BWD>(P, st);
+    bool finalized = false;
+    rc = launch<MODE_BWD>(P, st, &finalized);
     if (rc) return rc;
-    return launch_finalize(P, st);
+    return finalized ? RRT_OK : launch_finalize(P, st);
 }
 
 int rrt_render_fused_mse(const rrt_scene* scene, const float* target, const float* channel_weight, float* image,
@@ -249,9 +281,10 @@ int rrt_render_fused_mse(const rrt_scene* scene, const float* target, const floa
     cudaError_t e = cudaMemsetAsync(grad, 0, sizeof(float) * RRT_GRAD_SIZE(scene->num_objects) * scene->num_scenes, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(loss, 0, sizeof(double) * scene->num_scenes, st);
     if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "memset grad/loss: %s", cudaGetErrorString(e));
-    rc = launch<MODE_FUSED>(P, st);
+    bool finalized = false;
+    rc = launch<MODE_FUSED>(P, st, &finalized);
     if (rc) return rc;
-    return launch_finalize(P, st);
+    return finalized ? RRT_OK : launch_finalize(P, st);
 }
 
 int rrt_build_records(const rrt_scene* scene, float* records, void* stream) {
@@ -332,9 +365,7 @@ int rrt_small_step_mse(const rrt_scene* scene, const rrt_step* step, const float
     P.inv_s = 1.0f / (float)sc.samples;
     P.inv_n = 1.0f / (float)sc.n;
     P.pow2 = ((sc.samples & (sc.samples - 1)) == 0) && ((sc.n & (sc.n - 1)) == 0);
-    const long long rays_scene = (long long)P.rows * sc.n * sc.samples;
-    dim3 grid((unsigned)((rays_scene + kSmallThreads - 1) / kSmallThreads), 1);
-    render_small_kernel<MODE_FUSED, true><<<grid, kSmallThreads, 0, (cudaStream_t)stream>>>(P);
+    render_small_kernel<MODE_FUSED, true><<<small_grid(P), kSmallThreads, 0, (cudaStream_t)stream>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "whole-step kernel launch: %s", cudaGetErrorString(e));
     return RRT_OK;

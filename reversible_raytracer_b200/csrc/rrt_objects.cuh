@@ -21,6 +21,7 @@ struct Globals {       // per-scene constants, held in shared memory
     float L[3], I[3];
     float Lh[3], Ln;
     float U[3];        // -Lhat in canonical float32 order (shadow mask only)
+    int cam_identity;  // camera rotation part is exactly I (small-scene kernel)
 };
 
 // canonical -Lhat (bit-identical to orc_prep in oracle/oracle_c.c): RN sqrt and div

@@ -21,40 +21,47 @@ __device__ __forceinline__ int slot_for(int* slot_key, int key) {
     return -1;
 }
 
-// Sum of 19 per-lane values over the warp as a TRANSPOSED butterfly: at every stage a lane
+// Sum of NV per-lane values over the warp as a TRANSPOSED butterfly: at every stage a lane
 // keeps one half of its values and trades the other half with its partner, so the whole
-// reduction is 10+5+3+2+1 = 21 shuffles (instead of 19 x 5) and ends with lane l holding the
-// complete sum of value index `v` (returned; -1 for the lanes that hold padding).
+// reduction is ceil(NV/2) + ceil(NV/4) + ... shuffles (21 for NV = 19, 13 for NV = 12, instead
+// of NV x 5) and ends with lane l holding the complete sum of value index `v` (returned; -1
+// for the lanes that hold padding).  Fixed lane pairing => the result does not depend on
+// scheduling (it is one of the deterministic stages of RRT_FLAG_DETERMINISTIC).
 __device__ __forceinline__ float xchg_add(float keep, float send, int offset) {
     return keep + __shfl_xor_sync(0xffffffffu, send, offset);
 }
-__device__ __forceinline__ float warp_reduce19(const float (&a)[19], bool mine, int lane, int& v) {
-    float b[10], c[6], d[4], e[2];
-    bool up = lane & 16;
+template <int NI, int NO>
+__device__ __forceinline__ void reduce_stage(const float (&in)[NI], float (&out)[NO], bool up, int offset) {
 #pragma unroll
-    for (int j = 0; j < 10; j++) {
-        const float lo = mine ? a[j] : 0.f;
-        const float hi = (j < 9 && mine) ? a[j < 9 ? 10 + j : 18] : 0.f;   // value 19 is padding
-        b[j] = xchg_add(up ? hi : lo, up ? lo : hi, 16);
+    for (int j = 0; j < NO; j++) {
+        const float lo = in[j];
+        const float hi = (NO + j < NI) ? in[(NO + j < NI) ? NO + j : 0] : 0.f;
+        out[j] = xchg_add(up ? hi : lo, up ? lo : hi, offset);
     }
-    up = lane & 8;
+}
+template <int NV>
+__device__ __forceinline__ float warp_reduce_n(const float (&a)[NV], bool mine, int lane, int& v) {
+    constexpr int n1 = (NV + 1) / 2, n2 = (n1 + 1) / 2, n3 = (n2 + 1) / 2, n4 = (n3 + 1) / 2;
+    static_assert(n4 <= 2, "warp_reduce_n: at most 32 values");
+    float m[NV], b[n1], c[n2], d[n3], e[n4], f[1];
 #pragma unroll
-    for (int j = 0; j < 5; j++) c[j] = xchg_add(up ? b[5 + j] : b[j], up ? b[j] : b[5 + j], 8);
-    c[5] = 0.f;
-    up = lane & 4;
-#pragma unroll
-    for (int j = 0; j < 3; j++) d[j] = xchg_add(up ? c[3 + j] : c[j], up ? c[j] : c[3 + j], 4);
-    d[3] = 0.f;
-    up = lane & 2;
-#pragma unroll
-    for (int j = 0; j < 2; j++) e[j] = xchg_add(up ? d[2 + j] : d[j], up ? d[j] : d[2 + j], 2);
-    up = lane & 1;
-    const float total = xchg_add(up ? e[1] : e[0], up ? e[0] : e[1], 1);
-    const int j3 = ((lane >> 1) & 1) * 2 + (lane & 1);
-    const int ci = ((lane >> 2) & 1) * 3 + j3;
-    const int idx = ((lane >> 4) & 1) * 10 + ((lane >> 3) & 1) * 5 + ci;
-    v = (j3 < 3 && ci < 5 && idx < 19) ? idx : -1;
-    return total;
+    for (int j = 0; j < NV; j++) m[j] = mine ? a[j] : 0.f;
+    reduce_stage<NV, n1>(m, b, lane & 16, 16);
+    reduce_stage<n1, n2>(b, c, lane & 8, 8);
+    reduce_stage<n2, n3>(c, d, lane & 4, 4);
+    reduce_stage<n3, n4>(d, e, lane & 2, 2);
+    reduce_stage<n4, 1>(e, f, lane & 1, 1);
+    // which value this lane ended up with: at every stage the upper partner kept the upper half
+    const int j1 = lane & 1;
+    const int j2 = ((lane >> 1) & 1) * n4 + j1;
+    const int j3 = ((lane >> 2) & 1) * n3 + j2;
+    const int j4 = ((lane >> 3) & 1) * n2 + j3;
+    const int idx = ((lane >> 4) & 1) * n1 + j4;
+    v = (j1 < n4 && j2 < n3 && j3 < n2 && j4 < n1 && idx < NV) ? idx : -1;
+    return f[0];
+}
+__device__ __forceinline__ float warp_reduce19(const float (&a)[19], bool mine, int lane, int& v) {
+    return warp_reduce_n<19>(a, mine, lane, v);
 }
 
 // All 32 lanes call this together.  Each lane holds (key, acc[19]); lanes with the
@@ -78,6 +85,95 @@ __device__ __forceinline__ void warp_flush(int key, float (&acc)[19], int* slot_
     }
 #pragma unroll
     for (int v = 0; v < 19; v++) acc[v] = 0.f;
+}
+
+// ---------------------------------------------------------------- gradient finalisation of one scene
+// Converts the raw per-object sums [M = sum g_d' r_cam^T (9), g_b (3)] into d/d w2o and folds the
+// camera and light chains (see backward_ray).  Called by all `nthreads` threads of ONE CTA after
+// every contribution to the scene has landed (separate launch, or last CTA + __threadfence);
+// reads through L2 (__ldcg) because the sums were produced by other CTAs' atomics.
+__device__ __forceinline__ void finalize_scene(const KParams& P, int scene, int tid, int nthreads, float* camg /* shared [12] */) {
+    const rrt_scene& sc = P.sc;
+    const int N = sc.num_objects;
+    float* gobj = P.grad + (size_t)scene * RRT_GRAD_SIZE(N);
+    float* gglobal = gobj + (size_t)N * RRT_OBJ_GRAD_STRIDE;
+    const float* cam = sc.camera + (size_t)scene * sc.camera_scene_stride;
+    const float* w2o = sc.w2o + (size_t)scene * sc.w2o_scene_stride;
+    const bool geom_only = (sc.flags & RRT_FLAG_NO_MATERIAL_GRAD) != 0;
+    if (tid < 12) camg[tid] = 0.f;
+    __syncthreads();
+    float C[9], ct[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        C[r * 3] = cam[r * 4]; C[r * 3 + 1] = cam[r * 4 + 1]; C[r * 3 + 2] = cam[r * 4 + 2];
+        ct[r] = cam[r * 4 + 3];
+    }
+    float cg[12];
+#pragma unroll
+    for (int q = 0; q < 12; q++) cg[q] = 0.f;
+    for (int k = tid; k < N; k += nthreads) {
+        float* og = gobj + (size_t)k * RRT_OBJ_GRAD_STRIDE;
+        float M[9], gb[3], A[9];
+#pragma unroll
+        for (int q = 0; q < 9; q++) M[q] = __ldcg(og + q);
+#pragma unroll
+        for (int q = 0; q < 3; q++) gb[q] = __ldcg(og + 9 + q);
+        const float* w = w2o + (size_t)k * RRT_W2O_STRIDE;
+#pragma unroll
+        for (int r = 0; r < 3; r++) { A[r * 3] = w[r * 4]; A[r * 3 + 1] = w[r * 4 + 1]; A[r * 3 + 2] = w[r * 4 + 2]; }
+        // d/dA = M C^T + g_b ct^T ;  d/db = g_b        (d' = A C r, o' = A ct + b)
+        float out[12];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                out[r * 4 + c] = M[r * 3] * C[c * 3] + M[r * 3 + 1] * C[c * 3 + 1] + M[r * 3 + 2] * C[c * 3 + 2] + gb[r] * ct[c];
+            out[r * 4 + 3] = gb[r];
+        }
+#pragma unroll
+        for (int q = 0; q < 12; q++) og[q] = out[q];
+        if (geom_only) {                 // RRT_FLAG_NO_MATERIAL_GRAD: material entries are defined to be zero
+#pragma unroll
+            for (int q = 12; q < 19; q++) og[q] = 0.f;
+        }
+        if (sc.camera_grad) {
+            // d/dC = sum_k A_k^T M_k ; d/dct = sum_k A_k^T g_b,k
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    cg[r * 4 + c] += A[0 * 3 + r] * M[0 * 3 + c] + A[1 * 3 + r] * M[1 * 3 + c] + A[2 * 3 + r] * M[2 * 3 + c];
+                cg[r * 4 + 3] += A[0 * 3 + r] * gb[0] + A[1 * 3 + r] * gb[1] + A[2 * 3 + r] * gb[2];
+            }
+        }
+    }
+    if (sc.camera_grad) {
+#pragma unroll
+        for (int q = 0; q < 12; q++) {
+            float x = warp_sum(cg[q]);
+            if ((tid & 31) == 0 && x != 0.f) atomicAdd(&camg[q], x);
+        }
+    }
+    __syncthreads();
+    if (tid < 12) gglobal[6 + tid] = camg[tid];
+    if (tid == 0) {
+        if (geom_only) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) gglobal[q] = 0.f;
+            gglobal[18] = gglobal[19] = gglobal[20] = 0.f;
+        } else {
+            // Lhat = L/|L|  =>  g_L = (g_Lhat - Lhat (Lhat . g_Lhat)) / |L|    scene.py:83-86
+            const float* li = sc.light + (size_t)scene * sc.light_scene_stride;
+            float L0 = li[0], L1 = li[1], L2 = li[2];
+            float ln = sqrtf(L0 * L0 + L1 * L1 + L2 * L2);
+            float h0 = L0 / ln, h1 = L1 / ln, h2 = L2 / ln;
+            float g0 = __ldcg(gglobal), g1 = __ldcg(gglobal + 1), g2 = __ldcg(gglobal + 2);
+            float dot = h0 * g0 + h1 * g1 + h2 * g2;
+            gglobal[0] = (g0 - h0 * dot) / ln;
+            gglobal[1] = (g1 - h1 * dot) / ln;
+            gglobal[2] = (g2 - h2 * dot) / ln;
+        }
+    }
 }
 
 // ---------------------------------------------------------------- conservative tile culling

@@ -193,9 +193,13 @@ __device__ __forceinline__ void shade(int shader, float max_depth, const Obj& ob
 // [M = sum g_d' r_cam^T (9), g_b = sum g_o' (3), d/d(ka,kd,ks,sh,r,g,b)];
 // gg[9] receives [d/d Lhat (3), d/d intensity (3), d/d look_at (3)].
 // The chain M -> d/dA, d/d camera and Lhat -> L is applied by finalize_grads.
+// GEOM_ONLY (RRT_FLAG_NO_MATERIAL_GRAD): only og[0..11] is produced -- the material, light and
+// look_at sums are neither computed nor touched (og may then be a 12-float array).
+template <bool GEOM_ONLY = false, int NOG = 19>
 __device__ __forceinline__ void backward_ray(int shader, float max_depth, const Obj& ob, const float* mat,
                                              const Globals& g, const HitRec& h, const ShadeRec& r, const float rc[3],
-                                             const float gc[3], float og[19], float gg[9]) {
+                                             const float gc[3], float (&og)[NOG], float* gg) {
+    static_assert(NOG == (GEOM_ONLY ? 12 : 19), "backward_ray: accumulator size");
     float g_t = 0.f;
     float g_o[3] = {0.f, 0.f, 0.f}, g_d[3] = {0.f, 0.f, 0.f};
     const bool sphere = !(ob.flags & 1);
@@ -207,23 +211,29 @@ __device__ __forceinline__ void backward_ray(int shader, float max_depth, const 
         for (int c = 0; c < 3; c++) {
             if (!r.inside[c]) continue;
             g_ph += gc[c] * mat[4 + c] * g.I[c];
-            og[16 + c] += gc[c] * r.ph * g.I[c];
-            gg[3 + c] += gc[c] * r.ph * mat[4 + c];
+            if (!GEOM_ONLY) {
+                og[(GEOM_ONLY ? 0 : 16) + c] += gc[c] * r.ph * g.I[c];
+                gg[3 + c] += gc[c] * r.ph * mat[4 + c];
+            }
         }
-        og[12] += g_ph;
-        og[13] += g_ph * r.ndl;
+        if (!GEOM_ONLY) {
+            og[GEOM_ONLY ? 0 : 12] += g_ph;
+            og[GEOM_ONLY ? 0 : 13] += g_ph * r.ndl;
+        }
         float g_ndl = g_ph * mat[1];
         float g_n[3] = {0.f, 0.f, 0.f}, g_Lh[3] = {0.f, 0.f, 0.f};
         if (shader == RRT_SHADER_PHONG) {
-            og[14] += g_ph * r.pw;
-            if (r.rv > 0.0f) og[15] += g_ph * mat[2] * r.pw * __logf(r.rv);
+            if (!GEOM_ONLY) {
+                og[GEOM_ONLY ? 0 : 14] += g_ph * r.pw;
+                if (r.rv > 0.0f) og[GEOM_ONLY ? 0 : 15] += g_ph * mat[2] * r.pw * __logf(r.rv);
+            }
             float dpw = (r.rv != 0.0f) ? __fdividef(r.pw, r.rv) : pow_shininess(r.rv, mat[3] - 1.0f);  // rv^(sh-1)
             float g_rv = g_ph * mat[2] * mat[3] * dpw;
             float g_rm[3];
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 g_rm[c] = g_rv * g.look[c];
-                gg[6 + c] += g_rv * r.rm[c];
+                if (!GEOM_ONLY) gg[6 + c] += g_rv * r.rm[c];
             }
             g_ndl += 2.0f * (g_rm[0] * r.nrm[0] + g_rm[1] * r.nrm[1] + g_rm[2] * r.nrm[2]);
 #pragma unroll
@@ -231,8 +241,10 @@ __device__ __forceinline__ void backward_ray(int shader, float max_depth, const 
         }
 #pragma unroll
         for (int c = 0; c < 3; c++) { g_n[c] -= g_ndl * g.Lh[c]; g_Lh[c] -= g_ndl * r.nrm[c]; }
+        if (!GEOM_ONLY) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) gg[c] += g_Lh[c];
+            for (int c = 0; c < 3; c++) gg[c] += g_Lh[c];
+        }
         if (sphere) {
             float ndg = r.nrm[0] * g_n[0] + r.nrm[1] * g_n[1] + r.nrm[2] * g_n[2];
             float inv = __frcp_rn(r.pn);

@@ -157,18 +157,28 @@ class GDOptimizer(object):
                         var.sub_(g, alpha=float(step_lr))
             return value
 
+        def side_stream():
+            # Every step -- eager warm-up steps included -- runs on ONE private stream: autograd ties a
+            # leaf's gradient accumulator to the stream it was created on, and a capture on another
+            # stream would have to synchronise with it (cudaErrorStreamCaptureImplicit when that is
+            # the legacy default stream and the closure's graph is still referenced, e.g. by
+            # scene.shapes).
+            if st.get('stream') is None:
+                st['stream'] = torch.cuda.Stream(device=tVars[0].device)
+            return st['stream']
+
         def capture():
             dev = tVars[0].device
             st['lr'] = torch.zeros((), dtype=torch.float32, device=dev)
-            side = torch.cuda.Stream(device=dev)
+            side = side_stream()
             side.wait_stream(torch.cuda.current_stream(dev))
             saved = [v.detach().clone() for v in tVars]
-            with torch.cuda.stream(side):          # warm-up on a side stream (PyTorch capture recipe)
+            with torch.cuda.stream(side):          # warm-up on the capture stream (PyTorch capture recipe)
                 step(st['lr'])
             torch.cuda.current_stream(dev).wait_stream(side)
             g = torch.cuda.CUDAGraph()
             st['host'] = torch.zeros((), dtype=torch.float32).pin_memory()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=side):   # its per-stream scratch (render._ticket) exists from the warm-up
                 st['value'] = step(st['lr'])
                 # the loss read-back is part of the graph: a copy node into pinned host memory
                 st['host'].copy_(st['value'].detach().to(torch.float32), non_blocking=True)
@@ -209,6 +219,13 @@ class GDOptimizer(object):
                 st['graph'].replay()
                 torch.cuda.current_stream(st['lr'].device).synchronize()
                 return float(st['host'])
+            if use_graph:                          # eager steps of a to-be-captured optimiser: on the private stream
+                cur, side = torch.cuda.current_stream(tVars[0].device), side_stream()
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    value = step(step_lr).detach()
+                cur.wait_stream(side)
+                return float(value)
             return float(step(step_lr).detach())
 
         def recapture():

@@ -34,6 +34,9 @@ class RenderConfig:
     use_records: int = 1                # 0: never precompute / TMA-stage the sweep records (A/B, tests)
     shadows: int = 0                    # 1: hard shadows (scene.py:41-45 + shape.py:85-97; include/rrt_b200.h);
                                         # 2: same, scalar pass only in the general kernel (A/B, tests)
+    geom_grad_only: int = 0             # 1: RRT_FLAG_NO_MATERIAL_GRAD -- the reverse pass yields d/d w2o (+ camera) only,
+                                        # material / light / look_at gradients are zero and not computed
+    use_ticket: int = 1                 # 0: never fold the gradient finalisation into the render kernel (A/B, tests)
 
     @property
     def rows(self):
@@ -53,6 +56,26 @@ def _f32(t, name):
 
 RECORDS_MIN_N = 64           # from this many objects the sweep records are built once per render
                              # (rrt_build_records) and TMA-staged, instead of rebuilt in every CTA
+
+_TICKETS = {}
+
+
+def _ticket(device, num_scenes):
+    """Per-(device, stream) scratch for rrt_scene.ticket (uint32 [num_scenes], zero between calls):
+    lets the last CTA of each scene finalise the gradients inside the render kernel.  Calls on one
+    stream are serialised, so they may share it; different streams get different scratch.  While a
+    CUDA graph is being captured nothing is allocated (a memset node would be recorded): a stream
+    without scratch simply takes the separate finalize launch."""
+    stream = torch.cuda.current_stream(device)
+    key = (str(device), stream.cuda_stream)
+    t = _TICKETS.get(key)
+    if t is None or t.numel() < num_scenes:
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        with torch.cuda.device(device):
+            t = _TICKETS[key] = torch.zeros(max(int(num_scenes), 4096), dtype=torch.int32, device=device)
+    return t
+
 
 _BASE_RAYS = {}
 BASE_RAYS_MAX_N = 1024       # table = 12*n*n bytes; above this the kernels evaluate the grid themselves
@@ -110,7 +133,8 @@ class _Tables:
         d.row_begin, d.row_count = cfg.row_begin, cfg.row_count
         d.scene_begin = cfg.scene_begin
         d.flags = ((nat.FLAG_CULL if cfg.cull else 0) | (nat.FLAG_NO_SMALL if cfg.no_small else 0) |
-                   (nat.FLAG_SHADOWS if cfg.shadows else 0) | (nat.FLAG_SCALAR_SHADOWS if cfg.shadows == 2 else 0))
+                   (nat.FLAG_SHADOWS if cfg.shadows else 0) | (nat.FLAG_SCALAR_SHADOWS if cfg.shadows == 2 else 0) |
+                   (nat.FLAG_NO_MATERIAL_GRAD if cfg.geom_grad_only else 0))
         d.max_depth, d.camera_grad, d.seed = cfg.max_depth, cfg.camera_grad, cfg.seed & 0xFFFFFFFFFFFFFFFF
         d.obj_type, d.w2o, d.material = self.obj_type.data_ptr(), self.w2o.data_ptr(), self.material.data_ptr()
         d.light, d.camera = self.light.data_ptr(), self.camera.data_ptr()
@@ -127,6 +151,9 @@ class _Tables:
             self.base = base_rays(cfg.n, self.device)
             d.base_rays = self.base.data_ptr()
         self.desc = d
+        self.ticket = _ticket(self.device, self.B) if cfg.use_ticket else None
+        if self.ticket is not None:
+            d.ticket = self.ticket.data_ptr()
         self.records = None
         if self.N >= RECORDS_MIN_N and cfg.use_records:
             with torch.cuda.device(self.device):
@@ -243,8 +270,12 @@ class StreamedFusedMSE:
             self.e_in = [torch.cuda.Event() for _ in range(K)]
             self.e_k = [torch.cuda.Event() for _ in range(K)]
             self.e_fork, self.e_out = torch.cuda.Event(), torch.cuda.Event()
-        # fused kernel + finalize per slab, + one rrt_build_records per call from RECORDS_MIN_N objects
-        self.launches_per_call = 2 * K + (1 if self.N >= RECORDS_MIN_N and cfg.use_records else 0)
+            # rrt_scene.ticket scratch, one per kernel stream (their kernels overlap)
+            self.tickets = [torch.zeros(16, dtype=torch.int32, device=self.device) for _ in self.s_k] if cfg.use_ticket else None
+            torch.cuda.current_stream(self.device).synchronize()
+        # fused kernel per slab (the gradient finalisation is folded into it through rrt_scene.ticket),
+        # + one rrt_build_records per call from RECORDS_MIN_N objects
+        self.launches_per_call = (1 if cfg.use_ticket else 2) * K + (1 if self.N >= RECORDS_MIN_N and cfg.use_records else 0)
 
     def __call__(self, obj_type, w2o, material, light, camera, target_host, image_host=None, channel_weight=None):
         cfg, dev = self.cfg, self.device
@@ -277,6 +308,7 @@ class StreamedFusedMSE:
             sk = self.s_k[k & 1]
             desc = nat.RrtScene.from_buffer_copy(T.desc)          # same tables, this slab's rows
             desc.row_begin, desc.row_count = cfg.row_begin + r0, rc
+            desc.ticket = self.tickets[k & 1].data_ptr() if self.tickets is not None else None
             sk.wait_event(self.e_in[k])
             with torch.cuda.device(dev):
                 rc_ = L.rrt_render_fused_mse(C.byref(desc), self.dev_target[r0:r0 + rc].data_ptr(), cw,

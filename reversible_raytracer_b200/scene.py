@@ -288,7 +288,16 @@ class Scene(object):
                               max_depth=float(getattr(self.shader, 'maxDepth', 1.0)),
                               camera_grad=1 if cam.has_transform else 0,
                               cull=int(len(self.shapes) >= self.CULL_MIN_OBJECTS if cull is None else bool(cull)),
-                              shadows=int(self.shadows))
+                              shadows=int(self.shadows), geom_grad_only=int(self._geom_grad_only()))
+
+    def _geom_grad_only(self):
+        """True when no gradient can be asked for materials, light or look_at -- they were all given
+        as constants (tuples / NumPy), as in every decoder of the reference (autoencoder.py:57-71,
+        orbit_experiments/test_optimization.py:17-44).  The reverse pass then skips those sums
+        (RRT_FLAG_NO_MATERIAL_GRAD)."""
+        look = self.camera.look_at
+        return (not any(s.material.dynamic for s in self.shapes) and not self.lights[0].dynamic
+                and not self.camera.dynamic_look_at and not look.requires_grad)
 
     # -- rendering ------------------------------------------------------------------
     def _prepare(self, antialias_samples, jitter, seed, cull):

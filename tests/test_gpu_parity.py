@@ -4,12 +4,14 @@ Bars (BASELINE.json north_star): hit/object-index masks BIT-EXACT; pixels within
 rtol 1e-4 (+ atol 1e-5, images live in [0,1]); gradients within 1e-3 of each
 parameter block's max magnitude.
 """
+from dataclasses import replace
+
 import numpy as np
 import pytest
 import torch
 
 from oracle import oracle_c as oc, scenes
-from reversible_raytracer_b200 import render as R
+from reversible_raytracer_b200 import render as R, workloads as W
 import helpers
 from helpers import to_device, block_rel_err
 
@@ -588,3 +590,67 @@ def test_record_table_is_bit_identical(cuda):
         b = R.render_forward(replace(cfg, use_records=0, cull=cull), ot, w2o, mat, light, cam, jit, want_hit=True, want_tmin=True)
         for x, y in zip(a, b):
             assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize('name', ['C1_optimize_brightness', 'C2_test_balls_depth', 'C3_match_mirror_square', 'C4_orbit_view1',
+                                  'C5_stress_diag', 'many_general_chunked'])
+def test_no_material_grad_flag_and_in_kernel_finalize(name, cuda):
+    """RRT_FLAG_NO_MATERIAL_GRAD (geom_grad_only): d/d w2o and d/d camera.o2w as without the flag,
+    material / light / look_at entries exactly zero.  rrt_scene.ticket (last CTA of a scene finalises
+    inside the render kernel, one launch) against the separate finalize launch.  Fused and
+    backward entry points, whichever kernel the fixture selects."""
+    ps = oc.PackedScene.from_spec(CASES[name](), camera_grad=1)
+    cfg, ot, w2o, mat, light, cam, jit = to_device(ps, cuda)
+    img, hit, _ = R.render_forward(cfg, ot, w2o, mat, light, cam, jit)
+    target = (img * 0.5 + 0.1).contiguous()
+    dl = torch.randn_like(img)
+    N = ps.N
+
+    def both(c):
+        out = [R.render_backward(c, ot, w2o, mat, light, cam, dl, h, jit) for h in (hit, None)]
+        if c.samples <= 8 or not c.no_small:
+            out.append(R.render_fused_mse(c, ot, w2o, mat, light, cam, target, None, jit)[1])
+        return out
+    full = both(replace(cfg, use_ticket=0))
+    for variant in (dict(use_ticket=1), dict(use_ticket=1, geom_grad_only=1), dict(use_ticket=0, geom_grad_only=1)):
+        for g, g0 in zip(both(replace(cfg, **variant)), full):
+            gw, gm, gl, gc = R.split_grad(g, N)
+            gw0, gm0, gl0, gc0 = R.split_grad(g0, N)
+            tol = 1e-5
+            assert float((gw - gw0).abs().max()) <= tol * max(float(gw0.abs().max()), 1e-30)
+            assert float((gc[:12] - gc0[:12]).abs().max()) <= tol * max(float(gc0[:12].abs().max()), 1e-30)
+            if variant.get('geom_grad_only'):
+                assert float(gm.abs().max()) == 0.0 and float(gl.abs().max()) == 0.0 and float(gc[12:].abs().max()) == 0.0
+            else:
+                assert float((gm - gm0).abs().max()) <= tol * max(float(gm0.abs().max()), 1e-30)
+                assert float((gl - gl0).abs().max()) <= tol * max(float(gl0.abs().max()), 1e-30)
+    # the scratch is left zero for the next call
+    tk = R._ticket(cuda, 1)
+    assert tk is not None and int(tk.abs().sum()) == 0
+
+
+def test_many_small_scenes_persistent_ctas(cuda):
+    """The small-scene kernel's persistent CTAs walk contiguous ranges of work items that cross
+    scene boundaries (here 3000 scenes of 2 items: every CTA serves several scenes, flushing its
+    sums, reloading the tables and taking a per-scene ticket at each boundary).  Per-scene loss,
+    gradient, image and masks must equal single-scene launches of the same scenes."""
+    B, n = 3000, 8
+    tb = W.orbit_tables(B // 2)
+    rng = np.random.RandomState(5)
+    w2o = tb['w2o'].copy()
+    w2o[:, 0, 3] += rng.uniform(-0.3, 0.3, B).astype(np.float32)          # every scene differs
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    cfg = R.RenderConfig(n=n, samples=4, shader=tb['shader'], transpose=0, seed=11, camera_grad=1)
+    ot, mat, light, cam, w2o_d = t(tb['obj_type']), t(tb['material']), t(tb['light']), t(tb['camera']), t(w2o)
+    target = torch.rand((B, n, n, 3), device=cuda)
+    loss, grad, image, hit = R.render_fused_mse(cfg, ot, w2o_d, mat, light, cam, target, want_image=True, want_hit=True)
+    dl = torch.randn_like(image)
+    gb = R.render_backward(cfg, ot, w2o_d, mat, light, cam, dl, None)
+    for b in (0, 1, 2, 777, 1500, 2998, 2999):
+        c1 = replace(cfg, scene_begin=b)                                   # keys the in-kernel jitter like the batch
+        l1, g1, im1, h1 = R.render_fused_mse(c1, ot, w2o_d[b], mat, light, cam[b], target[b], want_image=True, want_hit=True)
+        assert torch.equal(h1, hit[b]) and torch.equal(im1, image[b])
+        np.testing.assert_allclose(float(l1), float(loss[b]), rtol=1e-6)
+        assert float((g1 - grad[b]).abs().max()) <= 1e-5 * float(g1.abs().max())
+        gb1 = R.render_backward(c1, ot, w2o_d[b], mat, light, cam[b], dl[b], None)
+        assert float((gb1 - gb[b]).abs().max()) <= 1e-5 * float(gb1.abs().max())

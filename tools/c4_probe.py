@@ -1,0 +1,34 @@
+"""C4 orbit batch (256 scenes x 2 views, 64x64, S=4) fused fwd+mse+bwd: us per batch for the
+flag combinations (exploration helper).  RRT_B200_LIB=<other .so> A/Bs kernel builds."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from dataclasses import replace
+from reversible_raytracer_b200 import render as R, workloads as W
+from tools.latency import timeit
+
+dev = torch.device('cuda')
+scenes_ = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+tb, tt = W.orbit_tables(scenes_), W.orbit_tables(scenes_, centre_noise=0.5)
+t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+cfg = R.RenderConfig(n=64, samples=4, shader=tb['shader'], transpose=0, seed=7, camera_grad=0)
+args = (t(tb['obj_type']), t(tb['w2o']), t(tb['material']), t(tb['light']), t(tb['camera']))
+target, _, _ = R.render_forward(cfg, args[0], t(tt['w2o']), *args[2:], None, want_hit=False)
+rays = 2 * scenes_ * 64 * 64 * 4
+for geom in (0, 1):
+    for ticket in (0, 1):
+        c = replace(cfg, geom_grad_only=geom, use_ticket=ticket)
+        fn = lambda: R.render_fused_mse(c, *args, target)
+        us = timeit(fn, warm=10, iters=300)
+        # GPU time alone: the same call replayed from a CUDA graph (no Python / launch overhead)
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            fn()
+        torch.cuda.current_stream().wait_stream(s)
+        with torch.cuda.graph(g, stream=s):
+            fn()
+        ug = timeit(g.replay, warm=10, iters=300)
+        print('lib=%s scenes=%d geom_only=%d ticket=%d: %.1f us eager, %.1f us graph replay  -> %.0f Mrays/s' %
+              (os.path.basename(os.environ.get('RRT_B200_LIB', 'default')), scenes_, geom, ticket, us, ug, rays / ug))

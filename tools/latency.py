@@ -53,12 +53,15 @@ def c3(fused):
     return GDOptimizer().optimize([c1, c2], cost, 0.000008, 0.1), sc
 
 
-def c4(num_scenes=256):
+def c4(num_scenes=256, geom_grad_only=1):
+    """Decoder batch of the orbit autoencoders.  geom_grad_only=1: like every decoder of the reference
+    (materials, light and camera direction are constants there) only d/d w2o is requested."""
     tb = W.orbit_tables(num_scenes)
     tt = W.orbit_tables(num_scenes, centre_noise=0.5)
     dev = torch.device('cuda')
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    cfg = R.RenderConfig(n=64, samples=4, shader=tb['shader'], transpose=0, seed=7, camera_grad=0)
+    cfg = R.RenderConfig(n=64, samples=4, shader=tb['shader'], transpose=0, seed=7, camera_grad=0,
+                         geom_grad_only=geom_grad_only)
     args = (t(tb['obj_type']), t(tb['w2o']), t(tb['material']), t(tb['light']), t(tb['camera']))
     target, _, _ = R.render_forward(cfg, args[0], t(tt['w2o']), *args[2:], None, want_hit=False)
     return lambda: R.render_fused_mse(cfg, *args, target), 2 * num_scenes * 64 * 64 * 4
