@@ -99,6 +99,16 @@ extern "C" {
  * (autoencoder.py:57-71, orbit_experiments/autoencoder_2ly.py:82-91: materials, light and camera
  * direction are constants there). */
 #define RRT_FLAG_NO_MATERIAL_GRAD 16
+/* Nearest-hit sweep without the conservative pre-filter.  By default, when a prebuilt record table
+ * is given (rrt_scene.obj_records), the hot loop of the sweep evaluates for every (ray, sphere)
+ * pair a float32 QUADRATIC FORM in (u, v) = (d_x/d_z, d_y/d_z) whose sign conservatively bounds the
+ * sign of the reference's discriminant det = pd^2 - vn*(o'.o' - 1) (shape.py:78-83): 5 fused
+ * multiply-adds per pair instead of 11 operations.  A pair it cannot exclude (every true hit, plus a
+ * shell of relative width 2^-18 around silhouettes) is then decided by the CANONICAL arithmetic, so
+ * hit masks, tmin and everything downstream are bit-identical with and without the filter (tested).
+ * Every (ray, object) pair is still tested individually -- this is not spatial culling.  This flag
+ * forces the canonical packed sweep for all pairs (A/B measurements, roofline accounting). */
+#define RRT_FLAG_CANONICAL_SWEEP 32
 
 #define RRT_OK 0
 #define RRT_ERR_INVALID (-1)   /* bad argument (message in rrt_last_error)            */
@@ -154,13 +164,16 @@ typedef struct rrt_scene {
     int32_t scene_begin;
     int32_t flags;        /* RRT_FLAG_* */
 
-    /* Optional [B][N][RRT_RECORD_FLOATS] float32 table of sweep records (the per-object
-     * constants of the ray-object test: A's diagonal, o' = A.c + b, 1 - o'.o', the
-     * off-diagonals), as filled by rrt_build_records() for THIS scene's current w2o / camera
-     * tables; 16-byte aligned.  With it the render kernels stage the object table in shared
-     * memory by one TMA bulk copy (cp.async.bulk + mbarrier) per 512-object chunk instead of
-     * rebuilding the records in every CTA.  NULL => the kernels build the records themselves.
-     * Same bits either way.  Must be rebuilt whenever w2o or the camera changes.               */
+    /* Optional float32 table of RRT_RECORD_TABLE_FLOATS(B, N) floats, 16-byte aligned, as filled
+     * by rrt_build_records() for THIS scene's current w2o / camera tables: first
+     * [B][N][RRT_RECORD_FLOATS] sweep records (the per-object constants of the ray-object test:
+     * A's diagonal, o' = A.c + b, 1 - o'.o', the off-diagonals), then [B][Npad][RRT_QUADRIC_FLOATS]
+     * pre-filter rows (see RRT_FLAG_CANONICAL_SWEEP; Npad = N rounded up to a multiple of 4).
+     * With it the render kernels stage the object table in shared memory by one TMA bulk copy
+     * (cp.async.bulk + mbarrier) per 512-object chunk instead of rebuilding the records in
+     * every CTA, and sphere-only chunks are swept with the pre-filter.  NULL => the kernels
+     * build the records themselves.  Same bits either way.  Must be rebuilt whenever w2o or the
+     * camera changes.                                                                          */
     const float* obj_records;
 
     /* Optional scratch, uint32 [num_scenes] in device memory: ZERO before its first use, left zero
@@ -173,6 +186,9 @@ typedef struct rrt_scene {
 } rrt_scene;
 
 #define RRT_RECORD_FLOATS 16
+#define RRT_QUADRIC_FLOATS 6
+#define RRT_RECORD_TABLE_FLOATS(num_scenes, num_objects) \
+    ((size_t)(num_scenes) * ((size_t)(num_objects) * RRT_RECORD_FLOATS + (((size_t)(num_objects) + 3) / 4 * 4) * RRT_QUADRIC_FLOATS))
 
 int rrt_version(void);
 const char* rrt_last_error(void);
@@ -215,8 +231,11 @@ int rrt_render_fused_mse(const rrt_scene* scene, const float* target,
                          double* loss, float* grad, void* stream);
 
 /*
- * Fills rrt_scene.obj_records: records [B][N][RRT_RECORD_FLOATS] from scene->w2o, obj_type and
- * the camera translation (o' = A.c + b, transform.py:44; cc = o'.o' - 1, shape.py:79,82).
+ * Fills rrt_scene.obj_records (RRT_RECORD_TABLE_FLOATS(B, N) floats) from scene->w2o, obj_type and
+ * the camera translation (o' = A.c + b, transform.py:44; cc = o'.o' - 1, shape.py:79,82), and the
+ * pre-filter rows derived from them in float64 (Q = A^T (o' o'^T - cc I) A, inflated by 2^-18 of
+ * its scale; objects outside the range in which that bound is proven -- non-finite entries,
+ * |A|_F or |o'| beyond 2^+-16 -- and squares get an always-pass row).
  * One tiny kernel; call it before the render entry points whenever the tables changed.
  */
 int rrt_build_records(const rrt_scene* scene, float* records, void* stream);

@@ -28,6 +28,11 @@ def grad_size(num_objects):
     return num_objects * OBJ_GRAD_STRIDE + GLOBAL_GRAD
 
 
+def record_table_floats(num_scenes, num_objects):
+    """RRT_RECORD_TABLE_FLOATS: sweep records [B][N][16] + pre-filter rows [B][N padded to 4][6]."""
+    return num_scenes * (num_objects * 16 + (num_objects + 3) // 4 * 4 * 6)
+
+
 class RrtScene(C.Structure):
     """`struct rrt_scene` of include/rrt_b200.h."""
     _fields_ = [
@@ -139,7 +144,7 @@ EXPORTS = ['rrt_version', 'rrt_last_error', 'rrt_render_forward', 'rrt_render_ba
            'rrt_peer_allreduce', 'rrt_peer_buffer_bytes', 'rrt_peer_signal_bytes', 'rrt_build_records',
            'rrt_small_step_mse']
 
-FLAG_CULL, FLAG_NO_SMALL, FLAG_SHADOWS, FLAG_SCALAR_SHADOWS, FLAG_NO_MATERIAL_GRAD = 1, 2, 4, 8, 16
+FLAG_CULL, FLAG_NO_SMALL, FLAG_SHADOWS, FLAG_SCALAR_SHADOWS, FLAG_NO_MATERIAL_GRAD, FLAG_CANONICAL_SWEEP = 1, 2, 4, 8, 16, 32
 HIT_SHADOWED = 0x40000000
 CHAIN_TRANSLATE, CHAIN_SCALE, CHAIN_ROTATE, CHAIN_INVERT, CHAIN_MAX_OPS = 1, 2, 3, 0x100, 8
 

@@ -146,6 +146,8 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
         // reverse-pass loops below; only the packed world directions stay in registers.
         __align__(16) float l_rc[3 * kRays], l_dw[3 * kRays], l_tmin[kRays];  // SoA: [x0..x7 | y0..y7 | z0..z7]
         int l_idx[kRays];
+        __align__(16) float l_uv[2 * kRays];          // (u, v) = (d_x/d_z, d_y/d_z) of the pre-filter: [u0..u7 | v0..v7]
+        bool rays_safe = true;                        // every ray inside the range the pre-filter's bound is proven for
         RayPack rp;
         // rolled on purpose (code size: this runs once per thread; instruction-cache misses
         // dominate small-scene workloads otherwise)
@@ -184,6 +186,18 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                     wz = dot3_canon(g.C[6], g.C[7], g.C[8], rcx, rcy, rcz);
                 }
             }
+            {
+                // padding rays get NaN (never a candidate); a real ray must have |d_z| within 2^+-10
+                // and |u|, |v| <= 2^10, else the whole CTA takes the canonical sweep
+                float u = __int_as_float(0x7fc00000), v = u;
+                if (ok) {
+                    u = __fdiv_rn(wx, wz);
+                    v = __fdiv_rn(wy, wz);
+                    const float az = fabsf(wz);
+                    rays_safe &= (az >= 9.765625e-4f) && (az <= 1024.0f) && (fabsf(u) <= 1024.0f) && (fabsf(v) <= 1024.0f);
+                }
+                l_uv[r] = u; l_uv[kRays + r] = v;
+            }
             l_rc[r] = rcx; l_rc[kRays + r] = rcy; l_rc[2 * kRays + r] = rcz;
             l_dw[r] = wx; l_dw[kRays + r] = wy; l_dw[2 * kRays + r] = wz;
             l_tmin[r] = __int_as_float(0x7f800000);
@@ -197,6 +211,19 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
 
         const bool use_stored = (MODE == MODE_BWD) && (P.hit_in != nullptr);
         const bool cull = (sc.flags & RRT_FLAG_CULL) && !use_stored;
+        // conservative pre-filter sweep (default with a prebuilt table): CTA-wide decision, because the
+        // shared-memory chunk then holds pre-filter rows instead of records
+        bool use_q = false;
+        RayQ rq;
+        if (sc.obj_records && !cull && !use_stored && !(sc.flags & RRT_FLAG_CANONICAL_SWEEP)) {
+            use_q = __syncthreads_and(rays_safe);
+            if (use_q) {
+                const u64* up = reinterpret_cast<const u64*>(l_uv);
+#pragma unroll
+                for (int p = 0; p < kRays / 2; p++) { rq.u[p] = up[p]; rq.v[p] = up[kRays / 2 + p]; }
+            }
+        }
+        bool staged_quadrics = false;                 // the staged chunk does not hold records (shadow pass restages)
         if (cull) {   // ---- bounding cone of this CTA's rays (exact min/max of the rays built above)
             const float big = 3.0e38f;
             float lo3[3] = {big, big, big}, hi3[3] = {-big, -big, -big};
@@ -272,7 +299,19 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                 const int cnt = min(kObjChunk, N - kb);
                 if (kb > 0 || trip > 0) __syncthreads();  // previous chunk fully consumed
                 bool staged_by_tma = false;
-                if (N > kObjChunk || trip == 0) {
+                const float* rec_g = sc.obj_records ? sc.obj_records + ((size_t)scene * N + kb) * RRT_RECORD_FLOATS : nullptr;
+                // chunk class from the prebuilt table: sphere-only chunks take the pre-filter
+                const bool qchunk = use_q && !(__float_as_int(__ldg(rec_g + 15)) & 1);
+                const int cnt_pad = (cnt + 3) & ~3;
+                if (qchunk) {
+                    const int npad = (N + 3) & ~3;
+                    stage_bytes_tma(smem_tab, sc.obj_records + (size_t)sc.num_scenes * N * RRT_RECORD_FLOATS +
+                                                  ((size_t)scene * npad + kb) * RRT_QUADRIC_FLOATS,
+                                    (unsigned)cnt_pad * 24u, &tma_bar, &tma_phase, tid);
+                    staged_by_tma = true;
+                    staged_quadrics = true;
+                } else if (N > kObjChunk || trip == 0 || staged_quadrics) {
+                    staged_quadrics = false;
                     if (sc.obj_records) {                  // precomputed records: one TMA bulk copy
                         stage_records_tma(smem_tab, sc.obj_records + ((size_t)scene * N + kb) * RRT_RECORD_FLOATS, cnt,
                                           &tma_bar, &tma_phase, &chunk_class, tid);
@@ -291,7 +330,9 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                 __syncthreads();
                 if (staged_by_tma && tid == 0) tma_phase ^= 1u;   // read again only after the next CTA-wide barrier
                 const int cls = chunk_class;
-                if (cull) {
+                if (qchunk) {
+                    sweep_quadric(smem_tab, cnt_pad, cnt, reinterpret_cast<const float4*>(rec_g), kb, rq, l_dw, l_tmin, l_idx);
+                } else if (cull) {
                     // one ballot word per 32 objects keeps list order without a compaction pass
                     for (int k0 = warp * 32; k0 < cnt; k0 += 32 * nwarps) {
                         const int k = k0 + lane;
@@ -322,7 +363,7 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
 #pragma unroll 1
             for (int kb = 0; kb < N; kb += kObjChunk) {
                 const int cnt = min(kObjChunk, N - kb);
-                if (N > kObjChunk) {                       // otherwise the whole table is still staged
+                if (N > kObjChunk || staged_quadrics) {    // otherwise the whole table is still staged
                     __syncthreads();
                     if (sc.obj_records) {
                         stage_records_tma(smem_tab, sc.obj_records + ((size_t)scene * N + kb) * RRT_RECORD_FLOATS, cnt,

@@ -140,12 +140,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, unsigned phase) {
 // Out of line on purpose, like rare_group: keeps the render kernel's register allocation
 // around the hot loop exactly as it is without the record table.  The barrier's phase lives in
 // shared memory (flipped by thread 0 after the CTA-wide barrier that follows every staging).
-__device__ __noinline__ void stage_records_tma(float4* smem_tab, const float* src, int cnt, unsigned long long* bar,
-                                               const unsigned* phase_s, int* chunk_class, int tid) {
+__device__ __noinline__ void stage_bytes_tma(float4* smem_tab, const float* src, unsigned bytes, unsigned long long* bar,
+                                             const unsigned* phase_s, int tid) {
     const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(bar);
     const unsigned phase = *phase_s;
-    if (tid == 0) tma_bulk_load((uint32_t)__cvta_generic_to_shared(smem_tab), src, (unsigned)cnt * 64u, mbar);
+    if (tid == 0) tma_bulk_load((uint32_t)__cvta_generic_to_shared(smem_tab), src, bytes, mbar);
     mbar_wait(mbar, phase);
+}
+__device__ __forceinline__ void stage_records_tma(float4* smem_tab, const float* src, int cnt, unsigned long long* bar,
+                                                  const unsigned* phase_s, int* chunk_class, int tid) {
+    stage_bytes_tma(smem_tab, src, (unsigned)cnt * 64u, bar, phase_s, tid);
     // rrt_build_records left the chunk's class bits in the spare slot of its first record
     if (tid == 0 && chunk_class) *chunk_class |= __float_as_int(smem_tab[3].w);
 }
@@ -209,4 +213,72 @@ __device__ __forceinline__ void sweep_mixed(const float4* __restrict__ tab, int 
         if (!(flags & 1)) gmax = object_max_det<true>((uint32_t)__cvta_generic_to_shared(tab + 4 * k), rp, 0.0f);
         if (gmax > 0.0f) rare_group(tab, k, 1, kbase, dw, tmin, idx);
     }
+}
+
+// ---------------------------------------------------------------- conservative pre-filter sweep
+// The default hot loop when a prebuilt table is available (RRT_FLAG_CANONICAL_SWEEP switches it
+// off).  Per (ray, sphere) pair ONE float32 quadratic form in (u, v) = (d_x/d_z, d_y/d_z), in
+// Horner form
+//     F = ((c00 u + c02) u + c22) + v ((c01 u + c12) + c11 v)          5 fused multiply-adds,
+// i.e. 20 FFMA2 per object for the thread's 8 rays with only u and v (16 registers) held per
+// thread -- whose sign conservatively bounds the sign of the canonical discriminant (quadric_row
+// in rrt_aux_kernels.cuh has the error budget).  Groups of kQGroup objects are branch-free (6
+// floats = 1.5 LDS.128 per object, coefficients as scalar-broadcast .F32 operands in all three
+// operand positions, 4 FMNMX3 per object, one vote per group); a group with any F > 0 goes to
+// rare_group, which evaluates the CANONICAL arithmetic from the full records (read from the
+// global table: the shared-memory chunk holds only the 24-byte pre-filter rows) and alone
+// decides hits.  So results are bit-identical to the canonical sweep.
+#ifndef RRT_QGROUP
+#define RRT_QGROUP 4
+#endif
+constexpr int kQGroup = RRT_QGROUP;      // objects per branch; the table is padded to a multiple of it... of 4 (see below)
+static_assert(kQGroup == 4 || kQGroup == 8, "pre-filter rows are padded to multiples of 4 objects; groups of 4 or 8");
+
+struct RayQ {
+    u64 u[kRays / 2], v[kRays / 2];
+};
+
+// row = (c00, c02, c22, c01, c12, c11)
+__device__ __forceinline__ float quad_obj_max(const float* g, const RayQ& rq, float gmax) {
+#pragma unroll
+    for (int p = 0; p < kRays / 2; p++) {
+        u64 t1 = fma2(bc(g[0]), rq.u[p], bc(g[1]));
+        u64 t2 = fma2(bc(g[3]), rq.u[p], bc(g[4]));
+        t1 = fma2(t1, rq.u[p], bc(g[2]));
+        t2 = fma2(bc(g[5]), rq.v[p], t2);
+        const u64 f = fma2(t2, rq.v[p], t1);
+        float lo, hi;
+        upk(f, lo, hi);
+        gmax = fmaxf(gmax, fmaxf(lo, hi));        // NaN (padding rays) is dropped: never a candidate
+    }
+    return gmax;
+}
+
+// `quad`: staged pre-filter rows of `count_pad` objects (a multiple of 4; padding rows never pass);
+// `rec_g`: the same chunk's full records in the global table; `count`: real objects in the chunk.
+__device__ __forceinline__ void sweep_quadric(const float4* __restrict__ quad, int count_pad, int count,
+                                              const float4* __restrict__ rec_g, int kbase, const RayQ& rq,
+                                              const float* dw, float* tmin, int* idx) {
+    uint32_t q0 = (uint32_t)__cvta_generic_to_shared(quad);
+    const int full = count_pad - count_pad % kQGroup;
+    uint32_t q_end = q0 + 24u * (uint32_t)full;
+    asm volatile("mov.u32 %0, %0;" : "+r"(q0));
+    asm volatile("mov.u32 %0, %0;" : "+r"(q_end));
+#pragma unroll 1
+    for (uint32_t q = q0; q != q_end; q += 24 * kQGroup) {
+        float g[6 * kQGroup];
+#pragma unroll
+        for (int i = 0; i < 6 * kQGroup / 4; i++) {
+            const float4 x = lds128(q + 16 * i);
+            g[4 * i] = x.x; g[4 * i + 1] = x.y; g[4 * i + 2] = x.z; g[4 * i + 3] = x.w;
+        }
+        float gmax = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kQGroup; j++) gmax = quad_obj_max(g + 6 * j, rq, gmax);
+        if (__builtin_expect(__any_sync(0xffffffffu, gmax > 0.0f), 0)) {
+            const int k = (int)((q - q0) / 24u);
+            rare_group(rec_g, k, min(kQGroup, count - k), kbase, dw, tmin, idx);
+        }
+    }
+    if (full < count) rare_group(rec_g, full, count - full, kbase, dw, tmin, idx);   // kQGroup == 8: a last half group
 }

@@ -37,6 +37,8 @@ class RenderConfig:
     geom_grad_only: int = 0             # 1: RRT_FLAG_NO_MATERIAL_GRAD -- the reverse pass yields d/d w2o (+ camera) only,
                                         # material / light / look_at gradients are zero and not computed
     use_ticket: int = 1                 # 0: never fold the gradient finalisation into the render kernel (A/B, tests)
+    canonical_sweep: int = 0            # 1: RRT_FLAG_CANONICAL_SWEEP -- no conservative pre-filter in the sweep (same bits,
+                                        # every pair evaluated with the reference's arithmetic; A/B, roofline accounting)
 
     @property
     def rows(self):
@@ -134,7 +136,8 @@ class _Tables:
         d.scene_begin = cfg.scene_begin
         d.flags = ((nat.FLAG_CULL if cfg.cull else 0) | (nat.FLAG_NO_SMALL if cfg.no_small else 0) |
                    (nat.FLAG_SHADOWS if cfg.shadows else 0) | (nat.FLAG_SCALAR_SHADOWS if cfg.shadows == 2 else 0) |
-                   (nat.FLAG_NO_MATERIAL_GRAD if cfg.geom_grad_only else 0))
+                   (nat.FLAG_NO_MATERIAL_GRAD if cfg.geom_grad_only else 0) |
+                   (nat.FLAG_CANONICAL_SWEEP if cfg.canonical_sweep else 0))
         d.max_depth, d.camera_grad, d.seed = cfg.max_depth, cfg.camera_grad, cfg.seed & 0xFFFFFFFFFFFFFFFF
         d.obj_type, d.w2o, d.material = self.obj_type.data_ptr(), self.w2o.data_ptr(), self.material.data_ptr()
         d.light, d.camera = self.light.data_ptr(), self.camera.data_ptr()
@@ -157,7 +160,7 @@ class _Tables:
         self.records = None
         if self.N >= RECORDS_MIN_N and cfg.use_records:
             with torch.cuda.device(self.device):
-                self.records = torch.empty((self.B, self.N, 16), dtype=torch.float32, device=self.device)
+                self.records = torch.empty(nat.record_table_floats(self.B, self.N), dtype=torch.float32, device=self.device)
                 rc = nat.lib().rrt_build_records(C.byref(d), self.records.data_ptr(), self.stream())
             nat.check(rc, 'rrt_build_records')
             d.obj_records = self.records.data_ptr()

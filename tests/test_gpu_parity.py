@@ -654,3 +654,82 @@ def test_many_small_scenes_persistent_ctas(cuda):
         assert float((g1 - grad[b]).abs().max()) <= 1e-5 * float(g1.abs().max())
         gb1 = R.render_backward(c1, ot, w2o_d[b], mat, light, cam[b], dl[b], None)
         assert float((gb1 - gb[b]).abs().max()) <= 1e-5 * float(gb1.abs().max())
+
+
+def _prefilter_equal(ps, cuda, with_fused=True):
+    """pre-filter sweep (default with a record table) vs RRT_FLAG_CANONICAL_SWEEP: every output bit."""
+    cfg, ot, w2o, mat, light, cam, jit = to_device(ps, cuda)
+    cfg = replace(cfg, no_small=1, use_records=1)
+    a = R.render_forward(replace(cfg, canonical_sweep=0), ot, w2o, mat, light, cam, jit, want_hit=True, want_tmin=True)
+    b = R.render_forward(replace(cfg, canonical_sweep=1), ot, w2o, mat, light, cam, jit, want_hit=True, want_tmin=True)
+    assert torch.equal(a[1], b[1]), 'hit masks differ'
+    assert torch.equal(a[2].view(torch.int32), b[2].view(torch.int32)), 'tmin differs'
+    assert torch.equal(a[0].view(torch.int32), b[0].view(torch.int32)), 'image differs'
+    return a
+
+
+@pytest.mark.parametrize('seed', range(12))
+def test_prefilter_sweep_is_bit_identical_random(seed, cuda):
+    """Random scenes over a wide range of scales, distances, rotations and anisotropy (>= 64 objects so
+    that the record table + pre-filter are active), spheres behind the camera, camera inside a sphere,
+    a rotated / translated camera (orbit variant)."""
+    from oracle import oracle_numpy as on
+    rng = np.random.RandomState(1000 + seed)
+    N = int(rng.choice([64, 100, 257, 600]))
+    shapes = []
+    for k in range(N):
+        z = rng.uniform(-4, 30)
+        c = (rng.uniform(-0.6, 0.6) * abs(z) - 0.1, rng.uniform(-0.6, 0.6) * abs(z) + 0.1, z)
+        t = on.translate(c)
+        if rng.rand() < 0.5:
+            ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+            t = on.compose(t, on.rotate(rng.uniform(0, 360), ax))
+        sc = 10.0 ** rng.uniform(-2.5, 1.2, 3) if rng.rand() < 0.5 else np.full(3, 10.0 ** rng.uniform(-2.5, 1.2))
+        t = on.compose(t, on.scale(sc))
+        shapes.append((on.SPHERE, t, scenes._mat(rng.uniform(0.1, 1, 3), 0.3, 0.7, 0.4, 50.)))
+    cam = None
+    if seed % 3 == 1:
+        cam = on.compose(on.translate(rng.uniform(-1, 1, 3)), on.rotate(rng.uniform(-40, 40), (0, 1, 0)))
+    spec = scenes.spec_from(40, 4, shapes, ((-1., -1., 2.), (0.961, 1., 0.87)), 'phong', cam=cam, seed=seed)
+    ps = oc.PackedScene.from_spec(spec, camera_grad=0)
+    img, hit, tmin = _prefilter_equal(ps, cuda)
+    img_o, hit_o, tmin_o = oc.render_forward(ps)
+    assert np.array_equal(hit.cpu().numpy().reshape(hit_o.shape), hit_o)
+    assert np.array_equal(tmin.cpu().numpy().reshape(tmin_o.shape).view(np.int32), tmin_o.view(np.int32))
+
+
+def test_prefilter_sweep_out_of_range_inputs(cuda):
+    """Objects and rays outside the range the pre-filter's bound is proven for must fall back to the
+    canonical arithmetic: huge / tiny / zero / NaN / inf matrices (always-pass rows), a camera whose
+    rays have d_z <= 0 or |d_x/d_z| > 2^10 (CTA-wide canonical sweep), squares mixed in."""
+    from oracle import oracle_numpy as on
+    base = scenes.stress(n=48, num_objects=80)
+    w = base['w2o'].copy()                                   # [N, 4, 4]
+    w[3, :3] *= 3.0e7; w[4, :3] *= 1.0e-7; w[5, :3, :3] = 0.0; w[6, 0, 0] = np.nan; w[7, 1, 3] = np.inf; w[8, :3, 3] *= 1.0e8
+    w[9, :3] *= 2.0e5; w[10, :3] *= 5.0e-6
+    base['w2o'] = w
+    base['obj_type'] = base['obj_type'].copy()
+    base['obj_type'][70:] = on.SQUARE                        # chunk with squares: canonical mixed sweep
+    for cam in (None, on.rotate(89.99, (0, 1, 0)), on.rotate(180, (0, 1, 0)), on.compose(on.translate((0, 0, 12)), on.rotate(90, (1, 0, 0)))):
+        spec = dict(base)
+        spec['cam_o2w'] = None if cam is None else np.asarray(cam[0], dtype=np.float32)
+        ps = oc.PackedScene.from_spec(spec, camera_grad=0)
+        _, hit, tmin = _prefilter_equal(ps, cuda)
+        _, hit_o, tmin_o = oc.render_forward(ps)
+        assert np.array_equal(hit.cpu().numpy().reshape(hit_o.shape), hit_o)
+        assert np.array_equal(tmin.cpu().numpy().reshape(tmin_o.shape).view(np.int32), tmin_o.view(np.int32))
+
+
+@pytest.mark.parametrize('general', [False, True])
+def test_prefilter_sweep_full_size_slab(general, cuda):
+    """BASELINE config 5 at full resolution (4096 x 4096, 1024 spheres; C5 and C5g), a 96-row slab in the
+    middle of the image: pre-filter and canonical sweeps agree on every bit of hit_index, tmin, image."""
+    tb = W.stress_tables(1024, general=general)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    args = (t(tb['obj_type']), t(tb['w2o']), t(tb['material']), t(tb['light']), t(tb['camera']))
+    cfg = R.RenderConfig(n=4096, samples=4, shader=tb['shader'], transpose=1, seed=4321, row_begin=2000, row_count=96)
+    a = R.render_forward(cfg, *args, None, want_hit=True, want_tmin=True)
+    b = R.render_forward(replace(cfg, canonical_sweep=1), *args, None, want_hit=True, want_tmin=True)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2].view(torch.int32), b[2].view(torch.int32))
+    assert torch.equal(a[0].view(torch.int32), b[0].view(torch.int32))
+    assert int((a[1] >= 0).sum()) > 100000

@@ -1,4 +1,6 @@
-"""C5 fused step time with a realistic (perturbed) target, like bench.py; A/B of the record table."""
+"""C5 / C5g fused step time with a realistic (perturbed) target, like bench.py: pre-filter sweep (default)
+against the canonical sweep (RRT_FLAG_CANONICAL_SWEEP), and a bitwise comparison of their outputs.
+RRT_B200_LIB=<other .so> A/Bs kernel builds.  usage: c5_time.py [n] [general]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -6,13 +8,23 @@ from dataclasses import replace
 from reversible_raytracer_b200 import render as R, workloads as W, _native as nat
 from tools.latency import timeit
 dev = torch.device('cuda')
-tb = W.stress_tables(1024); tt = W.stress_tables(1024, centre_noise=0.05)
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+general = len(sys.argv) > 2 and sys.argv[2] == 'general'
+tb = W.stress_tables(1024, general=general); tt = W.stress_tables(1024, general=general, centre_noise=0.05)
 t = lambda a: torch.from_numpy(a).to(dev)
 args = (t(tb['obj_type']), t(tb['w2o']), t(tb['material']), t(tb['light']), t(tb['camera']))
-cfg = R.RenderConfig(n=4096, samples=4, shader=nat.SHADER_PHONG, transpose=1, seed=4321)
+cfg = R.RenderConfig(n=n, samples=4, shader=nat.SHADER_PHONG, transpose=1, seed=4321)
 target = R.render_forward(cfg, args[0], t(tt['w2o']), *args[2:], None, want_hit=False)[0]
-for rep in range(2):
-    for rec in (1, 0):
-        c = replace(cfg, use_records=rec)
-        ms = timeit(lambda: R.render_fused_mse(c, *args, target, want_image=True), warm=2, iters=8) / 1e3
-        print('use_records=%d C5 fused ms: %.3f' % (rec, ms))
+lib = os.path.basename(os.environ.get('RRT_B200_LIB', 'default'))
+outs = {}
+for canon in (0, 1):
+    c = replace(cfg, canonical_sweep=canon)
+    outs[canon] = R.render_fused_mse(c, *args, target, want_image=True, want_hit=True)
+    ms = timeit(lambda: R.render_fused_mse(c, *args, target, want_image=True), warm=2, iters=8) / 1e3
+    mf = timeit(lambda: R.render_forward(c, *args, None, want_hit=False), warm=2, iters=8) / 1e3
+    print('lib=%s %s n=%d canonical_sweep=%d: fused %.3f ms (%.0f Mrays/s), forward %.3f ms' %
+          (lib, 'C5g' if general else 'C5', n, canon, ms, n * n * 4 / ms / 1e3, mf))
+a, b = outs[0], outs[1]
+print('pre-filter == canonical: hit %s, image %s, loss rel diff %.2e, grad rel diff %.2e' %
+      (torch.equal(a[3], b[3]), torch.equal(a[2], b[2]), abs(float(a[0]) - float(b[0])) / abs(float(b[0])),
+       float((a[1] - b[1]).abs().max() / b[1].abs().max())))
