@@ -32,29 +32,23 @@ class Encoder(torch.nn.Module):
         return torch.cat([c[..., :2], torch.relu(c[..., 2:])], dim=-1)
 
 
-def main(num_scenes=256, steps=30, lr=2e-8, n=64, seed=1234, verbose=True):
-    """Single GPU, or `torchrun --nproc-per-node G examples/orbit_autoencoder.py`: the scene
-    batch is sharded across ranks (sharding.scene_range), every rank renders and
-    back-propagates its own scenes, and ONE flat allreduce sums the encoder-weight
-    gradients (SURVEY.md 8e, C4)."""
+def make_trainer(num_scenes=256, lr=2e-8, n=64, seed=1234, dev=None, world=1, rank=0):
+    """-> (step, info): `step()` runs ONE training step of the batched orbit autoencoder on this
+    rank's scene range -- encoder forward (stock PyTorch), decoder = ONE fused render + squared
+    error + reverse-pass launch (only d/d w2o is requested: materials, light and camera are
+    constants, autoencoder_2ly.py:82-91), encoder backward, ONE flat NCCL allreduce of the
+    encoder-weight gradients + loss when world > 1, SGD update -- and returns
+    the loss tensor (global sum).  `info` has the sizes."""
     import torch.distributed as dist
     from reversible_raytracer_b200 import sharding
-    world, rank = int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1 and not dist.is_initialized():
-        dist.init_process_group('nccl', device_id=dev)
     tb = W.orbit_tables(num_scenes, seed=seed)
     first, count = sharding.scene_range(num_scenes, world, rank)          # this rank's scenes (x2 views)
     for key in ('w2o', 'camera'):
         tb[key] = tb[key][2 * first:2 * (first + count)]
-    num_scenes = count
-    verbose = verbose and rank == 0
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    cfg = R.RenderConfig(n=n, samples=4, shader=tb['shader'], transpose=0, seed=11, scene_begin=2 * first)
+    cfg = R.RenderConfig(n=n, samples=4, shader=tb['shader'], transpose=0, seed=11, scene_begin=2 * first, geom_grad_only=1)
     obj_type, material, light, camera = t(tb['obj_type']), t(tb['material']), t(tb['light']), t(tb['camera'])
-    B = 2 * num_scenes
+    B = 2 * count
     # data: the scenes rendered at their true centres (planet_orbit.py), as uint8 like the dataset
     X, _, _ = R.render_forward(cfg, obj_type, t(tb['w2o']), material, light, camera, None, want_hit=False)
     X = (X * 255).to(torch.uint8).float() / 255.0                                        # [B,n,n,3]
@@ -63,25 +57,48 @@ def main(num_scenes=256, steps=30, lr=2e-8, n=64, seed=1234, verbose=True):
     opt = torch.optim.SGD(enc.parameters(), lr=lr)
     fixed = torch.tensor([0., 0., 48.], device=dev).expand(B, 3)
     scales = torch.tensor([[4., 4., 4.], [6., 6., 6.]], device=dev).expand(B, 2, 3)
-    losses = []
-    for step in range(steps):
+    params = list(enc.parameters())
+    nparam = sum(p.numel() for p in params)
+    flat = torch.empty(nparam + 1, dtype=torch.float32, device=dev)
+
+    def step():
         centres = enc(X.reshape(B, -1))                                                  # [B,3] (one per view)
         w2o = R.w2o_translate_scale(torch.stack([centres, fixed], dim=1), scales)        # [B,2,12]
         loss = R.render_fused_mse_loss(cfg, obj_type, w2o, material, light, camera, X).sum()
         opt.zero_grad(set_to_none=True)
         loss.backward()
         if world > 1:                                        # one flat allreduce: [grads..., loss]
-            flat = torch.cat([p.grad.reshape(-1) for p in enc.parameters()] + [loss.detach().reshape(1)])
+            torch.cat([p.grad.reshape(-1) for p in params] + [loss.detach().reshape(1)], out=flat)
             dist.all_reduce(flat)
             off = 0
-            for p in enc.parameters():
+            for p in params:
                 p.grad.copy_(flat[off:off + p.numel()].reshape(p.shape))
                 off += p.numel()
             loss = flat[-1]
         opt.step()
-        losses.append(float(loss.detach()))
-        if verbose:
-            print('step %d cost %.3f' % (step, losses[-1]))
+        return loss.detach()
+    return step, dict(scenes_per_rank=count, views_per_rank=B, encoder_parameters=nparam,
+                      allreduce_bytes=(nparam + 1) * 4 if world > 1 else 0, rays_per_rank=B * n * n * 4)
+
+
+def main(num_scenes=256, steps=30, lr=2e-8, n=64, seed=1234, verbose=True):
+    """Single GPU, or `torchrun --nproc-per-node G examples/orbit_autoencoder.py`: the scene
+    batch is sharded across ranks (sharding.scene_range), every rank renders and
+    back-propagates its own scenes, and ONE flat allreduce sums the encoder-weight
+    gradients (SURVEY.md 8e, C4)."""
+    import torch.distributed as dist
+    world, rank = int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group('nccl', device_id=dev)
+    step, _ = make_trainer(num_scenes, lr, n, seed, dev, world, rank)
+    losses = []
+    for k in range(steps):
+        losses.append(float(step()))
+        if verbose and rank == 0:
+            print('step %d cost %.3f' % (k, losses[-1]))
     return losses
 
 

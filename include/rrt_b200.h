@@ -109,6 +109,14 @@ extern "C" {
  * Every (ray, object) pair is still tested individually -- this is not spatial culling.  This flag
  * forces the canonical packed sweep for all pairs (A/B measurements, roofline accounting). */
 #define RRT_FLAG_CANONICAL_SWEEP 32
+/* Deterministic reverse pass: gradients and loss are bit-identical from run to run (the reference's
+ * T.grad is, optimize.py:25; float atomics are not).  Everything up to a warp's per-object sums is
+ * evaluated in a fixed order anyway (thread: ray order; warp: fixed butterfly); with this flag the
+ * combination ACROSS warps and CTAs -- normally float atomics in shared and global memory -- is
+ * done in 128-bit fixed point (two int64 limbs per value, 2^-20 and 2^-60 units, integer atomics:
+ * integer addition is associative, so the result does not depend on the order of arrival).
+ * Range +-2^43, absolute resolution 2^-60 per contribution.  Needs rrt_scene.det_workspace. */
+#define RRT_FLAG_DETERMINISTIC 64
 
 #define RRT_OK 0
 #define RRT_ERR_INVALID (-1)   /* bad argument (message in rrt_last_error)            */
@@ -183,7 +191,13 @@ typedef struct rrt_scene {
      * camera and light chains) inside the render kernel instead of a second launch.  Calls that
      * may run concurrently (different streams) need different scratch.  NULL => separate launch. */
     uint32_t* ticket;
+
+    /* RRT_FLAG_DETERMINISTIC only: int64 [B][RRT_GRAD_SIZE(N) + 1][2] (RRT_DET_WORKSPACE_BYTES),
+     * 16-byte aligned device scratch, zeroed by the callee. */
+    int64_t* det_workspace;
 } rrt_scene;
+
+#define RRT_DET_WORKSPACE_BYTES(num_scenes, num_objects) ((size_t)(num_scenes) * (RRT_GRAD_SIZE(num_objects) + 1) * 16)
 
 #define RRT_RECORD_FLOATS 16
 #define RRT_QUADRIC_FLOATS 6

@@ -29,7 +29,7 @@ class RrtScene(C.Structure):
         ('light_scene_stride', C.c_int64), ('camera_scene_stride', C.c_int64),
         ('jitter_scene_stride', C.c_int64), ('base_rays', C.c_void_p),
         ('scene_begin', C.c_int32), ('flags', C.c_int32), ('obj_records', C.c_void_p),
-        ('ticket', C.c_void_p),
+        ('ticket', C.c_void_p), ('det_workspace', C.c_void_p),
     ]
 
 

@@ -99,7 +99,7 @@ __global__ void primary_rays_kernel(int n, double step, float* __restrict__ out)
 // One CTA per scene (the separate-launch form; with rrt_scene.ticket the render kernels call
 // finalize_scene themselves from the last CTA of each scene).
 __global__ void __launch_bounds__(128) finalize_grads(const __grid_constant__ KParams P) {
-    __shared__ float camg[12];
+    __shared__ float camg[48];
     finalize_scene(P, blockIdx.x, threadIdx.x, blockDim.x, camg);
 }
 

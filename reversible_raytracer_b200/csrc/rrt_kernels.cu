@@ -126,6 +126,8 @@ int check_scene(const rrt_scene* sc, int* rows_out) {
     if (((uintptr_t)sc->w2o & 15) || (sc->w2o_scene_stride & 3)) return fail(RRT_ERR_INVALID, "w2o must be 16-byte aligned");
     if (sc->shader == RRT_SHADER_DEPTH && !(sc->max_depth != 0.0f)) return fail(RRT_ERR_INVALID, "max_depth must be non-zero");
     if ((uintptr_t)sc->obj_records & 15) return fail(RRT_ERR_INVALID, "obj_records must be 16-byte aligned");
+    if ((sc->flags & RRT_FLAG_DETERMINISTIC) && (!sc->det_workspace || ((uintptr_t)sc->det_workspace & 15)))
+        return fail(RRT_ERR_INVALID, "RRT_FLAG_DETERMINISTIC needs a 16-byte aligned det_workspace");
     *rows_out = rows;
     return RRT_OK;
 }
@@ -211,6 +213,7 @@ int launch(KParams& P, cudaStream_t st, bool* finalized = nullptr) {
     kern<<<grid, block, smem, st>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "render kernel launch: %s", cudaGetErrorString(e));
+    if (finalized) *finalized = (MODE != MODE_FWD) && sc.ticket != nullptr;
     return RRT_OK;
 }
 
@@ -254,6 +257,8 @@ int rrt_render_backward(const rrt_scene* scene, const float* dl_dimage, const in
     P.grad = grad;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(grad, 0, sizeof(float) * RRT_GRAD_SIZE(scene->num_objects) * scene->num_scenes, st);
+    if (e == cudaSuccess && (scene->flags & RRT_FLAG_DETERMINISTIC))
+        e = cudaMemsetAsync(scene->det_workspace, 0, RRT_DET_WORKSPACE_BYTES(scene->num_scenes, scene->num_objects), st);
     if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "memset grad: %s", cudaGetErrorString(e));
     bool finalized = false;
     rc = launch<MODE_BWD>(P, st, &finalized);
@@ -280,6 +285,8 @@ int rrt_render_fused_mse(const rrt_scene* scene, const float* target, const floa
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(grad, 0, sizeof(float) * RRT_GRAD_SIZE(scene->num_objects) * scene->num_scenes, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(loss, 0, sizeof(double) * scene->num_scenes, st);
+    if (e == cudaSuccess && (scene->flags & RRT_FLAG_DETERMINISTIC))
+        e = cudaMemsetAsync(scene->det_workspace, 0, RRT_DET_WORKSPACE_BYTES(scene->num_scenes, scene->num_objects), st);
     if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "memset grad/loss: %s", cudaGetErrorString(e));
     bool finalized = false;
     rc = launch<MODE_FUSED>(P, st, &finalized);
@@ -350,6 +357,7 @@ int rrt_small_step_mse(const rrt_scene* scene, const rrt_step* step, const float
         return fail(RRT_ERR_INVALID, "rrt_step: bad parameter range");
     P.sc = *scene;
     if (scene->num_scenes != 1 || scene->num_objects < 1) return fail(RRT_ERR_UNSUPPORTED, "whole-step kernel: one scene, >= 1 shape");
+    if (scene->flags & RRT_FLAG_DETERMINISTIC) return fail(RRT_ERR_UNSUPPORTED, "whole-step kernel: RRT_FLAG_DETERMINISTIC is not supported");
     P.step = *step;
     P.target = target;
     P.cw[0] = channel_weight ? channel_weight[0] : 1.f;

@@ -9,6 +9,25 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// ---------------------------------------------------------------- RRT_FLAG_DETERMINISTIC
+// 128-bit fixed point: value = hi * 2^-20 + lo * 2^-60, two int64 limbs combined with integer
+// atomics (associative => the sum does not depend on the order in which warps / CTAs arrive).
+// The split is exact for |x| < 2^43 down to 2^-60; smaller bits are rounded once, per contribution.
+__device__ __forceinline__ void det_add(long long* limbs, double x) {
+    const long long hi = __double2ll_rn(x * 1048576.0);                              // 2^20
+    const double r = x - (double)hi * 9.5367431640625e-07;                          // exact
+    const long long lo = __double2ll_rn(r * 1152921504606846976.0);                 // 2^60
+    atomicAdd(reinterpret_cast<unsigned long long*>(limbs), (unsigned long long)hi);
+    atomicAdd(reinterpret_cast<unsigned long long*>(limbs) + 1, (unsigned long long)lo);
+}
+__device__ __forceinline__ double det_value(const long long* limbs) {
+    const long long hi = __ldcg(limbs), lo = __ldcg(limbs + 1);
+    return (double)hi * 9.5367431640625e-07 + (double)lo * 8.673617379884035e-19;    // 2^-20, 2^-60
+}
+__device__ __forceinline__ long long* det_scene(const rrt_scene& sc, int scene) {
+    return reinterpret_cast<long long*>(sc.det_workspace) + (size_t)scene * (RRT_GRAD_SIZE(sc.num_objects) + 1) * 2;
+}
+
 // find-or-insert a CTA slot for object `key` (called by one lane); -1 = table full
 __device__ __forceinline__ int slot_for(int* slot_key, int key) {
     int h = key & (kSlots - 1);
@@ -66,17 +85,23 @@ __device__ __forceinline__ float warp_reduce19(const float (&a)[19], bool mine, 
 
 // All 32 lanes call this together.  Each lane holds (key, acc[19]); lanes with the
 // same key are summed (transposed butterfly) and 19 lanes add one sum each to the CTA slot.
-__device__ __forceinline__ void warp_flush(int key, float (&acc)[19], int* slot_key, float* slots, float* gobj, int lane) {
+__device__ __forceinline__ void warp_flush(int key, float (&acc)[19], int* slot_key, float* slots, float* gobj, int lane,
+                                           long long* det_ws = nullptr) {
     unsigned active = __ballot_sync(0xffffffffu, key >= 0);
     while (active) {
         int leader = __ffs(active) - 1;
         int k = __shfl_sync(0xffffffffu, key, leader);
         bool mine = (key == k);
         active &= ~__ballot_sync(0xffffffffu, mine);
+        int v;
+        if (det_ws) {                 // deterministic: the warp's sums go straight to the fixed-point workspace
+            const float x = warp_reduce19(acc, mine, lane, v);
+            if (v >= 0 && x != 0.f) det_add(det_ws + ((size_t)k * RRT_OBJ_GRAD_STRIDE + v) * 2, (double)x);
+            continue;
+        }
         int slot = 0;
         if (lane == 0) slot = slot_for(slot_key, k);
         slot = __shfl_sync(0xffffffffu, slot, 0);
-        int v;
         const float x = warp_reduce19(acc, mine, lane, v);
         if (v >= 0 && x != 0.f) {
             if (slot >= 0) atomicAdd(&slots[slot * kSlotStride + v], x);
@@ -92,7 +117,7 @@ __device__ __forceinline__ void warp_flush(int key, float (&acc)[19], int* slot_
 // camera and light chains (see backward_ray).  Called by all `nthreads` threads of ONE CTA after
 // every contribution to the scene has landed (separate launch, or last CTA + __threadfence);
 // reads through L2 (__ldcg) because the sums were produced by other CTAs' atomics.
-__device__ __forceinline__ void finalize_scene(const KParams& P, int scene, int tid, int nthreads, float* camg /* shared [12] */) {
+__device__ __forceinline__ void finalize_scene(const KParams& P, int scene, int tid, int nthreads, float* camg /* shared [48] */) {
     const rrt_scene& sc = P.sc;
     const int N = sc.num_objects;
     float* gobj = P.grad + (size_t)scene * RRT_GRAD_SIZE(N);
@@ -100,8 +125,16 @@ __device__ __forceinline__ void finalize_scene(const KParams& P, int scene, int 
     const float* cam = sc.camera + (size_t)scene * sc.camera_scene_stride;
     const float* w2o = sc.w2o + (size_t)scene * sc.w2o_scene_stride;
     const bool geom_only = (sc.flags & RRT_FLAG_NO_MATERIAL_GRAD) != 0;
-    if (tid < 12) camg[tid] = 0.f;
-    __syncthreads();
+    if ((sc.flags & RRT_FLAG_DETERMINISTIC) && sc.det_workspace) {
+        // fixed-point sums -> the raw float sums the rest of this routine expects (and the loss)
+        const long long* ws = det_scene(sc, scene);
+        const int G = (int)RRT_GRAD_SIZE(N);
+        for (int i = tid; i < G; i += nthreads) gobj[i] = (float)det_value(ws + 2 * (size_t)i);
+        if (tid == 0 && P.loss) P.loss[scene] = det_value(ws + 2 * (size_t)G);
+        __threadfence();
+        __syncthreads();
+    }
+    __syncthreads();                 // (callers reuse camg)
     float C[9], ct[3];
 #pragma unroll
     for (int r = 0; r < 3; r++) {
@@ -147,15 +180,22 @@ __device__ __forceinline__ void finalize_scene(const KParams& P, int scene, int 
             }
         }
     }
+    // camera sums: warp butterfly, then the (<= 4) warps' partials in warp order -- a fixed order, so the
+    // finalisation never adds run-to-run noise (RRT_FLAG_DETERMINISTIC relies on it)
     if (sc.camera_grad) {
 #pragma unroll
         for (int q = 0; q < 12; q++) {
-            float x = warp_sum(cg[q]);
-            if ((tid & 31) == 0 && x != 0.f) atomicAdd(&camg[q], x);
+            const float x = warp_sum(cg[q]);
+            if ((tid & 31) == 0) camg[(tid >> 5) * 12 + q] = x;
         }
     }
     __syncthreads();
-    if (tid < 12) gglobal[6 + tid] = camg[tid];
+    if (tid < 12) {
+        float x = 0.f;
+        if (sc.camera_grad)
+            for (int w = 0; w < (nthreads + 31) / 32; w++) x += camg[w * 12 + tid];
+        gglobal[6 + tid] = x;
+    }
     if (tid == 0) {
         if (geom_only) {
 #pragma unroll

@@ -23,6 +23,8 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
     __shared__ int chunk_class;  // sticky per CTA: bit0 squares, bit1 general spheres seen
     __shared__ __align__(8) unsigned long long tma_bar;   // mbarrier of the record-table bulk copies
     __shared__ unsigned tma_phase;
+    __shared__ float camg_s[48];
+    __shared__ int last_s;
 
     const rrt_scene& sc = P.sc;
     // S is a compile-time constant except in the generic (PIX=1, SPT=8) instantiation, so the
@@ -74,6 +76,20 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
     const float* w2o = sc.w2o + (size_t)scene * sc.w2o_scene_stride;
     const float* mats = sc.material + (size_t)scene * sc.material_scene_stride;
     float* gobj = (MODE != MODE_FWD) ? P.grad + (size_t)scene * RRT_GRAD_SIZE(N) : nullptr;
+    long long* const det_ws = (MODE != MODE_FWD && (sc.flags & RRT_FLAG_DETERMINISTIC)) ? det_scene(sc, scene) : nullptr;
+    // the last CTA of a scene (rrt_scene.ticket) finalises its gradients: one launch per reverse pass
+    auto take_ticket = [&]() {
+        if (MODE == MODE_FWD || !sc.ticket) return;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) last_s = (atomicAdd(sc.ticket + scene, 1u) == gridDim.x * gridDim.y - 1);
+        __syncthreads();
+        if (last_s) {
+            __threadfence();
+            finalize_scene(P, scene, tid, blockDim.x, camg_s);
+            if (tid == 0) sc.ticket[scene] = 0u;
+        }
+    };
 
     float pixsum[PIX][3];
 #pragma unroll
@@ -100,7 +116,7 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
         bool nz = false;
 #pragma unroll
         for (int px = 0; px < PIX; px++) nz |= (gpix[px][0] != 0.f) | (gpix[px][1] != 0.f) | (gpix[px][2] != 0.f);
-        if (!__syncthreads_or(nz)) return;
+        if (!__syncthreads_or(nz)) { take_ticket(); return; }
     }
 
     // base rays (float64 grid -> float32), one per owned pixel
@@ -546,7 +562,7 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                 // flush the running per-object accumulator when some lane changes object
                 const bool change = fin ? (acc_key >= 0) : ((k >= 0) && (acc_key >= 0) && (k != acc_key));
                 if (__any_sync(0xffffffffu, change)) {
-                    warp_flush(acc_key, acc, slot_key, slots, gobj, lane);
+                    warp_flush(acc_key, acc, slot_key, slots, gobj, lane, det_ws);
                     acc_key = -1;
                 }
                 if (k >= 0) {
@@ -565,6 +581,21 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
 
     if (MODE != MODE_FWD) {
         // ---- warp -> CTA -> global reduction (per-object sums were flushed by the sentinel trip)
+        if (det_ws) {
+            // deterministic: every warp adds its (fixed-order) sums to the fixed-point workspace
+#pragma unroll
+            for (int v = 0; v < 9; v++) {
+                const float x = warp_sum(gg[v]);
+                const int dst = v < 6 ? v : 12 + v;
+                if (lane == 0 && x != 0.f) det_add(det_ws + ((size_t)N * RRT_OBJ_GRAD_STRIDE + dst) * 2, (double)x);
+            }
+            if (MODE == MODE_FUSED) {
+                const float x = warp_sum(loss_part);
+                if (lane == 0 && x != 0.f) det_add(det_ws + (size_t)RRT_GRAD_SIZE(N) * 2, (double)x);
+            }
+            take_ticket();
+            return;
+        }
 #pragma unroll
         for (int v = 0; v < 9; v++) {
             float x = warp_sum(gg[v]);
@@ -592,5 +623,6 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
             for (int w = 0; w < nwarps; w++) t += (double)loss_warp[w];
             if (t != 0.0) atomicAdd(&P.loss[scene], t);
         }
+        take_ticket();
     }
 }

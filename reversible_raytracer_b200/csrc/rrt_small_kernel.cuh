@@ -32,7 +32,7 @@ constexpr long long kSmallDefaultMaxRays = 16 << 20;  // total rays of a call (a
 // conflict-free) instead of registers: they are touched only by the few rays that hit something,
 // and 12..19 registers held across the whole item loop cost a fifth of the resident warps.
 template <int NACC>
-__device__ __forceinline__ void small_warp_flush(int key, float* acc_col, float* slots, int lane) {
+__device__ __forceinline__ void small_warp_flush(int key, float* acc_col, float* slots, int lane, long long* det_ws = nullptr) {
     const unsigned full = 0xffffffffu;
     float acc[NACC];
 #pragma unroll
@@ -45,7 +45,10 @@ __device__ __forceinline__ void small_warp_flush(int key, float* acc_col, float*
         todo &= ~__ballot_sync(full, mine);
         int v;
         const float x = warp_reduce_n<NACC>(acc, mine, lane, v);
-        if (v >= 0 && x != 0.f) atomicAdd(&slots[k * kSlotStride + v], x);
+        if (v >= 0 && x != 0.f) {
+            if (det_ws) det_add(det_ws + ((size_t)k * RRT_OBJ_GRAD_STRIDE + v) * 2, (double)x);   // RRT_FLAG_DETERMINISTIC
+            else atomicAdd(&slots[k * kSlotStride + v], x);
+        }
     }
 }
 
@@ -58,7 +61,7 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
     __shared__ float slots[kSmallMaxN * kSlotStride];
     __shared__ float gglob[9];
     __shared__ float loss_warp[kSmallThreads / 32];
-    __shared__ float camg_s[12];
+    __shared__ float camg_s[48];
     __shared__ int flag_s;
     __shared__ float acc_s[NACC * kSmallThreads];                 // per-thread running sums, [value][thread]
     __shared__ float gg_s[(GEOM ? 1 : 9) * kSmallThreads];        // light / look_at sums, [value][thread]
@@ -95,26 +98,34 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
     int cur_scene = -1;
     unsigned scene_items = 0;                          // items of cur_scene processed by this CTA
     float* gobj = nullptr;
+    long long* det_ws = nullptr;                       // RRT_FLAG_DETERMINISTIC: fixed-point sums of cur_scene
 
     // ---- end of a scene's items on this CTA: thread -> warp -> CTA -> global, ticket, finalisation
     auto flush_scene = [&](bool reduced) {
         if (MODE != MODE_FWD && reduced) {
-            if (__any_sync(full, acc_key >= 0)) small_warp_flush<NACC>(acc_key, acc_col, slots, lane);
+            if (__any_sync(full, acc_key >= 0)) small_warp_flush<NACC>(acc_key, acc_col, slots, lane, det_ws);
             acc_key = -1;
             if (!GEOM) {
 #pragma unroll
                 for (int v = 0; v < 9; v++) {
                     const float x = warp_sum(gg_col[v * kSmallThreads]);
-                    if (lane == 0 && x != 0.f) atomicAdd(&gglob[v], x);
+                    if (lane == 0 && x != 0.f) {
+                        if (det_ws) det_add(det_ws + ((size_t)N * RRT_OBJ_GRAD_STRIDE + (v < 6 ? v : 12 + v)) * 2, (double)x);
+                        else atomicAdd(&gglob[v], x);
+                    }
                     gg_col[v * kSmallThreads] = 0.f;
                 }
             }
             if (MODE == MODE_FUSED) {
                 const float x = warp_sum(loss_part);
-                if (lane == 0) loss_warp[warp] = x;
+                if (lane == 0) {
+                    loss_warp[warp] = x;
+                    if (det_ws && x != 0.f) det_add(det_ws + (size_t)RRT_GRAD_SIZE(N) * 2, (double)x);
+                }
                 loss_part = 0.f;
             }
             __syncthreads();
+            if (!det_ws) {
             for (int q = tid; q < N * NACC; q += kSmallThreads) {
                 const int k = q / NACC, v = q - k * NACC;
                 const float x = slots[k * kSlotStride + v];
@@ -129,6 +140,7 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
                 double t = 0.0;
                 for (int w = 0; w < kSmallThreads / 32; w++) t += (double)loss_warp[w];
                 if (t != 0.0) atomicAdd(&P.loss[cur_scene], t);
+            }
             }
         }
         if (MODE != MODE_FWD && !STEP && sc.ticket) {
@@ -185,6 +197,7 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
             cur_scene = scene;
             scene_items = 0;
             gobj = (MODE != MODE_FWD) ? P.grad + (size_t)scene * RRT_GRAD_SIZE(N) : nullptr;
+            det_ws = (MODE != MODE_FWD && !STEP && (sc.flags & RRT_FLAG_DETERMINISTIC)) ? det_scene(sc, scene) : nullptr;
             {
                 const size_t so = (size_t)scene * P.rows * n * 3;
                 tgt_s = (MODE == MODE_FUSED) ? P.target + so : nullptr;
@@ -378,7 +391,7 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
             if (gc[0] == 0.f && gc[1] == 0.f && gc[2] == 0.f) key = -1;
             const bool change = (key >= 0) && (acc_key >= 0) && (key != acc_key);
             if (__any_sync(full, change)) {                  // some lane's winner changed: flush the warp's sums
-                small_warp_flush<NACC>(acc_key, acc_col, slots, lane);
+                small_warp_flush<NACC>(acc_key, acc_col, slots, lane, det_ws);
                 acc_key = -1;
             }
             if (key >= 0) {

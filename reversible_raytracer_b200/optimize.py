@@ -58,7 +58,7 @@ class _WholeStep(object):
             raise ValueError('the optimised variables must be exactly the parameters of the shape transforms')
         cfg = scene.config(spec['antialias_samples'], cull=False)
         N, S = len(scene.shapes), cfg.samples
-        if N < 1 or N > 32 or S > 32 or (S & (S - 1)) or cfg.shadows or cfg.n * cfg.n * S > (16 << 20):
+        if N < 1 or N > 32 or S > 32 or (S & (S - 1)) or cfg.shadows or cfg.deterministic or cfg.n * cfg.n * S > (16 << 20):
             raise ValueError('not a small scene')
         if any(p.dtype != torch.float32 or p.device != dev for p in prog.param_tensors):
             raise ValueError('parameters must be float32 tensors on the scene device')

@@ -37,6 +37,8 @@ class RenderConfig:
     geom_grad_only: int = 0             # 1: RRT_FLAG_NO_MATERIAL_GRAD -- the reverse pass yields d/d w2o (+ camera) only,
                                         # material / light / look_at gradients are zero and not computed
     use_ticket: int = 1                 # 0: never fold the gradient finalisation into the render kernel (A/B, tests)
+    deterministic: int = 0              # 1: RRT_FLAG_DETERMINISTIC -- gradients and loss bit-identical from run to run
+                                        # (fixed-point accumulation across warps / CTAs instead of float atomics)
     canonical_sweep: int = 0            # 1: RRT_FLAG_CANONICAL_SWEEP -- no conservative pre-filter in the sweep (same bits,
                                         # every pair evaluated with the reference's arithmetic; A/B, roofline accounting)
 
@@ -137,7 +139,8 @@ class _Tables:
         d.flags = ((nat.FLAG_CULL if cfg.cull else 0) | (nat.FLAG_NO_SMALL if cfg.no_small else 0) |
                    (nat.FLAG_SHADOWS if cfg.shadows else 0) | (nat.FLAG_SCALAR_SHADOWS if cfg.shadows == 2 else 0) |
                    (nat.FLAG_NO_MATERIAL_GRAD if cfg.geom_grad_only else 0) |
-                   (nat.FLAG_CANONICAL_SWEEP if cfg.canonical_sweep else 0))
+                   (nat.FLAG_CANONICAL_SWEEP if cfg.canonical_sweep else 0) |
+                   (nat.FLAG_DETERMINISTIC if cfg.deterministic else 0))
         d.max_depth, d.camera_grad, d.seed = cfg.max_depth, cfg.camera_grad, cfg.seed & 0xFFFFFFFFFFFFFFFF
         d.obj_type, d.w2o, d.material = self.obj_type.data_ptr(), self.w2o.data_ptr(), self.material.data_ptr()
         d.light, d.camera = self.light.data_ptr(), self.camera.data_ptr()
@@ -153,6 +156,11 @@ class _Tables:
         if cfg.n <= BASE_RAYS_MAX_N:
             self.base = base_rays(cfg.n, self.device)
             d.base_rays = self.base.data_ptr()
+        self.det_ws = None
+        if cfg.deterministic:
+            with torch.cuda.device(self.device):
+                self.det_ws = torch.empty((self.B, nat.grad_size(self.N) + 1, 2), dtype=torch.int64, device=self.device)
+            d.det_workspace = self.det_ws.data_ptr()
         self.desc = d
         self.ticket = _ticket(self.device, self.B) if cfg.use_ticket else None
         if self.ticket is not None:
@@ -275,6 +283,9 @@ class StreamedFusedMSE:
             self.e_fork, self.e_out = torch.cuda.Event(), torch.cuda.Event()
             # rrt_scene.ticket scratch, one per kernel stream (their kernels overlap)
             self.tickets = [torch.zeros(16, dtype=torch.int32, device=self.device) for _ in self.s_k] if cfg.use_ticket else None
+            # RRT_FLAG_DETERMINISTIC: one fixed-point workspace per kernel stream, too
+            self.det_ws = [torch.empty((nat.grad_size(self.N) + 1, 2), dtype=torch.int64, device=self.device)
+                           for _ in self.s_k] if cfg.deterministic else None
             torch.cuda.current_stream(self.device).synchronize()
         # fused kernel per slab (the gradient finalisation is folded into it through rrt_scene.ticket),
         # + one rrt_build_records per call from RECORDS_MIN_N objects
@@ -312,6 +323,8 @@ class StreamedFusedMSE:
             desc = nat.RrtScene.from_buffer_copy(T.desc)          # same tables, this slab's rows
             desc.row_begin, desc.row_count = cfg.row_begin + r0, rc
             desc.ticket = self.tickets[k & 1].data_ptr() if self.tickets is not None else None
+            if self.det_ws is not None:
+                desc.det_workspace = self.det_ws[k & 1].data_ptr()
             sk.wait_event(self.e_in[k])
             with torch.cuda.device(dev):
                 rc_ = L.rrt_render_fused_mse(C.byref(desc), self.dev_target[r0:r0 + rc].data_ptr(), cw,

@@ -139,11 +139,14 @@ class Camera(object):
 class Scene(object):
     """scene.py:11-52"""
 
-    def __init__(self, shapes, lights, camera, shader, shadows=False):
+    def __init__(self, shapes, lights, camera, shader, shadows=False, deterministic=False):
         """`shadows=True` switches on the hard-shadow pass the reference has commented out
         (scene.py:41-45, Sphere.shadow shape.py:85-97; semantics in include/rrt_b200.h) --
-        an extension, off by default like in the reference."""
+        an extension, off by default like in the reference.  `deterministic=True` makes gradients
+        and losses bit-identical from run to run, like the reference's T.grad (optimize.py:25):
+        RRT_FLAG_DETERMINISTIC, fixed-point accumulation instead of float atomics."""
         self.shadows = bool(shadows)
+        self.deterministic = bool(deterministic)
         self.shapes = shapes
         self.lights = lights
         self.camera = camera
@@ -288,7 +291,8 @@ class Scene(object):
                               max_depth=float(getattr(self.shader, 'maxDepth', 1.0)),
                               camera_grad=1 if cam.has_transform else 0,
                               cull=int(len(self.shapes) >= self.CULL_MIN_OBJECTS if cull is None else bool(cull)),
-                              shadows=int(self.shadows), geom_grad_only=int(self._geom_grad_only()))
+                              shadows=int(self.shadows), geom_grad_only=int(self._geom_grad_only()),
+                              deterministic=int(self.deterministic))
 
     def _geom_grad_only(self):
         """True when no gradient can be asked for materials, light or look_at -- they were all given

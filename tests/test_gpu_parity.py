@@ -733,3 +733,63 @@ def test_prefilter_sweep_full_size_slab(general, cuda):
     assert torch.equal(a[1], b[1]) and torch.equal(a[2].view(torch.int32), b[2].view(torch.int32))
     assert torch.equal(a[0].view(torch.int32), b[0].view(torch.int32))
     assert int((a[1] >= 0).sum()) > 100000
+
+
+@pytest.mark.parametrize('name', ['C3_match_mirror_square', 'C4_orbit_view0', 'C5_stress_diag', 'C5g_stress_general',
+                                  'many_mixed_chunked'])
+def test_deterministic_mode_is_bitwise_reproducible(name, cuda):
+    """RRT_FLAG_DETERMINISTIC: loss and gradients are bit-identical from run to run (the reference's
+    T.grad is, optimize.py:25; float atomics are not) and agree with the default mode to float32
+    rounding.  Fused and backward entry points, with and without the in-kernel finalisation."""
+    ps = oc.PackedScene.from_spec(CASES[name](), camera_grad=1)
+    cfg, ot, w2o, mat, light, cam, jit = to_device(ps, cuda)
+    img, hit, _ = R.render_forward(cfg, ot, w2o, mat, light, cam, jit)
+    target = (img * 0.5 + 0.1).contiguous()
+    dl = torch.randn_like(img)
+    fused_ok = cfg.samples <= 8 or not cfg.no_small
+    for ticket in (1, 0):
+        c = replace(cfg, deterministic=1, use_ticket=ticket)
+        runs = []
+        for rep in range(4):
+            g_b = R.render_backward(c, ot, w2o, mat, light, cam, dl, None, jit)
+            l_f, g_f = R.render_fused_mse(c, ot, w2o, mat, light, cam, target, None, jit)[:2] if fused_ok else (g_b[:1], g_b)
+            runs.append((g_b.clone(), l_f.clone(), g_f.clone()))
+        for r in runs[1:]:
+            assert torch.equal(r[0], runs[0][0]) and torch.equal(r[1], runs[0][1]) and torch.equal(r[2], runs[0][2])
+        g0 = R.render_backward(replace(cfg, use_ticket=ticket), ot, w2o, mat, light, cam, dl, None, jit)
+        assert float((runs[0][0] - g0).abs().max()) <= 2e-5 * float(g0.abs().max())
+        if fused_ok:
+            l0, gf0 = R.render_fused_mse(replace(cfg, use_ticket=ticket), ot, w2o, mat, light, cam, target, None, jit)[:2]
+            np.testing.assert_allclose(float(runs[0][1]), float(l0), rtol=1e-6)
+            assert float((runs[0][2] - gf0).abs().max()) <= 2e-5 * float(gf0.abs().max())
+
+
+def test_deterministic_mode_batch_and_streamed(cuda):
+    """Deterministic mode on a scene batch (persistent small-scene CTAs crossing scene boundaries) and
+    through StreamedFusedMSE (two kernel streams, one workspace each)."""
+    B, n = 600, 16
+    tb = W.orbit_tables(B // 2)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    cfg = R.RenderConfig(n=n, samples=4, shader=tb['shader'], transpose=0, seed=3, camera_grad=1, deterministic=1)
+    args = (t(tb['obj_type']), t(tb['w2o']), t(tb['material']), t(tb['light']), t(tb['camera']))
+    target = torch.rand((B, n, n, 3), device=cuda)
+    a = R.render_fused_mse(cfg, *args, target)
+    for _ in range(3):
+        b = R.render_fused_mse(cfg, *args, target)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    ref = R.render_fused_mse(replace(cfg, deterministic=0), *args, target)
+    np.testing.assert_allclose(a[0].cpu().numpy(), ref[0].cpu().numpy(), rtol=1e-6)
+    assert float((a[1] - ref[1]).abs().max()) <= 2e-5 * float(ref[1].abs().max())
+    # streamed, 100 objects (record table + pre-filter), deterministic
+    ps = oc.PackedScene.from_spec(scenes.stress(n=96, num_objects=100, samples=4, seed=11), camera_grad=0)
+    c0, ot, w2o, mat, light, cam, _ = to_device(ps, cuda, with_jitter=False)
+    c = R.RenderConfig(n=c0.n, samples=4, shader=c0.shader, transpose=c0.transpose, seed=5, deterministic=1)
+    tgt = torch.rand((c.n, c.n, 3), device=cuda)
+    pin_t, pin_i = tgt.cpu().pin_memory(), torch.empty((c.n, c.n, 3)).pin_memory()
+    st = R.StreamedFusedMSE(c, w2o.shape[0], cuda, slabs=4)
+    outs = []
+    for _ in range(3):
+        l, g = st(ot, w2o, mat, light, cam, pin_t, pin_i)
+        torch.cuda.synchronize()
+        outs.append((l.clone(), g.clone()))
+    assert all(torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) for o in outs[1:])

@@ -67,6 +67,41 @@ def c4(num_scenes=256, geom_grad_only=1):
     return lambda: R.render_fused_mse(cfg, *args, target), 2 * num_scenes * 64 * 64 * 4
 
 
+def c4_hits(num_scenes=256):
+    """winning rays of the C4 decoder batch (for the credited flops)"""
+    tb = W.orbit_tables(num_scenes)
+    dev = torch.device('cuda')
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    cfg = R.RenderConfig(n=64, samples=4, shader=tb['shader'], transpose=0, seed=7)
+    _, hit, _ = R.render_forward(cfg, t(tb['obj_type']), t(tb['w2o']), t(tb['material']), t(tb['light']), t(tb['camera']), None)
+    return float((hit >= 0).sum())
+
+
+def c4_closure():
+    """One orbit scene pair through the drop-in API in the REFERENCE'S closure style
+    (orbit_experiments/test_optimization.py:17-44: everything rebuilt inside the cost function on
+    every call) + GDOptimizer.  -> (train, captured) ; captured() tells whether the step became a
+    CUDA graph."""
+    dev = torch.device('cuda')
+    target = torch.rand((2, 64, 64, 3), device=dev)
+    c = torch.tensor([3.0, -8.0, 32.0], device=dev)
+
+    def scene(obj_param, cam_y, seed):
+        material1 = Material((0.0, 0.9, 0.0), 0.3, 0.7, 0.5, 50.)
+        material2 = Material((0.9, 0.0, 0.0), 0.3, 0.9, 0.4, 50.)
+        center2 = np.asarray([0, 0, 48], dtype='float32')
+        shapes = [Sphere(translate(obj_param) * scale((4, 4, 4)), material1),
+                  Sphere(translate(center2) * scale((6, 6, 6)), material2)]
+        light = Light((-0., -0., 1), (1., 1., 1.))
+        camera = Camera(64, 64, translate((0, cam_y, 0)), np.asarray([0, 0, 1], dtype='float32'))
+        return Scene(shapes, [light], camera, PhongShader(specular=False))
+
+    def cost():
+        return scene(c, 2.5, 5).build_mse(target[0], seed=5) + scene(c, -2.5, 6).build_mse(target[1], seed=6)
+    train = GDOptimizer().optimize([c], cost, lr=1e-5)
+    return train, (lambda: train.state['graph'] is not None)
+
+
 if __name__ == '__main__':
     train, sc = c1()
     print('C1 optimize_brightness step: %.1f us' % timeit(train))
