@@ -15,7 +15,13 @@ Only DATA is copied (rendered images the reference ships), never sources.
                        first frame of match_mirror.py (root camera variant,
                        Phong with specular, 2 spheres + 1 square). JPEG-lossy.
   balls_15.npy         /root/reference/15.jpg decoded (32x32 uint8): the
-                       test_balls.py training target (test_balls.py:17).
+                       test_balls.py training target (test_balls.py:17) -- sample 15 of
+                       generate_data.py's depth dataset: two unit spheres, DepthMapShader(6.1),
+                       written by util.draw -> scipy.misc.imsave (rescaled to 0..255 by its max).
+  example_png.npy      /root/reference/example.png decoded (32x32 uint8): the test_1ball.py
+                       training target (test_1ball.py:17), one unit sphere, same pipeline, lossless.
+  orbit_samples_all.npz  arr_0[0:99] (all remaining samples of the orbit dataset; centres unknown,
+                       circle constraint) for the full-dataset fit test.
 """
 import os
 import numpy as np
@@ -32,4 +38,7 @@ np.save(os.path.join(HERE, 'match_mirror_frame0.npy'),
         np.asarray(Image.open(os.path.join(REF, 'output/0.jpg'))))
 np.save(os.path.join(HERE, 'balls_15.npy'),
         np.asarray(Image.open(os.path.join(REF, '15.jpg'))))
+np.save(os.path.join(HERE, 'example_png.npy'),
+        np.asarray(Image.open(os.path.join(REF, 'example.png'))))
+np.savez_compressed(os.path.join(HERE, 'orbit_samples_all.npz'), views=d[0:99])
 print('ok')

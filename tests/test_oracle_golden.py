@@ -303,3 +303,70 @@ def test_shadows_gradient_closed_form_equals_autograd():
     assert np.array_equal(hit_f[0], hit_flagged)
     grad_b = oc.render_backward(ps, (2 * (image_f[0] - target)).astype(np.float32), hit_f)
     assert np.max(np.abs(grad_f - grad_b)) <= 1e-9 * np.max(np.abs(grad_b))
+
+
+# ---- DepthMapShader pinned to the reference's own depth renders (shader.py:14-20)
+def _depth_spec(centres, seed=0):
+    m1 = scenes._mat((0.2, 0.9, 0.4), 0.3, 0.7, 0.5, 50.)
+    shapes = [(on.SPHERE, on.translate(c), m1) for c in centres]
+    return scenes.spec_from(32, 4, shapes, ((-1., -1., 2.), (0.961, 1., 0.87)), 'depth', max_depth=6.1, seed=seed)
+
+
+def _fit_depth_artefact(tgt_u8, init, iters=160, lr=2e-3):
+    """Gradient descent on the sphere centres through the C oracle's fused forward + reverse pass.
+    The artefacts were written by util.draw -> scipy.misc.imsave (generate_data.py:44-52), which
+    rescales by the image maximum: u8 = round(255 * render / max(render)); the scale is re-derived
+    from the current render on every step."""
+    tgt = tgt_u8.astype(np.float64) / 255.0
+    c = np.array(init, dtype=np.float64)
+    for _ in range(iters):
+        ps = oc.PackedScene.from_spec(_depth_spec(c))
+        img, _, _ = oc.render_forward(ps, want_aux=False)
+        k = 1.0 / float(img[0][:, :, 0].max())
+        t3 = np.zeros((1, 32, 32, 3), np.float32)
+        t3[0, :, :, 0] = tgt / k
+        _, _, _, grad = oc.render_fused_mse(ps, t3, channel_weight=np.array([1, 0, 0], np.float32))
+        c -= lr * (-oc.split_grad(grad[0], len(c))['w2o'][:, :, 3] * k * k)     # w2o = translate(-c): d/dc = -d/db
+    return c
+
+
+@pytest.mark.parametrize('which', ['15.jpg', 'example.png'])
+def test_depth_shader_pinned_to_reference_depth_renders(which):
+    """DepthMapShader(6.1) (shader.py:14-20, BASELINE config 2) against the two depth maps the reference
+    ships: 15.jpg (test_balls.py:17: two unit spheres of generate_data.py's dataset, JPEG) and
+    example.png (test_1ball.py:17: one sphere, lossless).  Their sphere centres are unknown
+    (rand() in generate_data.py:39-40), so they are recovered by gradient descent through the oracle
+    from a coarse grid estimate; the oracle must then reproduce the artefact.
+      15.jpg: every pixel away from silhouettes to the JPEG floor (<= 8/255), mean |diff| 1.1/255,
+        mismatches confined to silhouette pixels (the reference's AA jitter is unseeded), both centres
+        inside the box the generator draws from ([-2,2]^2 x [4,6]).
+      example.png: mean |diff| 1.7/255 with a unit sphere; its lower rim is up to 18/255 brighter than
+        any unit sphere renders (provenance unknown: an older renderer or a non-unit scale, as in
+        test_1ball.py's own model), so only the weaker bound is asserted there."""
+    if which == '15.jpg':
+        ref = np.load(os.path.join(GOLD, 'balls_15.npy'))
+        init, interior_tol, max_out = [(-1.0, 0.0, 4.5), (1.0, -1.0, 5.0)], 8, 60
+    else:
+        ref = np.load(os.path.join(GOLD, 'example_png.npy'))
+        init, interior_tol, max_out = [(1.5, 0.5, 4.5)], 20, 40
+    c = _fit_depth_artefact(ref, init)
+    assert np.all(np.abs(c[:, :2]) <= 2.0) and np.all((c[:, 2] >= 4.0) & (c[:, 2] <= 6.0)), c
+    spec = _depth_spec(c)
+    img_n, hit_n, _ = on.render(spec)
+    ps = oc.PackedScene.from_spec(spec)
+    im, h, _ = oc.render_forward(ps)
+    for name, img in (('numpy', img_n[:, :, 0]), ('c', im[0][:, :, 0])):
+        u8 = np.round(255.0 * img / img.max())
+        d = np.abs(u8 - ref.astype(np.float64))
+        assert d.mean() < 2.0, (which, name, d.mean())
+        # pixels whose 4 samples agree in OUR render and whose 8 neighbours do too are interior or
+        # background: they must match to the quantisation floor
+        uniform = np.all(h[0] == h[0][0:1], axis=0)
+        pad = np.pad(uniform, 1, mode='edge')
+        inner = np.ones_like(uniform)
+        for dy in (0, 1, 2):
+            for dx in (0, 1, 2):
+                inner &= pad[dy:dy + 32, dx:dx + 32]
+        assert inner.sum() > 700
+        assert d[inner].max() <= interior_tol, (which, name, d[inner].max())
+        assert (d > 8).sum() <= max_out, (which, name, int((d > 8).sum()))
