@@ -117,6 +117,22 @@ extern "C" {
  * integer addition is associative, so the result does not depend on the order of arrival).
  * Range +-2^43, absolute resolution 2^-60 per contribution.  Needs rrt_scene.det_workspace. */
 #define RRT_FLAG_DETERMINISTIC 64
+/* One mirror-reflection bounce (BASELINE config 3 names it; the reference itself has NO secondary
+ * ray -- match_mirror.py:40,45 matches an image to its left-right flip, the hook would be
+ * scene.py:41-45 / shader.py:43-45 -- so this is an extension and PARITY IS UNPINNED by the
+ * reference; it is pinned by a dense NumPy restatement, float64 autograd and finite differences).
+ * Root camera variant only (camera.o2w rotation = identity, origin 0), Phong shaders only.
+ * For a winning primary ray (object k, parameter t, world direction d), float32 canonical order:
+ *     n_o = p'/|p'| (sphere; p' = o' + t d')  or (0,0,+-1) (square)      object-space normal
+ *     n_w = A_k^T n_o / |A_k^T n_o|                                      world normal
+ *     r   = d - 2 (d.n_w) n_w ,  P = t d                                  reflected ray
+ * (P, r) is tested against every OTHER object in list order (canonical test with o'' = A_j P + b_j),
+ * nearest hit with t2 > 0, strict '<'; that hit is shaded by the scene's shader as seen along r;
+ *     rgb = (1 - k_k) rgb_primary + k_k rgb_secondary        (rgb_secondary = 0 if nothing is hit)
+ * with k_k = rrt_scene.reflectivity[k] of the PRIMARY object (a constant: it gets no gradient).
+ * The reverse pass differentiates through the secondary shading, the secondary object's transform,
+ * and -- through P, r, n_w -- the primary object's transform (masks constant, like everywhere). */
+#define RRT_FLAG_MIRROR 128
 
 #define RRT_OK 0
 #define RRT_ERR_INVALID (-1)   /* bad argument (message in rrt_last_error)            */
@@ -195,6 +211,10 @@ typedef struct rrt_scene {
     /* RRT_FLAG_DETERMINISTIC only: int64 [B][RRT_GRAD_SIZE(N) + 1][2] (RRT_DET_WORKSPACE_BYTES),
      * 16-byte aligned device scratch, zeroed by the callee. */
     int64_t* det_workspace;
+
+    /* RRT_FLAG_MIRROR only: float32 [B][N] (or [N] with stride 0) mirror coefficient k in [0,1] per object */
+    const float* reflectivity;
+    int64_t reflectivity_scene_stride;
 } rrt_scene;
 
 #define RRT_DET_WORKSPACE_BYTES(num_scenes, num_objects) ((size_t)(num_scenes) * (RRT_GRAD_SIZE(num_objects) + 1) * 16)

@@ -45,6 +45,8 @@ typedef struct {
     float cc;         /* o'.o' - 1      (shape.py:79,82)               */
     int type;
     float ka, kd, ks, sh, col[3];
+    int has64;        /* secondary (mirror) objects in the f64-record validation mode: origin kept in double */
+    double o64[3];
 } orc_obj;
 
 typedef struct {
@@ -126,6 +128,7 @@ static void orc_prep(const rrt_scene* sc, int scene, orc_obj* objs, orc_glob* g)
                            FMAF(o->A[r * 3 + 1], g->ct[1], FMAF(o->A[r * 3 + 0], g->ct[0], o->b[r])));
         o->cc = FMAF(o->o[2], o->o[2], FMAF(o->o[1], o->o[1], o->o[0] * o->o[0])) - 1.0f;
         o->type = sc->obj_type[k];
+        o->has64 = 0;
         o->ka = m[0]; o->kd = m[1]; o->ks = m[2]; o->sh = m[3];
         o->col[0] = m[4]; o->col[1] = m[5]; o->col[2] = m[6];
     }
@@ -141,6 +144,7 @@ typedef struct { float d[3], vn, pd, det, t; double d64[3], vn64, pd64, det64, t
 static int orc_f64_record = 0;
 void orc_set_f64_record(int on) { orc_f64_record = on; }
 
+static inline void orc_promote_d(const orc_obj* o, const double dw[3], orc_hit* h);
 static inline void orc_promote(const orc_obj* o, const float dw[3], orc_hit* h) {
     if (!orc_f64_record) {
         for (int c = 0; c < 3; c++) h->d64[c] = h->d[c];
@@ -149,15 +153,35 @@ static inline void orc_promote(const orc_obj* o, const float dw[3], orc_hit* h) 
     }
     for (int r = 0; r < 3; r++)
         h->d64[r] = (double)o->A[r * 3] * dw[0] + (double)o->A[r * 3 + 1] * dw[1] + (double)o->A[r * 3 + 2] * dw[2];
+    const double o0 = o->has64 ? o->o64[0] : (double)o->o[0], o1 = o->has64 ? o->o64[1] : (double)o->o[1],
+                 o2 = o->has64 ? o->o64[2] : (double)o->o[2];
     if (o->type == RRT_OBJ_SPHERE) {
-        double oo = (double)o->o[0] * o->o[0] + (double)o->o[1] * o->o[1] + (double)o->o[2] * o->o[2];
+        double oo = o0 * o0 + o1 * o1 + o2 * o2;
         h->vn64 = h->d64[0] * h->d64[0] + h->d64[1] * h->d64[1] + h->d64[2] * h->d64[2];
-        h->pd64 = h->d64[0] * o->o[0] + h->d64[1] * o->o[1] + h->d64[2] * o->o[2];
+        h->pd64 = h->d64[0] * o0 + h->d64[1] * o1 + h->d64[2] * o2;
         h->det64 = h->pd64 * h->pd64 - h->vn64 * (oo - 1.0);
         h->t64 = (-h->pd64 - sqrt(h->det64)) / h->vn64;
     } else {
         h->vn64 = h->pd64 = h->det64 = 0.0;
-        h->t64 = -(double)o->o[2] / h->d64[2];
+        h->t64 = -o2 / h->d64[2];
+    }
+}
+
+/* same, world direction given in double (the reflected ray of the mirror bounce in validation mode) */
+static inline void orc_promote_d(const orc_obj* o, const double dw[3], orc_hit* h) {
+    for (int r = 0; r < 3; r++)
+        h->d64[r] = (double)o->A[r * 3] * dw[0] + (double)o->A[r * 3 + 1] * dw[1] + (double)o->A[r * 3 + 2] * dw[2];
+    const double o0 = o->has64 ? o->o64[0] : (double)o->o[0], o1 = o->has64 ? o->o64[1] : (double)o->o[1],
+                 o2 = o->has64 ? o->o64[2] : (double)o->o[2];
+    if (o->type == RRT_OBJ_SPHERE) {
+        double oo = o0 * o0 + o1 * o1 + o2 * o2;
+        h->vn64 = h->d64[0] * h->d64[0] + h->d64[1] * h->d64[1] + h->d64[2] * h->d64[2];
+        h->pd64 = h->d64[0] * o0 + h->d64[1] * o1 + h->d64[2] * o2;
+        h->det64 = h->pd64 * h->pd64 - h->vn64 * (oo - 1.0);
+        h->t64 = (-h->pd64 - sqrt(h->det64)) / h->vn64;
+    } else {
+        h->vn64 = h->pd64 = h->det64 = 0.0;
+        h->t64 = -o2 / h->d64[2];
     }
 }
 
@@ -260,7 +284,7 @@ typedef struct {
 static inline void orc_shade(const rrt_scene* sc, const orc_obj* o, const orc_glob* g, const orc_hit* h,
                              orc_shade_rec* r, double rgb[3]) {
     r->t = h->t64;
-    for (int c = 0; c < 3; c++) { r->d[c] = h->d64[c]; r->o[c] = o->o[c]; }
+    for (int c = 0; c < 3; c++) { r->d[c] = h->d64[c]; r->o[c] = o->has64 ? o->o64[c] : (double)o->o[c]; }
     if (sc->shader == RRT_SHADER_DEPTH) { /* shader.py:14-20 */
         double v = 1.0 - r->t / (double)sc->max_depth;
         rgb[0] = rgb[1] = rgb[2] = v;
@@ -292,13 +316,154 @@ static inline void orc_shade(const rrt_scene* sc, const orc_obj* o, const orc_gl
     }
 }
 
+/* ---- mirror bounce (RRT_FLAG_MIRROR; include/rrt_b200.h) ---------------------------------------
+ * An EXTENSION: the reference has no secondary ray (match_mirror.py:40,45 matches an image to its
+ * left-right flip; the hook would be scene.py:41-45 / shader.py:43-45).  PARITY UNPINNED by the
+ * reference; pinned instead by the dense NumPy restatement, float64 autograd and finite differences.
+ * Root camera variant only (camera.o2w = identity, origin 0).  For a winning primary ray (object k,
+ * parameter t, world direction d), all in float32 canonical order (this defines the secondary mask):
+ *     n_o  = p'/|p'| (sphere, p' = o' + t d')   or  (0,0,+-1) (square)          object-space normal
+ *     m    = A_k^T n_o ,  n_w = m/|m|                                           world normal
+ *     r    = d - 2 (d.n_w) n_w ,   P = t d                                       reflected ray
+ * The secondary ray (P, r) is tested against every OTHER object in list order with the canonical
+ * ray-object test (o'' = A_j P + b_j), nearest hit with t2 > 0, strict '<'; the hit is shaded by the
+ * scene's shader as seen along r;  rgb = (1 - k_k) rgb_primary + k_k rgb_secondary  (0 if nothing is
+ * hit), k_k = reflectivity of the primary object (a constant: no gradient).  One bounce. */
+typedef struct {
+    float P[3], r[3], nw[3], no[3], mn, dn;
+    double P64[3], r64[3], nw64[3], no64[3], mn64, dn64;
+} orc_bounce;
+
+static inline void orc_bounce_geom(const orc_obj* o, const orc_hit* h, const float dw[3], orc_bounce* b) {
+    float m[3];
+    if (o->type == RRT_OBJ_SPHERE) {
+        float p[3];
+        for (int c = 0; c < 3; c++) p[c] = FMAF(h->t, h->d[c], o->o[c]);
+        float pn = sqrtf(FMAF(p[2], p[2], FMAF(p[1], p[1], p[0] * p[0])));
+        for (int c = 0; c < 3; c++) b->no[c] = p[c] / pn;
+    } else {
+        b->no[0] = b->no[1] = 0.0f;
+        b->no[2] = (o->o[2] > 0.0f) ? 1.0f : -1.0f;
+    }
+    for (int i = 0; i < 3; i++) m[i] = FMAF(o->A[6 + i], b->no[2], FMAF(o->A[3 + i], b->no[1], o->A[i] * b->no[0]));
+    b->mn = sqrtf(FMAF(m[2], m[2], FMAF(m[1], m[1], m[0] * m[0])));
+    for (int c = 0; c < 3; c++) b->nw[c] = m[c] / b->mn;
+    b->dn = FMAF(dw[2], b->nw[2], FMAF(dw[1], b->nw[1], dw[0] * b->nw[0]));
+    const float k2 = -2.0f * b->dn;
+    for (int c = 0; c < 3; c++) { b->r[c] = FMAF(k2, b->nw[c], dw[c]); b->P[c] = h->t * dw[c]; }
+    if (!orc_f64_record) {
+        for (int c = 0; c < 3; c++) { b->P64[c] = b->P[c]; b->r64[c] = b->r[c]; b->nw64[c] = b->nw[c]; b->no64[c] = b->no[c]; }
+        b->mn64 = b->mn; b->dn64 = b->dn;
+        return;
+    }
+    double m64[3];
+    if (o->type == RRT_OBJ_SPHERE) {
+        double p[3], pn = 0.0;
+        for (int c = 0; c < 3; c++) { p[c] = (double)o->o[c] + h->t64 * h->d64[c]; pn += p[c] * p[c]; }
+        pn = sqrt(pn);
+        for (int c = 0; c < 3; c++) b->no64[c] = p[c] / pn;
+    } else {
+        for (int c = 0; c < 3; c++) b->no64[c] = b->no[c];
+    }
+    b->mn64 = 0.0;
+    for (int i = 0; i < 3; i++) {
+        m64[i] = (double)o->A[i] * b->no64[0] + (double)o->A[3 + i] * b->no64[1] + (double)o->A[6 + i] * b->no64[2];
+        b->mn64 += m64[i] * m64[i];
+    }
+    b->mn64 = sqrt(b->mn64);
+    b->dn64 = 0.0;
+    for (int c = 0; c < 3; c++) { b->nw64[c] = m64[c] / b->mn64; b->dn64 += (double)dw[c] * b->nw64[c]; }
+    for (int c = 0; c < 3; c++) { b->r64[c] = (double)dw[c] - 2.0 * b->dn64 * b->nw64[c]; b->P64[c] = h->t64 * (double)dw[c]; }
+}
+
+/* nearest OTHER object along the reflected ray; fills o2 (object j2 re-based at origin P) and its hit record */
+static inline int orc_secondary(const orc_obj* objs, int N, int k, const orc_bounce* b, orc_obj* o2, orc_hit* h2) {
+    float tmin = INFINITY;
+    int j2 = -1;
+    for (int j = 0; j < N; j++) {
+        if (j == k) continue;
+        orc_obj t = objs[j];
+        for (int r = 0; r < 3; r++)
+            t.o[r] = FMAF(t.A[r * 3 + 2], b->P[2], FMAF(t.A[r * 3 + 1], b->P[1], FMAF(t.A[r * 3 + 0], b->P[0], t.b[r])));
+        t.cc = FMAF(t.o[2], t.o[2], FMAF(t.o[1], t.o[1], t.o[0] * t.o[0])) - 1.0f;
+        orc_hit hh;
+        float t2 = orc_test(&t, b->r, &hh);
+        if (t2 > 0.0f && t2 < tmin) { tmin = t2; j2 = j; *o2 = t; *h2 = hh; }
+    }
+    if (j2 >= 0) {
+        if (orc_f64_record) {
+            o2->has64 = 1;
+            for (int r = 0; r < 3; r++)
+                o2->o64[r] = (double)o2->A[r * 3] * b->P64[0] + (double)o2->A[r * 3 + 1] * b->P64[1] +
+                             (double)o2->A[r * 3 + 2] * b->P64[2] + (double)o2->b[r];
+            orc_promote_d(o2, b->r64, h2);
+        } else {
+            orc_promote(o2, b->r, h2);
+        }
+    }
+    return j2;
+}
+
+static void orc_backward_ray(const rrt_scene* sc, const orc_obj* o, const orc_glob* g, const orc_hit* h,
+                             const orc_shade_rec* r, const float rcam[3], const double origin[3], const double dwd[3],
+                             int camera_grad, const double* extra, double* god,
+                             const double gc[3], double* og, double* gg);
+
+/* reverse pass of one winning primary ray with the bounce: secondary object first (its own parameters,
+ * and the gradients w.r.t. P and r), then the primary object with the chain through the reflection */
+static void orc_mirror_backward(const rrt_scene* sc, const orc_obj* objs, int N, const orc_glob* g, int k,
+                                const orc_hit* h, const orc_shade_rec* r, const float dw[3], const double gc[3],
+                                double kr, double* gl, double* ggl) {
+    const orc_obj* o = &objs[k];
+    orc_bounce b;
+    orc_obj o2;
+    orc_hit h2;
+    memset(&o2, 0, sizeof o2);
+    memset(&h2, 0, sizeof h2);
+    orc_bounce_geom(o, h, dw, &b);
+    const int j2 = orc_secondary(objs, N, k, &b, &o2, &h2);
+    double gc1[3], gc2[3], extra[4] = {0, 0, 0, 0}, dA[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < 3; c++) { gc1[c] = (1.0 - kr) * gc[c]; gc2[c] = kr * gc[c]; }
+    const double dw64[3] = {dw[0], dw[1], dw[2]}, zero3[3] = {0, 0, 0};
+    if (j2 >= 0) {
+        orc_shade_rec r2;
+        double rgb2[3], god[6], GP[3], Gr[3];
+        orc_shade(sc, &o2, g, &h2, &r2, rgb2);
+        orc_backward_ray(sc, &o2, g, &h2, &r2, NULL, b.P64, b.r64, 0, NULL, god, gc2,
+                         gl + (size_t)j2 * RRT_OBJ_GRAD_STRIDE, ggl);
+        for (int c = 0; c < 3; c++) {
+            GP[c] = o2.A[c] * god[0] + o2.A[3 + c] * god[1] + o2.A[6 + c] * god[2];
+            Gr[c] = o2.A[c] * god[3] + o2.A[3 + c] * god[4] + o2.A[6 + c] * god[5];
+        }
+        extra[3] = GP[0] * dw64[0] + GP[1] * dw64[1] + GP[2] * dw64[2];              /* P = t d */
+        const double grn = Gr[0] * b.nw64[0] + Gr[1] * b.nw64[1] + Gr[2] * b.nw64[2];
+        double g_nw[3], g_m[3], dot = 0.0;
+        for (int c = 0; c < 3; c++) { g_nw[c] = -2.0 * (b.dn64 * Gr[c] + grn * dw64[c]); dot += b.nw64[c] * g_nw[c]; }
+        for (int c = 0; c < 3; c++) g_m[c] = (g_nw[c] - b.nw64[c] * dot) / b.mn64;   /* n_w = m/|m| */
+        for (int rr = 0; rr < 3; rr++)
+            for (int i = 0; i < 3; i++) dA[rr * 3 + i] = b.no64[rr] * g_m[i];          /* m = A^T n_o */
+        if (o->type == RRT_OBJ_SPHERE)
+            for (int rr = 0; rr < 3; rr++)
+                extra[rr] = (double)o->A[rr * 3] * g_m[0] + (double)o->A[rr * 3 + 1] * g_m[1] + (double)o->A[rr * 3 + 2] * g_m[2];
+    }
+    double* og1 = gl + (size_t)k * RRT_OBJ_GRAD_STRIDE;
+    orc_backward_ray(sc, o, g, h, r, NULL, zero3, dw64, 0, extra, NULL, gc1, og1, ggl);
+    for (int rr = 0; rr < 3; rr++)
+        for (int i = 0; i < 3; i++) og1[rr * 4 + i] += dA[rr * 3 + i];
+}
+
 /* ---- reverse pass for one winning ray (closed form) ---------
  * gc[3] = dL/d(image[a,b,:]) / S.  Accumulates into og (this object's 19 slots)
  * and gg (21 global slots).  Light-direction slots hold d/d(Lhat) here; the
  * normalisation chain is applied once at the end (orc_finish_grads). */
-static inline void orc_backward_ray(const rrt_scene* sc, const orc_obj* o, const orc_glob* g, const orc_hit* h,
-                                    const orc_shade_rec* r, const float rcam[3], const float dw[3],
-                                    const double gc[3], double* og, double* gg) {
+/* Mirror bounce (RRT_FLAG_MIRROR): `origin` / `dwd` are the ray's world origin and direction (camera
+ * origin and primary direction, or hit point P and reflected direction r of a secondary ray);
+ * `extra` = {dL/d(object-space normal)[3], dL/dt} fed in from the secondary ray through the reflection
+ * (primary rays only), `god` receives {g_o'[3], g_d'[3]} (object-space origin / direction gradients). */
+static void orc_backward_ray(const rrt_scene* sc, const orc_obj* o, const orc_glob* g, const orc_hit* h,
+                             const orc_shade_rec* r, const float rcam[3], const double origin[3], const double dwd[3],
+                             int camera_grad, const double* extra, double* god,
+                             const double gc[3], double* og, double* gg) {
     double g_t = 0.0, g_p[3] = {0, 0, 0};
     double g_o[3] = {0, 0, 0}, g_d[3] = {0, 0, 0};
     if (sc->shader == RRT_SHADER_DEPTH) {
@@ -329,6 +494,7 @@ static inline void orc_backward_ray(const rrt_scene* sc, const orc_obj* o, const
         }
         for (int c = 0; c < 3; c++) { g_n[c] -= g_ndl * g->Lh[c]; g_Lh[c] -= g_ndl * r->nrm[c]; }
         for (int c = 0; c < 3; c++) gg[c] += g_Lh[c];
+        if (extra) { for (int c = 0; c < 3; c++) g_n[c] += extra[c]; g_t += extra[3]; }
         if (o->type == RRT_OBJ_SPHERE) {
             double ndg = r->nrm[0] * g_n[0] + r->nrm[1] * g_n[1] + r->nrm[2] * g_n[2];
             for (int c = 0; c < 3; c++) g_p[c] = (g_n[c] - r->nrm[c] * ndg) / r->pn;
@@ -351,12 +517,13 @@ static inline void orc_backward_ray(const rrt_scene* sc, const orc_obj* o, const
         g_o[2] += -g_t / r->d[2];
         g_d[2] += -g_t * r->t / r->d[2];
     }
-    /* d' = A.dw ; o' = A.ct + b */
+    /* d' = A.dw ; o' = A.origin + b */
     for (int rr = 0; rr < 3; rr++) {
-        for (int c = 0; c < 3; c++) og[rr * 4 + c] += g_d[rr] * (double)dw[c] + g_o[rr] * (double)g->ct[c];
+        for (int c = 0; c < 3; c++) og[rr * 4 + c] += g_d[rr] * dwd[c] + g_o[rr] * origin[c];
         og[rr * 4 + 3] += g_o[rr];
     }
-    if (sc->camera_grad) {
+    if (god) for (int c = 0; c < 3; c++) { god[c] = g_o[c]; god[3 + c] = g_d[c]; }
+    if (camera_grad) {
         double g_dw[3], g_ct[3];
         for (int c = 0; c < 3; c++) {
             g_dw[c] = o->A[0 * 3 + c] * g_d[0] + o->A[1 * 3 + c] * g_d[1] + o->A[2 * 3 + c] * g_d[2];
@@ -419,8 +586,10 @@ static inline void orc_pixel_ray(const rrt_scene* sc, const orc_glob* g, int sce
  */
 static int orc_run(const rrt_scene* sc, int mode, float* image, int32_t* hit_out, float* tmin_out,
                    const float* dl_dimage, const int32_t* hit_in, const float* target, const float* cw,
-                   double* loss, double* grad) {
+                   double* loss, double* grad, int32_t* hit2_out) {
     int n = sc->n, S = sc->samples, N = sc->num_objects, B = sc->num_scenes, rows = orc_rows(sc);
+    const int mirror = (sc->flags & RRT_FLAG_MIRROR) != 0;
+    if (mirror && (!sc->reflectivity || sc->shader == RRT_SHADER_DEPTH || sc->camera_grad)) return RRT_ERR_UNSUPPORTED;
     size_t gsz = RRT_GRAD_SIZE(N);
     float w3[3] = {1.f, 1.f, 1.f};
     if (cw) { w3[0] = cw[0]; w3[1] = cw[1]; w3[2] = cw[2]; }
@@ -431,6 +600,7 @@ static int orc_run(const rrt_scene* sc, int mode, float* image, int32_t* hit_out
         orc_glob g;
         orc_soa soa;
         orc_prep(sc, scene, objs, &g);
+        const float* refl = mirror ? sc->reflectivity + (size_t)scene * sc->reflectivity_scene_stride : NULL;
         int all_sph = orc_all_spheres(objs, N);
         if (all_sph) orc_make_soa(objs, N, &soa, soa_store);
         double* gscene = grad ? grad + (size_t)scene * gsz : NULL;
@@ -471,8 +641,24 @@ static int orc_run(const rrt_scene* sc, int mode, float* image, int32_t* hit_out
                             if (!shadowed) {
                                 orc_promote(&objs[idx[s]], dws[s], &h);
                                 orc_shade(sc, &objs[idx[s]], &g, &h, &r, rgbs[s]);
+                                if (mirror && isfinite(tm[s])) {
+                                    orc_bounce bn;
+                                    orc_obj o2;
+                                    orc_hit h2;
+                                    orc_shade_rec r2;
+                                    double rgb2[3] = {0, 0, 0};
+                                    memset(&o2, 0, sizeof o2);
+                                    memset(&h2, 0, sizeof h2);
+                                    orc_bounce_geom(&objs[idx[s]], &h, dws[s], &bn);
+                                    int j2 = orc_secondary(objs, N, idx[s], &bn, &o2, &h2);
+                                    if (j2 >= 0) orc_shade(sc, &o2, &g, &h2, &r2, rgb2);
+                                    const double kr = refl[idx[s]];
+                                    for (int c = 0; c < 3; c++) rgbs[s][c] = (1.0 - kr) * rgbs[s][c] + kr * rgb2[c];
+                                    if (hit2_out) hit2_out[ro] = j2;
+                                }
                             }
                         }
+                        if (hit2_out && !(mirror && idx[s] >= 0 && !shadowed && isfinite(tm[s]))) hit2_out[ro] = -1;
                         if (hit_out) hit_out[ro] = (shadowed && idx[s] >= 0) ? (idx[s] | RRT_HIT_SHADOWED) : idx[s];
                         if (shadowed) idx[s] = -1;   /* (0,0,0) and no gradient from here on */
                         if (tmin_out) tmin_out[ro] = tm[s];
@@ -501,8 +687,15 @@ static int orc_run(const rrt_scene* sc, int mode, float* image, int32_t* hit_out
                         if (!isfinite(h.t)) continue; /* stale hit_in */
                         orc_promote(&objs[idx[s]], dws[s], &h);
                         orc_shade(sc, &objs[idx[s]], &g, &h, &r, rgb);
-                        orc_backward_ray(sc, &objs[idx[s]], &g, &h, &r, rc[s], dws[s], gc,
-                                         gl + (size_t)idx[s] * RRT_OBJ_GRAD_STRIDE, gl + (size_t)N * RRT_OBJ_GRAD_STRIDE);
+                        const double ct64[3] = {g.ct[0], g.ct[1], g.ct[2]}, dw64[3] = {dws[s][0], dws[s][1], dws[s][2]};
+                        double* og1 = gl + (size_t)idx[s] * RRT_OBJ_GRAD_STRIDE;
+                        double* ggl = gl + (size_t)N * RRT_OBJ_GRAD_STRIDE;
+                        if (mirror) {
+                            orc_mirror_backward(sc, objs, N, &g, idx[s], &h, &r, dws[s], gc, refl[idx[s]], gl, ggl);
+                            continue;
+                        }
+                        orc_backward_ray(sc, &objs[idx[s]], &g, &h, &r, rc[s], ct64, dw64, sc->camera_grad, NULL, NULL, gc,
+                                         og1, ggl);
                     }
                 }
             }
@@ -522,16 +715,21 @@ static int orc_run(const rrt_scene* sc, int mode, float* image, int32_t* hit_out
 }
 
 int orc_render_forward(const rrt_scene* sc, float* image, int32_t* hit_index, float* tmin) {
-    return orc_run(sc, 1, image, hit_index, tmin, NULL, NULL, NULL, NULL, NULL, NULL);
+    return orc_run(sc, 1, image, hit_index, tmin, NULL, NULL, NULL, NULL, NULL, NULL, NULL);
+}
+
+/* forward + the secondary (mirror) hit index per ray, [B][S][rows][n], -1 = none (test infrastructure) */
+int orc_render_forward_secondary(const rrt_scene* sc, float* image, int32_t* hit_index, int32_t* hit2) {
+    return orc_run(sc, 1, image, hit_index, NULL, NULL, NULL, NULL, NULL, NULL, NULL, hit2);
 }
 
 int orc_render_backward(const rrt_scene* sc, const float* dl_dimage, const int32_t* hit_index, double* grad) {
-    return orc_run(sc, 2, NULL, NULL, NULL, dl_dimage, hit_index, NULL, NULL, NULL, grad);
+    return orc_run(sc, 2, NULL, NULL, NULL, dl_dimage, hit_index, NULL, NULL, NULL, grad, NULL);
 }
 
 int orc_render_fused_mse(const rrt_scene* sc, const float* target, const float* channel_weight, float* image,
                          int32_t* hit_index, double* loss, double* grad) {
-    return orc_run(sc, 4 | 1, image, hit_index, NULL, NULL, NULL, target, channel_weight, loss, grad);
+    return orc_run(sc, 4 | 1, image, hit_index, NULL, NULL, NULL, target, channel_weight, loss, grad, NULL);
 }
 
 /* primary rays only (for pinning against numpy make_rays): out[rows][n][S][3] in

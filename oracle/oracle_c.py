@@ -30,6 +30,7 @@ class RrtScene(C.Structure):
         ('jitter_scene_stride', C.c_int64), ('base_rays', C.c_void_p),
         ('scene_begin', C.c_int32), ('flags', C.c_int32), ('obj_records', C.c_void_p),
         ('ticket', C.c_void_p), ('det_workspace', C.c_void_p),
+        ('reflectivity', C.c_void_p), ('reflectivity_scene_stride', C.c_int64),
     ]
 
 
@@ -66,7 +67,7 @@ def use_all_cores():
     return num_threads()
 
 
-FLAG_SHADOWS, HIT_SHADOWED = 4, 0x40000000
+FLAG_SHADOWS, HIT_SHADOWED, FLAG_MIRROR = 4, 0x40000000, 128
 
 
 def _ptr(a):
@@ -79,7 +80,7 @@ class PackedScene:
 
     def __init__(self, n, samples, obj_type, w2o, material, light, camera, shader,
                  transpose, max_depth=1.0, jitter_x=None, jitter_y=None, seed=0,
-                 camera_grad=0, row_begin=0, row_count=0, scene_begin=0, shadows=0):
+                 camera_grad=0, row_begin=0, row_count=0, scene_begin=0, shadows=0, reflectivity=None):
         self.n, self.samples = int(n), int(samples)
         self.obj_type = np.ascontiguousarray(obj_type, dtype=np.int32)
         self.N = int(self.obj_type.shape[0])
@@ -98,6 +99,8 @@ class PackedScene:
         self.row_count = int(row_count)
         self.scene_begin = int(scene_begin)
         self.shadows = int(shadows)
+        # mirror bounce (RRT_FLAG_MIRROR): per-object reflectivity [N] (or [B,N]); None = no bounce
+        self.reflectivity = None if reflectivity is None else np.ascontiguousarray(reflectivity, dtype=np.float32)
         self.rows = self.row_count if self.row_count > 0 else self.n - self.row_begin
         self.jitter_x = None if jitter_x is None else np.ascontiguousarray(jitter_x, dtype=np.float32)
         self.jitter_y = None if jitter_y is None else np.ascontiguousarray(jitter_y, dtype=np.float32)
@@ -122,14 +125,14 @@ class PackedScene:
             transpose=1 if root else 0, max_depth=spec.get('max_depth', 1.0),
             jitter_x=jx, jitter_y=jy, seed=use_rng_seed or 0,
             camera_grad=(0 if root else 1) if camera_grad is None else camera_grad,
-            shadows=int(bool(spec.get('shadows', 0))))
+            shadows=int(bool(spec.get('shadows', 0))), reflectivity=spec.get('reflectivity'))
 
     def slab(self, row_begin, row_count):
         jx = None if self.jitter_x is None else self.jitter_x.reshape(-1, self.n, self.n, self.samples)[:, row_begin:row_begin + row_count]
         jy = None if self.jitter_y is None else self.jitter_y.reshape(-1, self.n, self.n, self.samples)[:, row_begin:row_begin + row_count]
         return PackedScene(self.n, self.samples, self.obj_type, self.w2o, self.material, self.light,
                            self.camera, self.shader, self.transpose, self.max_depth, jx, jy, self.seed,
-                           self.camera_grad, row_begin, row_count, shadows=self.shadows)
+                           self.camera_grad, row_begin, row_count, shadows=self.shadows, reflectivity=self.reflectivity)
 
     def desc(self):
         def stride(a, per):
@@ -139,7 +142,10 @@ class PackedScene:
         d.shader, d.transpose = self.shader, self.transpose
         d.row_begin, d.row_count = self.row_begin, self.row_count
         d.scene_begin = self.scene_begin
-        d.flags = FLAG_SHADOWS if self.shadows else 0
+        d.flags = (FLAG_SHADOWS if self.shadows else 0) | (FLAG_MIRROR if self.reflectivity is not None else 0)
+        if self.reflectivity is not None:
+            d.reflectivity = _ptr(self.reflectivity)
+            d.reflectivity_scene_stride = 0 if self.reflectivity.size == self.N else self.N
         d.max_depth, d.camera_grad, d.seed = self.max_depth, self.camera_grad, self.seed
         d.obj_type, d.w2o, d.material = _ptr(self.obj_type), _ptr(self.w2o), _ptr(self.material)
         d.light, d.camera = _ptr(self.light), _ptr(self.camera)
@@ -166,6 +172,17 @@ def render_forward(ps, want_aux=True):
     rc = lib().orc_render_forward(C.byref(d), _ptr(image), _ptr(hit), _ptr(tmin))
     assert rc == 0, rc
     return image, hit, tmin
+
+
+def render_forward_secondary(ps):
+    """-> image, hit_index, secondary (mirror) hit index [B,S,rows,n] (-1 = none)"""
+    d = ps.desc()
+    image = np.zeros((ps.B, ps.rows, ps.n, 3), dtype=np.float32)
+    hit = np.zeros((ps.B, ps.samples, ps.rows, ps.n), dtype=np.int32)
+    hit2 = np.zeros((ps.B, ps.samples, ps.rows, ps.n), dtype=np.int32)
+    rc = lib().orc_render_forward_secondary(C.byref(d), _ptr(image), _ptr(hit), _ptr(hit2))
+    assert rc == 0, rc
+    return image, hit, hit2
 
 
 def render_backward(ps, dl_dimage, hit_index=None):

@@ -55,15 +55,56 @@ def leaf_params(spec):
     return p
 
 
-def forward(spec, params, hit_index, clip_closed=True):
-    """Differentiable float64 image[n,n,3] given constant winners `hit_index`."""
+def _hit_and_shade(spec, params, k, o, d, Lh, clip_closed):
+    """One object k, object-space ray origin o [3] (or [P,3]) and directions d [P,3]:
+    -> (t [P], object-space normal [P,3], rgb [P,3]); masks are the caller's business."""
+    mat = params['material'][k]
+    shader = spec['shader']
+    ob = o if o.dim() == 2 else o[None, :].expand_as(d)
+    if spec['obj_type'][k] == on.SPHERE:                # shape.py:109-138
+        pd = (d * ob).sum(1)
+        vn = (d * d).sum(1)
+        det = pd * pd - vn * ((ob * ob).sum(1) - 1.0)
+        t = (-pd - torch.sqrt(det)) / vn
+        p = ob + t[:, None] * d
+        nrm = p / torch.sqrt((p * p).sum(1))[:, None]
+    else:                                               # shape.py:25-69
+        t = -ob[:, 2] / d[:, 2]
+        nrm = torch.zeros_like(d)
+        nrm[:, 2] = torch.where(ob[:, 2].detach() > 0, 1.0, -1.0)
+    if shader == 'depth':                               # shader.py:14-20
+        rgb = (1.0 - t / float(spec['max_depth']))[:, None] * torch.ones(3, dtype=F64)
+    else:                                               # shader.py:28-53
+        # shininess is a constant in every reference script (no d/d shininess is
+        # ever requested; it would be NaN for rv<0): detached here.
+        ka, kd, ks, sh = mat[0], mat[1], mat[2], mat[3].detach()
+        ndl = -(nrm @ Lh)
+        ph = ka + kd * ndl
+        if shader == 'phong':
+            rm = 2.0 * ndl[:, None] * nrm + Lh
+            rv = rm @ params['look_at']
+            ph = ph + ks * torch.pow(rv, sh)
+        col = ph[:, None] * mat[4:7][None, :] * params['light_int'][None, :]
+        with torch.no_grad():
+            inside = (col >= 0) & (col <= 1) if clip_closed else (col > 0) & (col < 1)
+            const = torch.clamp(col, 0, 1)
+        rgb = torch.where(inside, col, const)           # clip with constant mask
+    return t, nrm, rgb
+
+
+def forward(spec, params, hit_index, clip_closed=True, hit2_index=None):
+    """Differentiable float64 image[n,n,3] given constant winners `hit_index` (and, for the mirror
+    bounce -- spec['reflectivity'], RRT_FLAG_MIRROR in include/rrt_b200.h --, the constant secondary
+    winners `hit2_index`)."""
     n, S = int(spec['n']), int(spec['samples'])
     R = effective_rays(spec)                                  # [S,n,n,3]
     cam = params['cam_o2w']
     Cm, ct = cam[:3, :3], cam[:3, 3]
     Lh = params['light_dir'] / torch.sqrt((params['light_dir'] ** 2).sum())   # scene.py:83-86
-    shader = spec['shader']
     hit_index = torch.as_tensor(np.asarray(hit_index))
+    refl = spec.get('reflectivity')
+    if refl is not None:
+        hit2_index = torch.as_tensor(np.asarray(hit2_index))
     image = torch.zeros(n, n, 3, dtype=F64)
     for s in range(S):
         img_s = torch.zeros(n, n, 3, dtype=F64)
@@ -72,49 +113,39 @@ def forward(spec, params, hit_index, clip_closed=True):
             if sel[0].numel() == 0:
                 continue
             A, b = params['w2o'][k, :3, :3], params['w2o'][k, :3, 3]
-            mat = params['material'][k]
             dw = R[s][sel] @ Cm.T                               # world dirs   [P,3]
             o = A @ ct + b                                      # object-space origin
             d = dw @ A.T                                        # object-space dirs
-            if spec['obj_type'][k] == on.SPHERE:                # shape.py:109-138
-                pd = d @ o
-                vn = (d * d).sum(1)
-                det = pd * pd - vn * ((o * o).sum() - 1.0)
-                t = (-pd - torch.sqrt(det)) / vn
-                p = o + t[:, None] * d
-                nrm = p / torch.sqrt((p * p).sum(1))[:, None]
-            else:                                               # shape.py:25-69
-                t = -o[2] / d[:, 2]
-                sgn = 1.0 if o[2].item() > 0 else -1.0
-                nrm = torch.zeros_like(d)
-                nrm[:, 2] = sgn
-            if shader == 'depth':                               # shader.py:14-20
-                rgb = (1.0 - t / float(spec['max_depth']))[:, None] * torch.ones(3, dtype=F64)
-            else:                                               # shader.py:28-53
-                # shininess is a constant in every reference script (no d/d shininess is
-                # ever requested; it would be NaN for rv<0): detached here.
-                ka, kd, ks, sh = mat[0], mat[1], mat[2], mat[3].detach()
-                ndl = -(nrm @ Lh)
-                ph = ka + kd * ndl
-                if shader == 'phong':
-                    rm = 2.0 * ndl[:, None] * nrm + Lh
-                    rv = rm @ params['look_at']
-                    ph = ph + ks * torch.pow(rv, sh)
-                col = ph[:, None] * mat[4:7][None, :] * params['light_int'][None, :]
-                with torch.no_grad():
-                    inside = (col >= 0) & (col <= 1) if clip_closed else (col > 0) & (col < 1)
-                    const = torch.clamp(col, 0, 1)
-                rgb = torch.where(inside, col, const)           # clip with constant mask
+            t, nrm, rgb = _hit_and_shade(spec, params, k, o, d, Lh, clip_closed)
+            if refl is not None:                                # one mirror bounce (extension)
+                kr = float(refl[k])
+                m = nrm @ A                                     # A^T n_o per row
+                nw = m / torch.sqrt((m * m).sum(1))[:, None]
+                dn = (dw * nw).sum(1)
+                r = dw - 2.0 * dn[:, None] * nw
+                P = ct[None, :] + t[:, None] * dw
+                rgb2 = torch.zeros_like(rgb)
+                j2s = hit2_index[s][sel]
+                for j in range(len(spec['obj_type'])):
+                    sub = (j2s == j).nonzero(as_tuple=True)[0]
+                    if sub.numel() == 0:
+                        continue
+                    Aj, bj = params['w2o'][j, :3, :3], params['w2o'][j, :3, 3]
+                    o2 = P[sub] @ Aj.T + bj[None, :]
+                    d2 = r[sub] @ Aj.T
+                    _, _, c2 = _hit_and_shade(spec, params, j, o2, d2, Lh, clip_closed)
+                    rgb2 = rgb2.index_put((sub,), c2)
+                rgb = (1.0 - kr) * rgb + kr * rgb2
             img_s = img_s.index_put(sel, rgb)
         image = image + img_s
     return image / S
 
 
-def gradients(spec, hit_index, loss_fn):
+def gradients(spec, hit_index, loss_fn, hit2_index=None):
     """Returns (loss float, image float64[n,n,3], grads dict of float64 arrays).
     loss_fn: image tensor -> scalar tensor."""
     params = leaf_params(spec)
-    image = forward(spec, params, hit_index)
+    image = forward(spec, params, hit_index, hit2_index=hit2_index)
     loss = loss_fn(image)
     names = list(params.keys())
     gs = torch.autograd.grad(loss, [params[k] for k in names], allow_unused=True)

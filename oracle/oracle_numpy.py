@@ -258,6 +258,70 @@ def depth_shade(dist, max_depth):
 
 
 # ----------------------------------------------------------------------------
+# mirror bounce (RRT_FLAG_MIRROR in include/rrt_b200.h) -- an EXTENSION, dense restatement
+# ----------------------------------------------------------------------------
+def mirror_shade(spec, k, origin, rays, dist, shader):
+    """What the reflected rays of shape k's hits see, dense over the image like everything
+    else here: -> (rgb2 float64[n,n,3], hit2 int32[n,n]).  The reference has no secondary ray
+    (match_mirror.py:40,45; the hook would be scene.py:41-45), so PARITY IS UNPINNED by it; the
+    semantics are those stated in include/rrt_b200.h: world normal n_w = A^T n_o / |.|,
+    r = d - 2 (d.n_w) n_w from P = origin + t d, every OTHER shape in list order, nearest hit with
+    t2 > 0 (strict '<'), shaded by the scene's shader as seen along r."""
+    n = rays.shape[0]
+    w2o = np.asarray(spec['w2o'][k], dtype=F32)
+    A = w2o[:3, :3]
+    o, r = apply_rayfield(w2o, origin, rays)                 # object space, IMAGE index space
+    d_w = np.ascontiguousarray(rays.transpose(1, 0, 2)) if spec.get('cam_o2w') is None else rays
+    with np.errstate(all='ignore'):
+        t = np.where(np.isinf(dist), F32(0), dist).astype(F32)
+        if spec['obj_type'][k] == SPHERE:
+            p = o + t[:, :, None] * r
+            n_o = p / np.sqrt(np.sum(p * p, 2))[:, :, None]
+        else:
+            n_o = np.zeros_like(r)
+            n_o[:, :, 2] = F32(1.0) if o[2] > 0 else F32(-1.0)
+        m = np.tensordot(n_o, A, 1)                          # A^T n_o per pixel
+        n_w = m / np.sqrt(np.sum(m * m, 2))[:, :, None]
+        dn = np.sum(d_w * n_w, 2)
+        refl = (d_w - F32(2) * dn[:, :, None] * n_w).astype(F32)
+        P = (np.asarray(origin, dtype=F32)[None, None, :] + t[:, :, None] * d_w).astype(F32)
+        rgb2 = np.zeros((n, n, 3), dtype=np.float64)
+        hit2 = np.full((n, n), -1, dtype=np.int32)
+        tmin = np.full((n, n), np.inf, dtype=F32)
+        for j in range(len(spec['obj_type'])):
+            if j == k:
+                continue
+            wj = np.asarray(spec['w2o'][j], dtype=F32)
+            Aj, bj = wj[:3, :3], wj[:3, 3]
+            o2 = (np.tensordot(P, Aj.T, 1) + bj[None, None, :]).astype(F32)
+            d2 = np.tensordot(refl, Aj.T, 1).astype(F32)
+            if spec['obj_type'][j] == SPHERE:
+                pd = np.sum(d2 * o2, 2)
+                vn = np.sum(d2 * d2, 2)
+                det = np.square(pd) - vn * (np.sum(o2 * o2, 2) - F32(1))
+                t2 = (-pd - np.sqrt(det)) / vn
+                t2 = np.where((det <= 0) | np.isnan(det), F32(np.inf), t2).astype(F32)
+                p2 = o2 + np.where(np.isinf(t2), F32(0), t2)[:, :, None] * d2
+                nrm2 = p2 / np.sqrt(np.sum(p2 * p2, 2))[:, :, None]
+            else:
+                t2 = -o2[:, :, 2] / d2[:, :, 2]
+                inter = o2 + t2[:, :, None] * d2
+                mask = (inter[:, :, 0] > -0.5) & (inter[:, :, 0] < 0.5) & (inter[:, :, 1] > -0.5) & (inter[:, :, 1] < 0.5) & \
+                    (t2 > 0) & (d2[:, :, 2] != 0)
+                t2 = np.where(mask, t2, F32(np.inf)).astype(F32)
+                nrm2 = np.zeros_like(d2)
+                nrm2[:, :, 2] = np.where(o2[:, :, 2] > 0, F32(1), F32(-1))
+            t2 = np.where(t2 > 0, t2, F32(np.inf)).astype(F32)          # secondary hits must lie ahead
+            shad2 = phong_shade(nrm2, t2, spec['material'][j], spec['light_dir'], spec['light_int'],
+                                spec['look_at'], specular=(shader == 'phong'))
+            take = (t2 < tmin) & ~np.isinf(dist)
+            rgb2 = np.where(take[:, :, None], shad2, rgb2)
+            tmin = np.where(take, t2, tmin)
+            hit2[take] = j
+    return rgb2, hit2
+
+
+# ----------------------------------------------------------------------------
 # scene.py: Scene.build
 # ----------------------------------------------------------------------------
 def draw_jitter(n, samples, rng):
@@ -281,6 +345,7 @@ def render(spec, return_aux=True):
     shader = spec['shader']
     shadows = bool(spec.get('shadows', 0))
     shadow_mask = np.zeros((S, n, n), dtype=bool)
+    hit2_index = np.full((S, n, n), -1, dtype=np.int32)       # mirror bounce: what the reflected ray hit
     for s in range(S):
         sdx = (jx[:, :, s] + F32(s)) / F32(S)          # scene.py:31
         sdy = (jy[:, :, s] + F32(s)) / F32(S)          # scene.py:32
@@ -303,6 +368,11 @@ def render(spec, return_aux=True):
                 shad = phong_shade(nrm, dist, spec['material'][k], spec['light_dir'],
                                    spec['light_int'], spec['look_at'],
                                    specular=(shader == 'phong'))
+            hit2_k = None
+            if spec.get('reflectivity') is not None:                 # one mirror bounce (extension)
+                kr = float(spec['reflectivity'][k])
+                rgb2, hit2_k = mirror_shade(spec, k, origin, rays, dist, shader)
+                shad = np.where(np.isinf(dist)[:, :, None], shad, (1.0 - kr) * shad + kr * rgb2)
             in_shadow = np.zeros((n, n), dtype=bool)
             if shadows:
                 # scene.py:41-45 (commented out in the reference): for each shape != obj draw
@@ -321,11 +391,15 @@ def render(spec, return_aux=True):
             min_d = np.where(take, dist, min_d)                      # scene.py:47
             hit_index[s][take] = k
             shadow_mask[s][take] = in_shadow[take]
+            if hit2_k is not None:
+                hit2_index[s][take] = hit2_k[take]
         tmins[s] = min_d
         image = image + img_s                                        # scene.py:49
     image = image / S                                                # scene.py:50
     if return_aux:
         if shadows:
             hit_index = np.where(shadow_mask & (hit_index >= 0), hit_index | 0x40000000, hit_index)
+        if spec.get('reflectivity') is not None and return_aux == 'mirror':
+            return image, hit_index, tmins, hit2_index
         return image, hit_index, tmins
     return image

@@ -125,3 +125,22 @@ def shadow_scene(n=64, samples=4, seed=0, shader='phong', general=False):
                      ((-1., -1., 2.), (0.961, 1., 0.87)), shader, max_depth=8.0, seed=seed)
     spec['shadows'] = 1
     return spec
+
+
+def mirror_scene(n=64, samples=4, seed=0, general=False, reflectivity=(0.0, 0.6, 0.8, 0.3)):
+    """Mirror bounce (RRT_FLAG_MIRROR; an extension -- the reference has no secondary ray): match_mirror.py's
+    two spheres (the second partly reflective) in front of a reflective square 'mirror', plus a small
+    sphere only visible through reflections.  Root camera variant."""
+    m1 = _mat((0.2, 0.9, 0.4), 0.3, 0.7, 0.5, 50.)
+    m2 = _mat((0.87, 0.1, 0.507), 0.3, 0.9, 0.4, 50.)
+    m3 = _mat((0.6, 0.6, 0.9), 0.2, 0.6, 0.3, 30.)
+    s1 = on.translate((-.5, -.5, 4))
+    s2 = on.translate((.6, .5, 4.2))
+    if general:
+        s2 = _chain(s2, on.rotate(30, (0, 0, 1)), on.scale((1.1, 0.7, 0.9)))
+    sq = _chain(on.translate((0.2, 0, 6.0)), on.rotate(25, [0., 1., 0.]), on.scale((6, 6, 1)))
+    s3 = _chain(on.translate((-1.6, 0.9, 2.5)), on.scale((0.5, 0.5, 0.5)))
+    spec = spec_from(n, samples, [(on.SPHERE, s1, m1), (on.SPHERE, s2, m2), (on.SQUARE, sq, m3), (on.SPHERE, s3, m1)],
+                     ((-1., -1., 2.), (1., 0.87, 0.961)), 'phong', seed=seed)
+    spec['reflectivity'] = np.asarray(reflectivity, dtype=F32)
+    return spec

@@ -48,6 +48,7 @@ class RrtScene(C.Structure):
         ('jitter_scene_stride', C.c_int64), ('base_rays', C.c_void_p),
         ('scene_begin', C.c_int32), ('flags', C.c_int32), ('obj_records', C.c_void_p),
         ('ticket', C.c_void_p), ('det_workspace', C.c_void_p),
+        ('reflectivity', C.c_void_p), ('reflectivity_scene_stride', C.c_int64),
     ]
 
 
@@ -144,7 +145,7 @@ EXPORTS = ['rrt_version', 'rrt_last_error', 'rrt_render_forward', 'rrt_render_ba
            'rrt_peer_allreduce', 'rrt_peer_buffer_bytes', 'rrt_peer_signal_bytes', 'rrt_build_records',
            'rrt_small_step_mse']
 
-FLAG_CULL, FLAG_NO_SMALL, FLAG_SHADOWS, FLAG_SCALAR_SHADOWS, FLAG_NO_MATERIAL_GRAD, FLAG_CANONICAL_SWEEP, FLAG_DETERMINISTIC = 1, 2, 4, 8, 16, 32, 64
+FLAG_CULL, FLAG_NO_SMALL, FLAG_SHADOWS, FLAG_SCALAR_SHADOWS, FLAG_NO_MATERIAL_GRAD, FLAG_CANONICAL_SWEEP, FLAG_DETERMINISTIC, FLAG_MIRROR = 1, 2, 4, 8, 16, 32, 64, 128
 HIT_SHADOWED = 0x40000000
 CHAIN_TRANSLATE, CHAIN_SCALE, CHAIN_ROTATE, CHAIN_INVERT, CHAIN_MAX_OPS = 1, 2, 3, 0x100, 8
 

@@ -126,6 +126,12 @@ int check_scene(const rrt_scene* sc, int* rows_out) {
     if (((uintptr_t)sc->w2o & 15) || (sc->w2o_scene_stride & 3)) return fail(RRT_ERR_INVALID, "w2o must be 16-byte aligned");
     if (sc->shader == RRT_SHADER_DEPTH && !(sc->max_depth != 0.0f)) return fail(RRT_ERR_INVALID, "max_depth must be non-zero");
     if ((uintptr_t)sc->obj_records & 15) return fail(RRT_ERR_INVALID, "obj_records must be 16-byte aligned");
+    if (sc->flags & RRT_FLAG_MIRROR) {
+        if (!sc->reflectivity) return fail(RRT_ERR_INVALID, "RRT_FLAG_MIRROR needs the reflectivity table");
+        if (sc->shader == RRT_SHADER_DEPTH) return fail(RRT_ERR_UNSUPPORTED, "RRT_FLAG_MIRROR: Phong shaders only");
+        if (sc->camera_grad || !sc->transpose)
+            return fail(RRT_ERR_UNSUPPORTED, "RRT_FLAG_MIRROR: root camera variant only (identity camera.o2w, no camera gradient)");
+    }
     if ((sc->flags & RRT_FLAG_DETERMINISTIC) && (!sc->det_workspace || ((uintptr_t)sc->det_workspace & 15)))
         return fail(RRT_ERR_INVALID, "RRT_FLAG_DETERMINISTIC needs a 16-byte aligned det_workspace");
     *rows_out = rows;
@@ -357,7 +363,8 @@ int rrt_small_step_mse(const rrt_scene* scene, const rrt_step* step, const float
         return fail(RRT_ERR_INVALID, "rrt_step: bad parameter range");
     P.sc = *scene;
     if (scene->num_scenes != 1 || scene->num_objects < 1) return fail(RRT_ERR_UNSUPPORTED, "whole-step kernel: one scene, >= 1 shape");
-    if (scene->flags & RRT_FLAG_DETERMINISTIC) return fail(RRT_ERR_UNSUPPORTED, "whole-step kernel: RRT_FLAG_DETERMINISTIC is not supported");
+    if (scene->flags & (RRT_FLAG_DETERMINISTIC | RRT_FLAG_MIRROR))
+        return fail(RRT_ERR_UNSUPPORTED, "whole-step kernel: RRT_FLAG_DETERMINISTIC / RRT_FLAG_MIRROR are not supported");
     P.step = *step;
     P.target = target;
     P.cw[0] = channel_weight ? channel_weight[0] : 1.f;

@@ -77,6 +77,10 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
     const float* mats = sc.material + (size_t)scene * sc.material_scene_stride;
     float* gobj = (MODE != MODE_FWD) ? P.grad + (size_t)scene * RRT_GRAD_SIZE(N) : nullptr;
     long long* const det_ws = (MODE != MODE_FWD && (sc.flags & RRT_FLAG_DETERMINISTIC)) ? det_scene(sc, scene) : nullptr;
+    // RRT_FLAG_MIRROR (opt-in extension): needs the identity camera, Phong shaders
+    const bool mirror_on = (sc.flags & RRT_FLAG_MIRROR) && sc.reflectivity && sc.shader != RRT_SHADER_DEPTH && cam_identity &&
+                           g.ct[0] == 0.f && g.ct[1] == 0.f && g.ct[2] == 0.f;
+    const float* refl = mirror_on ? sc.reflectivity + (size_t)scene * sc.reflectivity_scene_stride : nullptr;
     // the last CTA of a scene (rrt_scene.ticket) finalises its gradients: one launch per reverse pass
     auto take_ticket = [&]() {
         if (MODE == MODE_FWD || !sc.ticket) return;
@@ -442,6 +446,13 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                 ShadeRec sr;
                 float rgb[3];
                 shade(sc.shader, sc.max_depth, ob, m7, g, h, sr, rgb);
+                if (mirror_on) {                          // one mirror bounce (extension)
+                    float rgb2[3];
+                    mirror_shade(sc.shader, sc.max_depth, w2o, mats, sc.obj_type, N, g, k, ob, h, dwx, dwy, dwz, rgb2);
+                    const float kr = __ldg(refl + k);
+#pragma unroll
+                    for (int c = 0; c < 3; c++) rgb[c] = (1.0f - kr) * rgb[c] + kr * rgb2[c];
+                }
                 const int px = r / SPT;
 #pragma unroll
                 for (int q = 0; q < PIX; q++)
@@ -572,6 +583,25 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                     acc_key = k;
                     {
                         const float rc3[3] = {l_rc[r], l_rc[kRays + r], l_rc[2 * kRays + r]};
+                        if (mirror_on) {
+                            const float kr = __ldg(refl + k);
+                            const float gc2[3] = {kr * gc[0], kr * gc[1], kr * gc[2]};
+                            const float gc1[3] = {(1.0f - kr) * gc[0], (1.0f - kr) * gc[1], (1.0f - kr) * gc[2]};
+                            float og2[19], extra[4], dA[9];
+                            const int j2 = mirror_backward<false, 19>(sc.shader, sc.max_depth, w2o, mats, sc.obj_type, N, g, k, ob, h,
+                                                                      dwx, dwy, dwz, gc2, og2, gg, extra, dA);
+                            if (j2 >= 0) {
+#pragma unroll 1
+                                for (int v = 0; v < 19; v++) {
+                                    if (og2[v] == 0.f) continue;
+                                    if (det_ws) det_add(det_ws + ((size_t)j2 * RRT_OBJ_GRAD_STRIDE + v) * 2, (double)og2[v]);
+                                    else atomicAdd(&gobj[(size_t)j2 * RRT_OBJ_GRAD_STRIDE + v], og2[v]);
+                                }
+                            }
+                            backward_ray(sc.shader, sc.max_depth, ob, m7, g, h, sr, rc3, gc1, acc, gg, j2 >= 0 ? extra : nullptr);
+#pragma unroll
+                            for (int q = 0; q < 9; q++) acc[q] += dA[q];
+                        } else
                         backward_ray(sc.shader, sc.max_depth, ob, m7, g, h, sr, rc3, gc, acc, gg);
                     }
                 }

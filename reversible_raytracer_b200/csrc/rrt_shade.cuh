@@ -195,10 +195,14 @@ __device__ __forceinline__ void shade(int shader, float max_depth, const Obj& ob
 // The chain M -> d/dA, d/d camera and Lhat -> L is applied by finalize_grads.
 // GEOM_ONLY (RRT_FLAG_NO_MATERIAL_GRAD): only og[0..11] is produced -- the material, light and
 // look_at sums are neither computed nor touched (og may then be a 12-float array).
+// Mirror bounce (RRT_FLAG_MIRROR): `extra` = {dL/d(object-space normal)[3], dL/dt} arriving through the
+// reflection (primary rays), `god` receives {g_o'[3], g_d'[3]}, `origin` is the world origin of a
+// secondary ray (o'' = A P + b also depends on A: M += g_o' P^T; valid because the camera is the identity).
 template <bool GEOM_ONLY = false, int NOG = 19>
 __device__ __forceinline__ void backward_ray(int shader, float max_depth, const Obj& ob, const float* mat,
                                              const Globals& g, const HitRec& h, const ShadeRec& r, const float rc[3],
-                                             const float gc[3], float (&og)[NOG], float* gg) {
+                                             const float gc[3], float (&og)[NOG], float* gg,
+                                             const float* extra = nullptr, float* god = nullptr, const float* origin = nullptr) {
     static_assert(NOG == (GEOM_ONLY ? 12 : 19), "backward_ray: accumulator size");
     float g_t = 0.f;
     float g_o[3] = {0.f, 0.f, 0.f}, g_d[3] = {0.f, 0.f, 0.f};
@@ -245,6 +249,11 @@ __device__ __forceinline__ void backward_ray(int shader, float max_depth, const 
 #pragma unroll
             for (int c = 0; c < 3; c++) gg[c] += g_Lh[c];
         }
+        if (extra) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) g_n[c] += extra[c];
+            g_t += extra[3];
+        }
         if (sphere) {
             float ndg = r.nrm[0] * g_n[0] + r.nrm[1] * g_n[1] + r.nrm[2] * g_n[2];
             float inv = __frcp_rn(r.pn);
@@ -276,7 +285,134 @@ __device__ __forceinline__ void backward_ray(int shader, float max_depth, const 
 #pragma unroll
     for (int rr = 0; rr < 3; rr++) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) og[rr * 3 + c] += g_d[rr] * rc[c];
+        for (int c = 0; c < 3; c++) og[rr * 3 + c] += g_d[rr] * rc[c] + (origin ? g_o[rr] * origin[c] : 0.f);
         og[9 + rr] += g_o[rr];
     }
+    if (god) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { god[c] = g_o[c]; god[3 + c] = g_d[c]; }
+    }
+}
+
+// ---------------------------------------------------------------- mirror bounce (RRT_FLAG_MIRROR)
+// Semantics in include/rrt_b200.h; canonical float32 order shared with orc_bounce_geom /
+// orc_secondary in oracle/oracle_c.c (this defines which object a reflected ray sees), shading and
+// the reverse pass at float32 tolerance.  An opt-in extension outside the roofline-accountable
+// path: scalar, per ray, out of line.
+struct Bounce {
+    float P[3], r[3], nw[3], no[3], mn, dn;
+};
+
+__device__ __forceinline__ void bounce_geom(const Obj& ob, const HitRec& h, float dwx, float dwy, float dwz, Bounce& b) {
+    if (!(ob.flags & 1)) {
+        const float p0 = __fmaf_rn(h.t, h.d[0], ob.o[0]), p1 = __fmaf_rn(h.t, h.d[1], ob.o[1]), p2 = __fmaf_rn(h.t, h.d[2], ob.o[2]);
+        const float pn = __fsqrt_rn(dot3_canon(p0, p1, p2, p0, p1, p2));
+        b.no[0] = __fdiv_rn(p0, pn); b.no[1] = __fdiv_rn(p1, pn); b.no[2] = __fdiv_rn(p2, pn);
+    } else {
+        b.no[0] = b.no[1] = 0.f;
+        b.no[2] = (ob.o[2] > 0.0f) ? 1.0f : -1.0f;
+    }
+    float m[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) m[i] = dot3_canon(ob.a[i], ob.a[3 + i], ob.a[6 + i], b.no[0], b.no[1], b.no[2]);   // A^T n_o
+    b.mn = __fsqrt_rn(dot3_canon(m[0], m[1], m[2], m[0], m[1], m[2]));
+#pragma unroll
+    for (int c = 0; c < 3; c++) b.nw[c] = __fdiv_rn(m[c], b.mn);
+    b.dn = dot3_canon(dwx, dwy, dwz, b.nw[0], b.nw[1], b.nw[2]);
+    const float k2 = __fmul_rn(-2.0f, b.dn);
+    b.r[0] = __fmaf_rn(k2, b.nw[0], dwx); b.r[1] = __fmaf_rn(k2, b.nw[1], dwy); b.r[2] = __fmaf_rn(k2, b.nw[2], dwz);
+    b.P[0] = __fmul_rn(h.t, dwx); b.P[1] = __fmul_rn(h.t, dwy); b.P[2] = __fmul_rn(h.t, dwz);
+}
+
+// nearest OTHER object along the reflected ray (list order, strict '<', t2 > 0); fills ob2 (object j2
+// re-based at origin P) and its hit record
+__device__ __noinline__ int mirror_secondary(const float* __restrict__ w2o, const int* __restrict__ obj_type, int N, int k,
+                                             const Bounce& b, Obj& ob2, HitRec& h2) {
+    float tmin = __int_as_float(0x7f800000);
+    int j2 = -1;
+#pragma unroll 1
+    for (int j = 0; j < N; j++) {
+        if (j == k) continue;
+        Obj t;
+        make_obj(w2o + (size_t)j * RRT_W2O_STRIDE, obj_type[j], b.P, t);
+        HitRec hh;
+        const float t2 = obj_test<false>(t, b.r[0], b.r[1], b.r[2], hh);
+        if (t2 > 0.0f && t2 < tmin) { tmin = t2; j2 = j; ob2 = t; h2 = hh; }
+    }
+    return j2;
+}
+
+// forward: what the reflected ray of a winning primary ray sees (0 if nothing)
+__device__ __noinline__ void mirror_shade(int shader, float max_depth, const float* __restrict__ w2o,
+                                          const float* __restrict__ mats, const int* __restrict__ obj_type, int N,
+                                          const Globals& g, int k, const Obj& ob, const HitRec& h,
+                                          float dwx, float dwy, float dwz, float rgb2[3]) {
+    Bounce b;
+    bounce_geom(ob, h, dwx, dwy, dwz, b);
+    Obj ob2;
+    HitRec h2;
+    const int j2 = mirror_secondary(w2o, obj_type, N, k, b, ob2, h2);
+    rgb2[0] = rgb2[1] = rgb2[2] = 0.f;
+    if (j2 >= 0) {
+        float m7[7];
+#pragma unroll
+        for (int q = 0; q < 7; q++) m7[q] = __ldg(mats + (size_t)j2 * RRT_MAT_STRIDE + q);
+        ShadeRec sr2;
+        shade(shader, max_depth, ob2, m7, g, h2, sr2, rgb2);
+    }
+}
+
+// reverse: the secondary object's sums og2 (for object j2 = return value, -1: none), and what flows
+// back into the primary object through the reflection: extra = {dL/d n_o [3], dL/dt}, dA[9] (direct
+// term of n_w = A^T n_o / |.|; added to the primary's M sums, which ARE d/dA for the identity camera)
+template <bool GEOM_ONLY, int NOG>
+__device__ __noinline__ int mirror_backward(int shader, float max_depth, const float* __restrict__ w2o,
+                                            const float* __restrict__ mats, const int* __restrict__ obj_type, int N,
+                                            const Globals& g, int k, const Obj& ob, const HitRec& h,
+                                            float dwx, float dwy, float dwz, const float gc2[3],
+                                            float (&og2)[NOG], float* gg, float extra[4], float dA[9]) {
+    Bounce b;
+    bounce_geom(ob, h, dwx, dwy, dwz, b);
+    Obj ob2;
+    HitRec h2;
+    const int j2 = mirror_secondary(w2o, obj_type, N, k, b, ob2, h2);
+#pragma unroll
+    for (int v = 0; v < NOG; v++) og2[v] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; q++) extra[q] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 9; q++) dA[q] = 0.f;
+    if (j2 < 0) return -1;
+    float m7[7];
+#pragma unroll
+    for (int q = 0; q < 7; q++) m7[q] = __ldg(mats + (size_t)j2 * RRT_MAT_STRIDE + q);
+    ShadeRec sr2;
+    float rgb2[3], god[6];
+    shade(shader, max_depth, ob2, m7, g, h2, sr2, rgb2);
+    backward_ray<GEOM_ONLY, NOG>(shader, max_depth, ob2, m7, g, h2, sr2, b.r, gc2, og2, gg, nullptr, god, b.P);
+    float GP[3], Gr[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {                      // A_j2^T g_o'', A_j2^T g_d''
+        GP[c] = ob2.a[c] * god[0] + ob2.a[3 + c] * god[1] + ob2.a[6 + c] * god[2];
+        Gr[c] = ob2.a[c] * god[3] + ob2.a[3 + c] * god[4] + ob2.a[6 + c] * god[5];
+    }
+    const float dw[3] = {dwx, dwy, dwz};
+    extra[3] = GP[0] * dwx + GP[1] * dwy + GP[2] * dwz;                        // P = t d
+    const float grn = Gr[0] * b.nw[0] + Gr[1] * b.nw[1] + Gr[2] * b.nw[2];
+    float g_nw[3], dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; c++) { g_nw[c] = -2.0f * (b.dn * Gr[c] + grn * dw[c]); dot += b.nw[c] * g_nw[c]; }   // r = d - 2 (d.n) n
+    float g_m[3];
+    const float imn = 1.0f / b.mn;
+#pragma unroll
+    for (int c = 0; c < 3; c++) g_m[c] = (g_nw[c] - b.nw[c] * dot) * imn;      // n_w = m/|m|
+#pragma unroll
+    for (int rr = 0; rr < 3; rr++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) dA[rr * 3 + i] = b.no[rr] * g_m[i];         // m = A^T n_o
+    if (!(ob.flags & 1)) {
+#pragma unroll
+        for (int rr = 0; rr < 3; rr++) extra[rr] = ob.a[rr * 3] * g_m[0] + ob.a[rr * 3 + 1] * g_m[1] + ob.a[rr * 3 + 2] * g_m[2];
+    }
+    return j2;
 }

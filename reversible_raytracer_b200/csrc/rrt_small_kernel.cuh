@@ -99,6 +99,11 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
     unsigned scene_items = 0;                          // items of cur_scene processed by this CTA
     float* gobj = nullptr;
     long long* det_ws = nullptr;                       // RRT_FLAG_DETERMINISTIC: fixed-point sums of cur_scene
+    // RRT_FLAG_MIRROR (opt-in extension): scene tables the secondary rays read; requires the identity camera
+    const bool mirror_on = !STEP && (sc.flags & RRT_FLAG_MIRROR) && sc.reflectivity && sc.shader != RRT_SHADER_DEPTH;
+    const float* w2o_s = nullptr;
+    const float* mats_g = nullptr;
+    const float* refl_s = nullptr;
 
     // ---- end of a scene's items on this CTA: thread -> warp -> CTA -> global, ticket, finalisation
     auto flush_scene = [&](bool reduced) {
@@ -220,6 +225,9 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
                 store_rec(tab + 4 * tid, ob);
             }
             for (int q = tid; q < N * RRT_MAT_STRIDE; q += kSmallThreads) mat_s[q] = __ldg(mats + q);
+            w2o_s = w2o;
+            mats_g = mats;
+            refl_s = mirror_on ? sc.reflectivity + (size_t)scene * sc.reflectivity_scene_stride : nullptr;
             if (MODE != MODE_FWD) {
                 for (int q = tid; q < N * kSlotStride; q += kSmallThreads) slots[q] = 0.f;
                 if (tid < 9) gglob[tid] = 0.f;
@@ -249,6 +257,7 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
             __syncthreads();
         }
         scene_items++;
+        const bool mir = mirror_on && g.cam_identity && g.ct[0] == 0.f && g.ct[1] == 0.f && g.ct[2] == 0.f;
 
         const unsigned gid = blk * kSmallThreads + tid;      // ray index within the scene: [rows][n][S]
         const bool active = gid < rays_scene;
@@ -356,6 +365,13 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
 #pragma unroll
             for (int q = 0; q < 7; q++) m7[q] = mat_s[idx * RRT_MAT_STRIDE + q];
             shade(sc.shader, sc.max_depth, ob, m7, g, h, sr, rgb);
+            if (MODE != MODE_BWD && mir) {       // one mirror bounce (extension)
+                float rgb2[3];
+                mirror_shade(sc.shader, sc.max_depth, w2o_s, mats_g, sc.obj_type, N, g, idx, ob, h, wx, wy, wz, rgb2);
+                const float kr = __ldg(refl_s + idx);
+#pragma unroll
+                for (int c = 0; c < 3; c++) rgb[c] = (1.0f - kr) * rgb[c] + kr * rgb2[c];
+            }
         }
 
         if (MODE != MODE_BWD) {
@@ -401,6 +417,27 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
                 for (int v = 0; v < NACC; v++) da[v] = 0.f;
 #pragma unroll
                 for (int v = 0; v < 9; v++) dg[v] = 0.f;
+                if (mir) {
+                    // secondary object first (its sums go straight to its CTA slot / the fixed-point
+                    // workspace), then the primary one with the chain through the reflection
+                    const float kr = __ldg(refl_s + key);
+                    const float gc2[3] = {kr * gc[0], kr * gc[1], kr * gc[2]};
+                    const float gc1[3] = {(1.0f - kr) * gc[0], (1.0f - kr) * gc[1], (1.0f - kr) * gc[2]};
+                    float og2[NACC], extra[4], dA[9];
+                    const int j2 = mirror_backward<GEOM, NACC>(sc.shader, sc.max_depth, w2o_s, mats_g, sc.obj_type, N, g, key, ob, h,
+                                                               wx, wy, wz, gc2, og2, dg, extra, dA);
+                    if (j2 >= 0) {
+#pragma unroll 1
+                        for (int v = 0; v < NACC; v++) {
+                            if (og2[v] == 0.f) continue;
+                            if (det_ws) det_add(det_ws + ((size_t)j2 * RRT_OBJ_GRAD_STRIDE + v) * 2, (double)og2[v]);
+                            else atomicAdd(&slots[j2 * kSlotStride + v], og2[v]);
+                        }
+                    }
+                    backward_ray<GEOM, NACC>(sc.shader, sc.max_depth, ob, m7, g, h, sr, rc3, gc1, da, dg, j2 >= 0 ? extra : nullptr);
+#pragma unroll
+                    for (int q = 0; q < 9; q++) da[q] += dA[q];
+                } else
                 backward_ray<GEOM, NACC>(sc.shader, sc.max_depth, ob, m7, g, h, sr, rc3, gc, da, dg);
 #pragma unroll
                 for (int v = 0; v < NACC; v++) acc_col[v * kSmallThreads] += da[v];

@@ -54,6 +54,8 @@ class _WholeStep(object):
             raise ValueError('needs chain-expressible shape transforms with parameters and a constant camera')
         if st['mat'] is None or st['light_t'] is None:
             raise ValueError('materials and light must be constants')
+        if st['refl'] is not None:
+            raise ValueError('the mirror bounce is not supported by the whole-step kernel')
         if {id(p) for p in prog.param_tensors} != {id(v) for v in tVars}:
             raise ValueError('the optimised variables must be exactly the parameters of the shape transforms')
         cfg = scene.config(spec['antialias_samples'], cull=False)

@@ -102,7 +102,7 @@ def base_rays(n, device):
 class _Tables:
     """Packed device tables + the rrt_scene descriptor that points at them."""
 
-    def __init__(self, cfg, obj_type, w2o, material, light, camera, jitter=None):
+    def __init__(self, cfg, obj_type, w2o, material, light, camera, jitter=None, reflectivity=None):
         w2o = _f32(w2o, 'w2o')
         self.batched = w2o.dim() == 3
         if not self.batched:
@@ -136,7 +136,15 @@ class _Tables:
         d.shader, d.transpose = cfg.shader, cfg.transpose
         d.row_begin, d.row_count = cfg.row_begin, cfg.row_count
         d.scene_begin = cfg.scene_begin
-        d.flags = ((nat.FLAG_CULL if cfg.cull else 0) | (nat.FLAG_NO_SMALL if cfg.no_small else 0) |
+        # mirror bounce (RRT_FLAG_MIRROR, an extension): per-object reflectivity [N] or [B,N], a constant
+        self.reflectivity = None
+        if reflectivity is not None:
+            self.reflectivity = _f32(reflectivity, 'reflectivity').reshape(-1, self.N)
+            if self.reflectivity.shape[0] not in (1, self.B):
+                raise ValueError('reflectivity must be [N] or [B, N]')
+            if not cfg.transpose or cfg.camera_grad:
+                raise nat.NativeError('the mirror bounce supports the root camera variant only (identity camera)')
+        d.flags = ((nat.FLAG_MIRROR if self.reflectivity is not None else 0) | (nat.FLAG_CULL if cfg.cull else 0) | (nat.FLAG_NO_SMALL if cfg.no_small else 0) |
                    (nat.FLAG_SHADOWS if cfg.shadows else 0) | (nat.FLAG_SCALAR_SHADOWS if cfg.shadows == 2 else 0) |
                    (nat.FLAG_NO_MATERIAL_GRAD if cfg.geom_grad_only else 0) |
                    (nat.FLAG_CANONICAL_SWEEP if cfg.canonical_sweep else 0) |
@@ -156,6 +164,9 @@ class _Tables:
         if cfg.n <= BASE_RAYS_MAX_N:
             self.base = base_rays(cfg.n, self.device)
             d.base_rays = self.base.data_ptr()
+        if self.reflectivity is not None:
+            d.reflectivity = self.reflectivity.data_ptr()
+            d.reflectivity_scene_stride = 0 if self.reflectivity.shape[0] == 1 else self.N
         self.det_ws = None
         if cfg.deterministic:
             with torch.cuda.device(self.device):
@@ -177,9 +188,11 @@ class _Tables:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
 
-def render_forward(cfg, obj_type, w2o, material, light, camera, jitter=None, want_hit=True, want_tmin=False):
-    """-> image [B,rows,n,3] (or [rows,n,3] when w2o is unbatched), hit_index, tmin."""
-    T = _Tables(cfg, obj_type, w2o, material, light, camera, jitter)
+def render_forward(cfg, obj_type, w2o, material, light, camera, jitter=None, want_hit=True, want_tmin=False,
+                   reflectivity=None):
+    """-> image [B,rows,n,3] (or [rows,n,3] when w2o is unbatched), hit_index, tmin.
+    `reflectivity` [N]: one mirror bounce (RRT_FLAG_MIRROR in include/rrt_b200.h; an extension)."""
+    T = _Tables(cfg, obj_type, w2o, material, light, camera, jitter, reflectivity)
     with torch.cuda.device(T.device):
         image = torch.empty((T.B, cfg.rows, cfg.n, 3), dtype=torch.float32, device=T.device)
         hit = torch.empty((T.B, cfg.samples, cfg.rows, cfg.n), dtype=torch.int32, device=T.device) if want_hit else None
@@ -195,9 +208,9 @@ def render_forward(cfg, obj_type, w2o, material, light, camera, jitter=None, wan
     return image, hit, tmin
 
 
-def render_backward(cfg, obj_type, w2o, material, light, camera, dl_dimage, hit_index=None, jitter=None):
+def render_backward(cfg, obj_type, w2o, material, light, camera, dl_dimage, hit_index=None, jitter=None, reflectivity=None):
     """-> flat gradient [B, N*19+21] (layout: include/rrt_b200.h)."""
-    T = _Tables(cfg, obj_type, w2o, material, light, camera, jitter)
+    T = _Tables(cfg, obj_type, w2o, material, light, camera, jitter, reflectivity)
     dl = _f32(dl_dimage, 'dl_dimage')
     if dl.numel() != T.B * cfg.rows * cfg.n * 3:
         raise ValueError('dl_dimage must be [B, rows, n, 3]')
@@ -215,10 +228,10 @@ def render_backward(cfg, obj_type, w2o, material, light, camera, dl_dimage, hit_
 
 
 def render_fused_mse(cfg, obj_type, w2o, material, light, camera, target, channel_weight=None, jitter=None,
-                     want_image=False, want_hit=False):
+                     want_image=False, want_hit=False, reflectivity=None):
     """Fused forward + sum_c w_c*sum((image-target)^2) + reverse pass, one kernel.
     -> loss float64 [B], grad float32 [B, N*19+21], image or None, hit_index or None."""
-    T = _Tables(cfg, obj_type, w2o, material, light, camera, jitter)
+    T = _Tables(cfg, obj_type, w2o, material, light, camera, jitter, reflectivity)
     tg = _f32(target, 'target')
     if tg.numel() != T.B * cfg.rows * cfg.n * 3:
         raise ValueError('target must be [B, rows, n, 3]')
@@ -355,9 +368,9 @@ class _RenderFn(torch.autograd.Function):
     """image = render(w2o, material, light, camera); backward = the reverse-pass kernel."""
 
     @staticmethod
-    def forward(ctx, w2o, material, light, camera, cfg, obj_type, jitter):
-        image, hit, _ = render_forward(cfg, obj_type, w2o, material, light, camera, jitter, want_hit=True)
-        ctx.cfg, ctx.obj_type, ctx.jitter = cfg, obj_type, jitter
+    def forward(ctx, w2o, material, light, camera, cfg, obj_type, jitter, reflectivity=None):
+        image, hit, _ = render_forward(cfg, obj_type, w2o, material, light, camera, jitter, want_hit=True, reflectivity=reflectivity)
+        ctx.cfg, ctx.obj_type, ctx.jitter, ctx.reflectivity = cfg, obj_type, jitter, reflectivity
         ctx.save_for_backward(w2o, material, light, camera, hit)
         ctx.shapes = (w2o.shape, material.shape, light.shape, camera.shape)
         return image
@@ -366,7 +379,7 @@ class _RenderFn(torch.autograd.Function):
     def backward(ctx, dl_dimage):
         w2o, material, light, camera, hit = ctx.saved_tensors
         N = w2o.shape[-2]
-        flat = render_backward(ctx.cfg, ctx.obj_type, w2o, material, light, camera, dl_dimage, hit, ctx.jitter)
+        flat = render_backward(ctx.cfg, ctx.obj_type, w2o, material, light, camera, dl_dimage, hit, ctx.jitter, ctx.reflectivity)
         gw, gm, gl, gc = split_grad(flat, N)
         shp = ctx.shapes
 
@@ -377,13 +390,13 @@ class _RenderFn(torch.autograd.Function):
             if g.shape != shape and g.dim() == len(shape) and shape[0] == 1 and g.shape[0] != 1:
                 g = g.sum(0, keepdim=True)
             return g.reshape(shape)
-        return fit(gw, shp[0]), fit(gm, shp[1]), fit(gl, shp[2]), fit(gc, shp[3]), None, None, None
+        return fit(gw, shp[0]), fit(gm, shp[1]), fit(gl, shp[2]), fit(gc, shp[3]), None, None, None, None
 
 
-def render(cfg, obj_type, w2o, material, light, camera, jitter=None):
+def render(cfg, obj_type, w2o, material, light, camera, jitter=None, reflectivity=None):
     """Differentiable render: image [B,rows,n,3] / [rows,n,3] with autograd to the
     four parameter tables."""
-    return _RenderFn.apply(w2o, material, light, camera, cfg, obj_type, jitter)
+    return _RenderFn.apply(w2o, material, light, camera, cfg, obj_type, jitter, reflectivity)
 
 
 def w2o_translate_scale(centres, scales):

@@ -49,7 +49,11 @@ def _obj_type_tensor(kinds, device):
 class Material(object):
     """scene.py:89-101"""
 
-    def __init__(self, color, ks, kd, ka, shininess):
+    def __init__(self, color, ks, kd, ka, shininess, reflectivity=0.0):
+        """`reflectivity` (extension, default 0 = the reference's behaviour): mirror coefficient k in
+        [0,1] of one reflection bounce, rgb = (1-k) rgb + k rgb_seen_along_the_reflected_ray
+        (RRT_FLAG_MIRROR in include/rrt_b200.h; a constant, root camera variant only)."""
+        self.reflectivity = float(reflectivity)
         # live parameters (torch tensors) are re-read on every build; constants are packed once
         self.dynamic = any(isinstance(v, torch.Tensor) for v in (color, ks, kd, ka, shininess))
         self.ks = as_tensor(ks)
@@ -246,6 +250,8 @@ class Scene(object):
         if shapes and not any(s.material.dynamic for s in shapes):
             st['mat'] = torch.stack([s.material.packed(device) for s in shapes]).detach()
         st['light_t'] = None if self.lights[0].dynamic else self.lights[0].packed(device).detach()
+        refl = [float(getattr(s.material, 'reflectivity', 0.0)) for s in shapes]
+        st['refl'] = as_tensor(np.asarray(refl, dtype=np.float32), device=device) if any(r != 0.0 for r in refl) else None
         self._cache = st
         return st
 
@@ -316,6 +322,7 @@ class Scene(object):
         tables = self.pack(device)
         jit = self._jitter_for(cfg.n, cfg.samples, jitter, seed, device)
         self.camera._rays, self.camera._last_sample = None, ('lazy', jit, cfg.samples, not self.camera.has_transform)
+        self._refl = self._static(device)['refl']          # mirror bounce (Material.reflectivity), or None
         return device, cfg, tables, jit
 
     def build(self, antialias_samples=4, jitter=None, seed=None, cull=None):
@@ -323,7 +330,7 @@ class Scene(object):
         GPU, differentiable w.r.t. shape transforms, materials, the light and (orbit
         variant) the camera transform."""
         device, cfg, (obj_type, w2o, mat, light, cam), jit = self._prepare(antialias_samples, jitter, seed, cull)
-        return R.render(cfg, obj_type, w2o, mat, light, cam, jit)
+        return R.render(cfg, obj_type, w2o, mat, light, cam, jit, self._refl)
 
     def build_mse(self, target, antialias_samples=4, channel_weight=None, jitter=None, seed=None,
                   want_image=False, cull=None):
@@ -333,7 +340,7 @@ class Scene(object):
         the detached image."""
         device, cfg, (obj_type, w2o, mat, light, cam), jit = self._prepare(antialias_samples, jitter, seed, cull)
         loss, image = _FusedMSE.apply(w2o, mat, light, cam, cfg, obj_type, jit,
-                                      as_tensor(target).to(device), channel_weight, want_image)
+                                      as_tensor(target).to(device), channel_weight, want_image, self._refl)
         return (loss, image) if want_image else loss
 
     def mse_cost(self, target, antialias_samples=4, channel_weight=None, jitter=None, seed=None):
@@ -352,9 +359,9 @@ class Scene(object):
 
 class _FusedMSE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, w2o, mat, light, cam, cfg, obj_type, jit, target, channel_weight, want_image):
+    def forward(ctx, w2o, mat, light, cam, cfg, obj_type, jit, target, channel_weight, want_image, reflectivity=None):
         loss, grad, image, _ = R.render_fused_mse(cfg, obj_type, w2o, mat, light, cam, target, channel_weight, jit,
-                                                  want_image=want_image)
+                                                  want_image=want_image, reflectivity=reflectivity)
         ctx.N = w2o.shape[-2]
         ctx.save_for_backward(grad)
         if image is None:
@@ -366,4 +373,4 @@ class _FusedMSE(torch.autograd.Function):
     def backward(ctx, g_loss, _g_image):
         (grad,) = ctx.saved_tensors
         gw, gm, gl, gc = R.split_grad(grad * g_loss, ctx.N)
-        return gw, gm, gl, gc, None, None, None, None, None, None
+        return gw, gm, gl, gc, None, None, None, None, None, None, None

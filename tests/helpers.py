@@ -25,6 +25,12 @@ def to_device(ps, device, with_jitter=True):
     return cfg, t(ps.obj_type), w2o, t(ps.material), t(ps.light), t(ps.camera), jitter
 
 
+def reflectivity_of(ps, device):
+    """mirror bounce: the PackedScene's per-object reflectivity as a device tensor, or None"""
+    r = getattr(ps, 'reflectivity', None)
+    return None if r is None else torch.from_numpy(np.ascontiguousarray(r)).to(device)
+
+
 def block_rel_err(a, b):
     """max |a-b| / max |b| over one parameter block (gradient tolerance metric)."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)

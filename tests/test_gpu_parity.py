@@ -793,3 +793,42 @@ def test_deterministic_mode_batch_and_streamed(cuda):
         torch.cuda.synchronize()
         outs.append((l.clone(), g.clone()))
     assert all(torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) for o in outs[1:])
+
+
+@pytest.mark.parametrize('general', [False, True])
+def test_mirror_bounce_parity(general, cuda):
+    """RRT_FLAG_MIRROR (one reflection bounce; an extension, PARITY UNPINNED by the reference, pinned by
+    the dense NumPy restatement, float64 autograd and finite differences in tests/test_oracle_golden.py):
+    the kernels against the C oracle -- primary masks bit-exact, pixels rtol 1e-4 (the secondary hit
+    of every reflected ray is decided in canonical float32 order on both sides), gradients <= 1e-3
+    per block.  Forward, backward (stored and re-swept winners) and fused entry points, both kernels."""
+    from helpers import reflectivity_of
+    spec = scenes.mirror_scene(n=64, general=general)
+    ps = oc.PackedScene.from_spec(spec, camera_grad=0)
+    img_o, hit_o, hit2_o = oc.render_forward_secondary(ps)
+    assert (hit2_o >= 0).mean() > 0.03                          # reflections are actually visible
+    cfg, ot, w2o, mat, light, cam, jit = to_device(ps, cuda)
+    refl = reflectivity_of(ps, cuda)
+    img, hit, _ = R.render_forward(cfg, ot, w2o, mat, light, cam, jit, reflectivity=refl)
+    assert np.array_equal(hit.cpu().numpy().reshape(hit_o.shape), hit_o)
+    np.testing.assert_allclose(img.cpu().numpy().reshape(img_o.shape), img_o, rtol=PIX_RTOL, atol=PIX_ATOL)
+    plain, _, _ = R.render_forward(cfg, ot, w2o, mat, light, cam, jit)
+    assert float((plain - img).abs().max()) > 0.1               # the flag changes the picture
+    rng = np.random.RandomState(3)
+    dl = rng.normal(size=img_o[0].shape).astype(np.float32)
+    grad_o = oc.render_backward(ps, dl, hit_o)
+    for stored in (hit, None):
+        g = R.render_backward(cfg, ot, w2o, mat, light, cam, torch.from_numpy(dl).to(cuda), stored, jit, reflectivity=refl)
+        compare_grads(g.cpu().numpy().astype(np.float64), grad_o[0], ps.N)
+    target = np.clip(img_o[0] + rng.normal(0, 0.1, img_o[0].shape), 0, 1).astype(np.float32)
+    image_o, _, loss_o, gradf_o = oc.render_fused_mse(ps, target)
+    loss, grad, image, _ = R.render_fused_mse(cfg, ot, w2o, mat, light, cam, torch.from_numpy(target).to(cuda), None, jit,
+                                              want_image=True, reflectivity=refl)
+    np.testing.assert_allclose(image.cpu().numpy().reshape(image_o.shape), image_o, rtol=PIX_RTOL, atol=PIX_ATOL)
+    np.testing.assert_allclose(float(loss), loss_o[0], rtol=1e-4)
+    compare_grads(grad.cpu().numpy().astype(np.float64), gradf_o[0], ps.N)
+    # deterministic mode covers the bounce, too
+    c = replace(cfg, deterministic=1)
+    a = R.render_fused_mse(c, ot, w2o, mat, light, cam, torch.from_numpy(target).to(cuda), None, jit, reflectivity=refl)
+    b = R.render_fused_mse(c, ot, w2o, mat, light, cam, torch.from_numpy(target).to(cuda), None, jit, reflectivity=refl)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])

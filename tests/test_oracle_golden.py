@@ -370,3 +370,71 @@ def test_depth_shader_pinned_to_reference_depth_renders(which):
         assert inner.sum() > 700
         assert d[inner].max() <= interior_tol, (which, name, d[inner].max())
         assert (d > 8).sum() <= max_out, (which, name, int((d > 8).sum()))
+
+
+# ---- mirror bounce (RRT_FLAG_MIRROR): an EXTENSION with no reference at all -- match_mirror.py:40,45
+# matches an image to its left-right flip, the hook would be scene.py:41-45 / shader.py:43-45 -- so
+# PARITY IS UNPINNED by the reference.  Pinned by: dense NumPy restatement == canonical C (masks and
+# images), closed-form reverse pass == float64 autograd, autograd == central finite differences.
+@pytest.mark.parametrize('general', [False, True])
+def test_mirror_c_oracle_vs_numpy_oracle(general):
+    spec = scenes.mirror_scene(n=64, general=general)
+    img_n, hit_n, _, hit2_n = on.render(spec, return_aux='mirror')
+    ps = oc.PackedScene.from_spec(spec)
+    img_c, hit_c, hit2_c = oc.render_forward_secondary(ps)
+    assert (hit2_c >= 0).mean() > 0.03 and set(np.unique(hit2_c)) >= {-1, 0, 1, 2, 3}     # every object is seen in some mirror
+    assert (hit_n != hit_c[0]).sum() <= 2 and (hit2_n != hit2_c[0]).sum() <= 6            # FMA vs no-FMA edge rays
+    d = np.abs(img_n - img_c[0])
+    assert (d > 1e-4).sum() <= 24 and np.median(d) < 1e-6
+    # and the flag is not a no-op, nor does it touch rays that hit nothing
+    plain = dict(spec)
+    plain.pop('reflectivity')
+    img_p = on.render(plain, return_aux=False)
+    assert np.abs(img_p - img_n).max() > 0.1
+    assert np.all(img_n[(hit_n < 0).all(0)] == 0)
+
+
+@pytest.mark.parametrize('general', [False, True])
+def test_mirror_closed_form_equals_autograd(general):
+    """The closed-form reverse pass through the bounce (secondary object; P, r, n_w chain into the
+    primary object's transform) == float64 autograd of the same forward with constant masks."""
+    spec = scenes.mirror_scene(n=40, general=general)
+    ps = oc.PackedScene.from_spec(spec, camera_grad=0)
+    img, hit, hit2 = oc.render_forward_secondary(ps)
+    dl = np.random.RandomState(1).normal(size=img[0].shape).astype(np.float32)
+    oc.lib().orc_set_f64_record(1)
+    try:
+        grad = oc.render_backward(ps, dl, hit)
+    finally:
+        oc.lib().orc_set_f64_record(0)
+    dlt = torch.from_numpy(dl).double()
+    _, im, g = og.gradients(spec, hit[0], lambda im_: (im_ * dlt).sum(), hit2_index=hit2[0])
+    assert np.abs(im - img[0]).max() < 1e-4
+    gc = oc.split_grad(grad[0], ps.N)
+    for k in ('w2o', 'material', 'light_dir', 'light_int', 'look_at'):
+        ref, a = g[k], gc[k]
+        if k == 'w2o':
+            ref = ref[:, :3, :]
+        if k == 'material':
+            ref, a = np.delete(ref, 3, 1), np.delete(a, 3, 1)
+        assert np.max(np.abs(a - ref)) <= 1e-10 * np.max(np.abs(ref)), k
+
+
+def test_mirror_autograd_finite_differences():
+    spec = scenes.mirror_scene(n=32)
+    ps = oc.PackedScene.from_spec(spec, camera_grad=0)
+    _, hit, hit2 = oc.render_forward_secondary(ps)
+    w = torch.from_numpy(np.random.RandomState(3).normal(size=(32, 32, 3)))
+    loss_fn = lambda im: (im * w).sum()
+    _, _, g = og.gradients(spec, hit[0], loss_fn, hit2_index=hit2[0])
+
+    def f(name, index, eps):
+        p = og.leaf_params(spec)
+        with torch.no_grad():
+            p[name][index] += eps
+            return float(loss_fn(og.forward(spec, p, hit[0], hit2_index=hit2[0])))
+    for name, index in (('w2o', (0, 0, 3)), ('w2o', (1, 1, 3)), ('w2o', (1, 0, 0)), ('w2o', (2, 2, 3)), ('w2o', (2, 0, 2)),
+                        ('w2o', (3, 1, 3)), ('material', (3, 1)), ('material', (0, 5)), ('light_dir', (0,)), ('look_at', (1,))):
+        eps = 1e-8 if name == 'w2o' else 1e-6
+        fd = (f(name, index, eps) - f(name, index, -eps)) / (2 * eps)
+        assert abs(fd - g[name][index]) <= 2e-4 * max(1.0, abs(fd)), (name, index, fd, g[name][index])
