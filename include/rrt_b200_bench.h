@@ -21,7 +21,9 @@ extern "C" {
  *   mode 2  FFMA2 + one ALU-pipe FMNMX3 per 4 FFMA2       (does anything issue in an FFMA2's shadow?)
  *   mode 3  FFMA2 + one broadcast LDS.128 per 8 FFMA2     (object constants from shared memory)
  *   mode 4  FFMA2 + one LDC (constant bank, uniform dynamic address) per 8 FFMA2
- *   mode 5  the quadric pre-filter's mix: 24 FFMA2 : 4 FMNMX3 : 1.5 LDS.128
+ *   mode 5  a pre-filter-like mix: 24 FFMA2 : 4 FMNMX3 : 1.5 LDS.128
+ *   mode 6  FFMA2 with multiplier and addend as scalar-broadcast (.F32) operands (the pre-filter's Horner steps)
+ *   mode 7  FFMA2 with a broadcast multiplier and a pre-duplicated packed addend
  * tflops counts 2 flops per FMA lane (the other instructions are overhead, not credited).
  * Synchronises the stream.  tflops / ms are HOST pointers.  Returns 0, or -1 (bad argument),
  * -2 (CUDA error).

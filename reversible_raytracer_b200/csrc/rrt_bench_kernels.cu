@@ -23,6 +23,7 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
     asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
+__device__ __forceinline__ u64 bc(float v) { return pk(v, v); }
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
@@ -60,6 +61,16 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, f
     // loaded operands are consumed one load LATER (bn/cn -> b/c), like the software-pipelined
     // object loop of the render kernel: the load latency is off the FMA dependency chains
     u64 bn = b, cn = c;
+    // run-time scalars (not foldable into immediates) for the operand-form modes
+    float sx[4], sy[4];
+    u64 sp[4];
+    {
+        const float4 v0 = tab[threadIdx.x & 7], v1 = tab[8 + (threadIdx.x & 7)];
+        sx[0] = v0.x; sx[1] = v0.z; sx[2] = v1.x; sx[3] = v1.z;
+        sy[0] = v0.y; sy[1] = v0.w; sy[2] = v1.y; sy[3] = v1.w;
+#pragma unroll
+        for (int i = 0; i < 4; i++) sp[i] = pk(sy[i], sy[i]);
+    }
     float m = 0.f;
     uint32_t sbase = (uint32_t)__cvta_generic_to_shared(tab);
     asm volatile("mov.u32 %0, %0;" : "+r"(sbase));
@@ -70,6 +81,14 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, f
         for (int rep = 0; rep < 8; rep++) {
 #pragma unroll
             for (int q = 0; q < 16; q++) {
+                if (MODE == 6) {            // multiplier AND addend as scalar-broadcast (.F32) operands, like the pre-filter's Horner steps
+                    a[q] = fma2(bc(sx[q & 3]), a[q], bc(sy[q & 3]));
+                    continue;
+                }
+                if (MODE == 7) {            // multiplier broadcast, addend a pre-duplicated packed pair
+                    a[q] = fma2(bc(sx[q & 3]), a[q], sp[q & 3]);
+                    continue;
+                }
                 a[q] = fma2(a[q], b, c);
                 if (MODE == 2 && (q & 3) == 3) {
                     float lo, hi;
@@ -121,7 +140,7 @@ void launch(int blocks, float* out, int iters, cudaStream_t st) {
 }  // namespace
 
 extern "C" int rrt_bench_fp32_peak(int mode, int iters, double* tflops, double* ms, void* stream) {
-    if (!tflops || iters <= 0 || mode < 0 || mode > 5) return -1;
+    if (!tflops || iters <= 0 || mode < 0 || mode > 7) return -1;
     cudaStream_t st = (cudaStream_t)stream;
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
@@ -144,7 +163,9 @@ extern "C" int rrt_bench_fp32_peak(int mode, int iters, double* tflops, double* 
             case 2: launch<2>(blocks, out, iters, st); break;
             case 3: launch<3>(blocks, out, iters, st); break;
             case 4: launch<4>(blocks, out, iters, st); break;
-            default: launch<5>(blocks, out, iters, st); break;
+            case 5: launch<5>(blocks, out, iters, st); break;
+            case 6: launch<6>(blocks, out, iters, st); break;
+            default: launch<7>(blocks, out, iters, st); break;
         }
         cudaEventRecord(e1, st);
         cudaEventSynchronize(e1);

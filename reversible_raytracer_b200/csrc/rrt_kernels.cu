@@ -57,7 +57,7 @@ constexpr int kRays = RRT_RAYS;   // rays per thread (kRays/2 packed pairs)
 #define RRT_SWEEP_UNROLL 1
 #endif
 #ifndef RRT_MIN_BLOCKS
-#define RRT_MIN_BLOCKS 4   // 128 registers: the pre-filter sweep keeps 5 packed monomials per ray pair (40 registers)
+#define RRT_MIN_BLOCKS 5   // 96 registers; only one packed ray set (canonical: 12 pairs, pre-filter: 8 pairs) is live per sweep
 #endif
 #ifndef RRT_MAX_WARPS
 #define RRT_MAX_WARPS 4

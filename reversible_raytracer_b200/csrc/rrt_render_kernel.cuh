@@ -168,7 +168,6 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
         int l_idx[kRays];
         __align__(16) float l_uv[2 * kRays];          // (u, v) = (d_x/d_z, d_y/d_z) of the pre-filter: [u0..u7 | v0..v7]
         bool rays_safe = true;                        // every ray inside the range the pre-filter's bound is proven for
-        RayPack rp;
         // rolled on purpose (code size: this runs once per thread; instruction-cache misses
         // dominate small-scene workloads otherwise)
 #pragma unroll 1
@@ -223,26 +222,13 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
             l_tmin[r] = __int_as_float(0x7f800000);
             l_idx[r] = -1;
         }
-        {
-            const u64* dp = reinterpret_cast<const u64*>(l_dw);   // (x0,x1) (x2,x3) ... pairs
-#pragma unroll
-            for (int p = 0; p < kRays / 2; p++) { rp.dx[p] = dp[p]; rp.dy[p] = dp[kRays / 2 + p]; rp.dz[p] = dp[kRays + p]; }
-        }
-
         const bool use_stored = (MODE == MODE_BWD) && (P.hit_in != nullptr);
         const bool cull = (sc.flags & RRT_FLAG_CULL) && !use_stored;
         // conservative pre-filter sweep (default with a prebuilt table): CTA-wide decision, because the
         // shared-memory chunk then holds pre-filter rows instead of records
         bool use_q = false;
-        RayQ rq;
-        if (sc.obj_records && !cull && !use_stored && !(sc.flags & RRT_FLAG_CANONICAL_SWEEP)) {
+        if (sc.obj_records && !cull && !use_stored && !(sc.flags & RRT_FLAG_CANONICAL_SWEEP))
             use_q = __syncthreads_and(rays_safe);
-            if (use_q) {
-                const u64* up = reinterpret_cast<const u64*>(l_uv);
-#pragma unroll
-                for (int p = 0; p < kRays / 2; p++) { rq.u[p] = up[p]; rq.v[p] = up[kRays / 2 + p]; }
-            }
-        }
         bool staged_quadrics = false;                 // the staged chunk does not hold records (shadow pass restages)
         if (cull) {   // ---- bounding cone of this CTA's rays (exact min/max of the rays built above)
             const float big = 3.0e38f;
@@ -350,9 +336,23 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                 __syncthreads();
                 if (staged_by_tma && tid == 0) tma_phase ^= 1u;   // read again only after the next CTA-wide barrier
                 const int cls = chunk_class;
+                // the packed rays of the sweep that is actually taken are (re)loaded from local memory per
+                // chunk, so that only ONE of the two packs is ever live in registers
                 if (qchunk) {
+                    RayQ rq;
+                    const u64* up = reinterpret_cast<const u64*>(l_uv);
+#pragma unroll
+                    for (int p = 0; p < kRays / 2; p++) { rq.u[p] = up[p]; rq.v[p] = up[kRays / 2 + p]; }
                     sweep_quadric(smem_tab, cnt_pad, cnt, reinterpret_cast<const float4*>(rec_g), kb, rq, l_dw, l_tmin, l_idx);
-                } else if (cull) {
+                    continue;
+                }
+                RayPack rp;
+                {
+                    const u64* dp = reinterpret_cast<const u64*>(l_dw);   // (x0,x1) (x2,x3) ... pairs
+#pragma unroll
+                    for (int p = 0; p < kRays / 2; p++) { rp.dx[p] = dp[p]; rp.dy[p] = dp[kRays / 2 + p]; rp.dz[p] = dp[kRays + p]; }
+                }
+                if (cull) {
                     // one ballot word per 32 objects keeps list order without a compaction pass
                     for (int k0 = warp * 32; k0 < cnt; k0 += 32 * nwarps) {
                         const int k = k0 + lane;

@@ -274,12 +274,7 @@ __device__ __forceinline__ void sweep_quadric(const float4* __restrict__ quad, i
         }
         float gmax = 0.0f;
 #pragma unroll
-        for (int j = 0; j < kQGroup; j++) {
-            gmax = quad_obj_max(g + 6 * j, rq, gmax);
-#ifdef RRT_QSPLIT
-            if (j == kQGroup / 2 - 1) asm volatile("" : "+f"(gmax));     // A/B: keep the second half's loads behind the first half
-#endif
-        }
+        for (int j = 0; j < kQGroup; j++) gmax = quad_obj_max(g + 6 * j, rq, gmax);
         if (__builtin_expect(__any_sync(0xffffffffu, gmax > 0.0f), 0)) {
             const int k = (int)((q - q0) / 24u);
             rare_group(rec_g, k, min(kQGroup, count - k), kbase, dw, tmin, idx);

@@ -588,3 +588,35 @@ def test_fit_depth_artefact_through_kernels(cuda):
         for dx in (0, 1, 2):
             inner &= pad[dy:dy + 32, dx:dx + 32]
     assert inner.sum() > 700 and d[inner].max() <= 8, d[inner].max()
+
+
+def test_scene_api_mirror_bounce(cuda):
+    """Material(..., reflectivity=k) through the drop-in API (BASELINE config 3 names a mirror-reflection
+    scene; the reference has no secondary ray, so this is an extension): Scene.build == the C oracle with
+    the same tables, a sphere that is ONLY visible in the mirror receives gradient through the reflection,
+    and gradient descent through the mirror moves it towards a target."""
+    m1 = Material((0.2, 0.9, 0.4), 0.3, 0.7, 0.5, 50.)
+    m2 = Material((0.87, 0.1, 0.507), 0.3, 0.9, 0.4, 50., reflectivity=0.5)
+    mirror = Material((0.6, 0.6, 0.9), 0.2, 0.6, 0.3, 30., reflectivity=0.8)
+    hidden = torch.tensor([-1.6, 0.9, 2.5], device=cuda, requires_grad=True)        # outside the field of view
+    objs = [Sphere(translate((-.5, -.5, 4)), m1), Sphere(translate((.6, .5, 4.2)), m2),
+            Square(translate((0.2, 0, 6.0)) * rotate(25, [0., 1., 0.]) * scale((6, 6, 1)), mirror),
+            Sphere(translate(hidden) * scale((0.5, 0.5, 0.5)), m1)]
+    sc = Scene(objs, [Light((-1., -1., 2.), (1., 0.87, 0.961))], Camera(64, 64), PhongShader())
+    img = sc.build(seed=3)
+    ps = _oracle_tables_from(sc, 3)
+    ps.reflectivity = np.asarray([0.0, 0.5, 0.8, 0.0], dtype=np.float32)
+    img_o, hit_o, hit2_o = oc.render_forward_secondary(ps)
+    np.testing.assert_allclose(img.detach().cpu().numpy(), img_o[0], rtol=1e-4, atol=1e-5)
+    assert not (hit_o == 3).any() and (hit2_o == 3).sum() > 20                     # seen only through reflections
+    (g,) = torch.autograd.grad(img.sum(), [hidden])
+    assert float(g.abs().max()) > 1e-3
+    # optimise the hidden sphere towards a target rendered with it somewhere else
+    with torch.no_grad():
+        hidden += torch.tensor([0.15, -0.1, 0.1], device=cuda)
+    target = sc.build(seed=3).detach()
+    with torch.no_grad():
+        hidden -= torch.tensor([0.15, -0.1, 0.1], device=cuda)
+    train = GDOptimizer().optimize([hidden], lambda: sc.build_mse(target, seed=3), lr=2e-3)
+    losses = [train() for _ in range(40)]
+    assert losses[-1] < 0.5 * losses[0], (losses[0], losses[-1])

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from reversible_raytracer_b200 import render as R
 names = ['scalar FFMA', 'FFMA2', 'FFMA2 + 1 FMNMX3 per 4', 'FFMA2 + 1 LDS.128 per 8', 'FFMA2 + 1 LDC per 8',
-         'quadric mix 24 FFMA2 : 4 FMNMX3 : 1.5 LDS.128']
+         'quadric mix 24 FFMA2 : 4 FMNMX3 : 1.5 LDS.128', 'FFMA2 with two .F32 broadcast operands', 'FFMA2 with .F32 multiplier + packed-duplicate addend']
 torch.zeros(1, device='cuda')
 for m, nm in enumerate(names):
     tf, ms = R.measure_fp32_peak(m, 4096)
