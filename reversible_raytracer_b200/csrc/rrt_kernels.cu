@@ -57,7 +57,9 @@ constexpr int kRays = RRT_RAYS;   // rays per thread (kRays/2 packed pairs)
 #define RRT_SWEEP_UNROLL 1
 #endif
 #ifndef RRT_MIN_BLOCKS
-#define RRT_MIN_BLOCKS 5   // 96 registers; only one packed ray set (canonical: 12 pairs, pre-filter: 8 pairs) is live per sweep
+#define RRT_MIN_BLOCKS 4   // 128 registers, no spills.  5 CTAs/SM (96 registers) run the same speed but their extra
+                           // resident threads push local memory (per-ray arrays) out of L2: DRAM writes 377 MB vs
+                           // the algorithmic 201 MB per C5 launch (profiles/r2_traffic_probe.txt)
 #endif
 #ifndef RRT_MAX_WARPS
 #define RRT_MAX_WARPS 4
@@ -188,10 +190,15 @@ int launch(KParams& P, cudaStream_t st, bool* finalized = nullptr) {
     if (finalized) *finalized = false;
     if (use_small_kernel(P)) {
         const unsigned grid = small_grid(P);
-        if (MODE != MODE_FWD && (sc.flags & RRT_FLAG_NO_MATERIAL_GRAD))
+        const bool geom = MODE != MODE_FWD && (sc.flags & RRT_FLAG_NO_MATERIAL_GRAD);
+        if (sc.flags & RRT_FLAG_MIRROR) {
+            if (geom) render_small_kernel<MODE, false, true, true><<<grid, kSmallThreads, 0, st>>>(P);
+            else render_small_kernel<MODE, false, false, true><<<grid, kSmallThreads, 0, st>>>(P);
+        } else if (geom) {
             render_small_kernel<MODE, false, true><<<grid, kSmallThreads, 0, st>>>(P);
-        else
+        } else {
             render_small_kernel<MODE><<<grid, kSmallThreads, 0, st>>>(P);
+        }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "small-scene kernel launch: %s", cudaGetErrorString(e));
         if (finalized) *finalized = (MODE != MODE_FWD) && sc.ticket != nullptr;
@@ -208,7 +215,12 @@ int launch(KParams& P, cudaStream_t st, bool* finalized = nullptr) {
     const int staged = sc.num_objects < kObjChunk ? sc.num_objects : kObjChunk;
     size_t smem = (size_t)(staged > 0 ? staged : 1) * 64;
     void (*kern)(const KParams) = nullptr;
-    if (S == 1) kern = render_kernel<kRays, 1, MODE>;
+    if (sc.flags & RRT_FLAG_MIRROR) {
+        if (S == 1) kern = render_kernel<kRays, 1, MODE, true>;
+        else if (S == 2) kern = render_kernel<kRays / 2, 2, MODE, true>;
+        else if (S == 4) kern = render_kernel<kRays / 4, 4, MODE, true>;
+        else kern = render_kernel<1, kRays, MODE, true>;
+    } else if (S == 1) kern = render_kernel<kRays, 1, MODE>;
     else if (S == 2) kern = render_kernel<kRays / 2, 2, MODE>;
     else if (S == 4) kern = render_kernel<kRays / 4, 4, MODE>;
     else kern = render_kernel<1, kRays, MODE>;

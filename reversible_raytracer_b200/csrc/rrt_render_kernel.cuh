@@ -7,7 +7,9 @@
 // Thread (warp w, lane l) owns pixels (row = tile_row0 + w, cols = col0 + l*PIX .. +PIX-1),
 // each with SPT samples: PIX*SPT = 8 rays.  S > SPT (generic path, PIX = 1) loops
 // over chunks of SPT samples.
-template <int PIX, int SPT, int MODE>
+// MIRROR instantiations carry the opt-in reflection bounce (RRT_FLAG_MIRROR); the default ones contain none
+// of its code (it would triple the stack frame, and local memory of all resident threads competes for L2).
+template <int PIX, int SPT, int MODE, bool MIRROR = false>
 __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_kernel(const __grid_constant__ KParams P) {
     extern __shared__ float4 smem_tab[];  // kObjChunk (or N) sweep records
     __shared__ Globals g;
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
     float* gobj = (MODE != MODE_FWD) ? P.grad + (size_t)scene * RRT_GRAD_SIZE(N) : nullptr;
     long long* const det_ws = (MODE != MODE_FWD && (sc.flags & RRT_FLAG_DETERMINISTIC)) ? det_scene(sc, scene) : nullptr;
     // RRT_FLAG_MIRROR (opt-in extension): needs the identity camera, Phong shaders
-    const bool mirror_on = (sc.flags & RRT_FLAG_MIRROR) && sc.reflectivity && sc.shader != RRT_SHADER_DEPTH && cam_identity &&
+    const bool mirror_on = MIRROR && (sc.flags & RRT_FLAG_MIRROR) && sc.reflectivity && sc.shader != RRT_SHADER_DEPTH && cam_identity &&
                            g.ct[0] == 0.f && g.ct[1] == 0.f && g.ct[2] == 0.f;
     const float* refl = mirror_on ? sc.reflectivity + (size_t)scene * sc.reflectivity_scene_stride : nullptr;
     // the last CTA of a scene (rrt_scene.ticket) finalises its gradients: one launch per reverse pass
@@ -446,7 +448,7 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                 ShadeRec sr;
                 float rgb[3];
                 shade(sc.shader, sc.max_depth, ob, m7, g, h, sr, rgb);
-                if (mirror_on) {                          // one mirror bounce (extension)
+                if (MIRROR && mirror_on) {                // one mirror bounce (extension)
                     float rgb2[3];
                     mirror_shade(sc.shader, sc.max_depth, w2o, mats, sc.obj_type, N, g, k, ob, h, dwx, dwy, dwz, rgb2);
                     const float kr = __ldg(refl + k);
@@ -583,7 +585,7 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                     acc_key = k;
                     {
                         const float rc3[3] = {l_rc[r], l_rc[kRays + r], l_rc[2 * kRays + r]};
-                        if (mirror_on) {
+                        if (MIRROR && mirror_on) {
                             const float kr = __ldg(refl + k);
                             const float gc2[3] = {kr * gc[0], kr * gc[1], kr * gc[2]};
                             const float gc1[3] = {(1.0f - kr) * gc[0], (1.0f - kr) * gc[1], (1.0f - kr) * gc[2]};

@@ -52,7 +52,7 @@ __device__ __forceinline__ void small_warp_flush(int key, float* acc_col, float*
     }
 }
 
-template <int MODE, bool STEP = false, bool GEOM = false>
+template <int MODE, bool STEP = false, bool GEOM = false, bool MIRROR = false>
 __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_small_kernel(const __grid_constant__ KParams P) {
     constexpr int NACC = GEOM ? 12 : 19;
     __shared__ float4 tab[kSmallMaxN * 4];
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
     float* gobj = nullptr;
     long long* det_ws = nullptr;                       // RRT_FLAG_DETERMINISTIC: fixed-point sums of cur_scene
     // RRT_FLAG_MIRROR (opt-in extension): scene tables the secondary rays read; requires the identity camera
-    const bool mirror_on = !STEP && (sc.flags & RRT_FLAG_MIRROR) && sc.reflectivity && sc.shader != RRT_SHADER_DEPTH;
+    const bool mirror_on = MIRROR && !STEP && (sc.flags & RRT_FLAG_MIRROR) && sc.reflectivity && sc.shader != RRT_SHADER_DEPTH;
     const float* w2o_s = nullptr;
     const float* mats_g = nullptr;
     const float* refl_s = nullptr;
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
             __syncthreads();
         }
         scene_items++;
-        const bool mir = mirror_on && g.cam_identity && g.ct[0] == 0.f && g.ct[1] == 0.f && g.ct[2] == 0.f;
+        const bool mir = MIRROR && mirror_on && g.cam_identity && g.ct[0] == 0.f && g.ct[1] == 0.f && g.ct[2] == 0.f;
 
         const unsigned gid = blk * kSmallThreads + tid;      // ray index within the scene: [rows][n][S]
         const bool active = gid < rays_scene;
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
 #pragma unroll
             for (int q = 0; q < 7; q++) m7[q] = mat_s[idx * RRT_MAT_STRIDE + q];
             shade(sc.shader, sc.max_depth, ob, m7, g, h, sr, rgb);
-            if (MODE != MODE_BWD && mir) {       // one mirror bounce (extension)
+            if (MIRROR && MODE != MODE_BWD && mir) {       // one mirror bounce (extension)
                 float rgb2[3];
                 mirror_shade(sc.shader, sc.max_depth, w2o_s, mats_g, sc.obj_type, N, g, idx, ob, h, wx, wy, wz, rgb2);
                 const float kr = __ldg(refl_s + idx);
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
                 for (int v = 0; v < NACC; v++) da[v] = 0.f;
 #pragma unroll
                 for (int v = 0; v < 9; v++) dg[v] = 0.f;
-                if (mir) {
+                if (MIRROR && mir) {
                     // secondary object first (its sums go straight to its CTA slot / the fixed-point
                     // workspace), then the primary one with the chain through the reflection
                     const float kr = __ldg(refl_s + key);

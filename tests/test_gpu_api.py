@@ -593,15 +593,18 @@ def test_fit_depth_artefact_through_kernels(cuda):
 def test_scene_api_mirror_bounce(cuda):
     """Material(..., reflectivity=k) through the drop-in API (BASELINE config 3 names a mirror-reflection
     scene; the reference has no secondary ray, so this is an extension): Scene.build == the C oracle with
-    the same tables, a sphere that is ONLY visible in the mirror receives gradient through the reflection,
-    and gradient descent through the mirror moves it towards a target."""
+    the same tables; a sphere that is ONLY visible in the mirror receives gradients through the
+    reflection (geometry and material); and its colour is recovered from a target image by gradient
+    descent through the mirror."""
     m1 = Material((0.2, 0.9, 0.4), 0.3, 0.7, 0.5, 50.)
     m2 = Material((0.87, 0.1, 0.507), 0.3, 0.9, 0.4, 50., reflectivity=0.5)
     mirror = Material((0.6, 0.6, 0.9), 0.2, 0.6, 0.3, 30., reflectivity=0.8)
-    hidden = torch.tensor([-1.6, 0.9, 2.5], device=cuda, requires_grad=True)        # outside the field of view
+    colour = torch.tensor([0.2, 0.9, 0.4], device=cuda, requires_grad=True)
+    m_hidden = Material(colour, 0.3, 0.7, 0.5, 50.)
+    hidden = torch.tensor([2.6, 0.9, 2.5], device=cuda, requires_grad=True)         # outside the field of view
     objs = [Sphere(translate((-.5, -.5, 4)), m1), Sphere(translate((.6, .5, 4.2)), m2),
             Square(translate((0.2, 0, 6.0)) * rotate(25, [0., 1., 0.]) * scale((6, 6, 1)), mirror),
-            Sphere(translate(hidden) * scale((0.5, 0.5, 0.5)), m1)]
+            Sphere(translate(hidden) * scale((0.5, 0.5, 0.5)), m_hidden)]
     sc = Scene(objs, [Light((-1., -1., 2.), (1., 0.87, 0.961))], Camera(64, 64), PhongShader())
     img = sc.build(seed=3)
     ps = _oracle_tables_from(sc, 3)
@@ -609,14 +612,25 @@ def test_scene_api_mirror_bounce(cuda):
     img_o, hit_o, hit2_o = oc.render_forward_secondary(ps)
     np.testing.assert_allclose(img.detach().cpu().numpy(), img_o[0], rtol=1e-4, atol=1e-5)
     assert not (hit_o == 3).any() and (hit2_o == 3).sum() > 20                     # seen only through reflections
-    (g,) = torch.autograd.grad(img.sum(), [hidden])
-    assert float(g.abs().max()) > 1e-3
-    # optimise the hidden sphere towards a target rendered with it somewhere else
+    g_pos, g_col = torch.autograd.grad(img.sum(), [hidden, colour])
+    assert float(g_pos.abs().max()) > 1e-3 and float(g_col.abs().max()) > 1e-3
+    # the oracle's gradient of the same loss, through the same reflection
+    grad_o = oc.render_backward(ps, np.ones_like(img_o[0]), hit_o)
+    go = oc.split_grad(grad_o[0], 4)
+    np.testing.assert_allclose(g_col.cpu().numpy(), go['material'][3, 4:7], rtol=2e-3, atol=1e-6)
+    np.testing.assert_allclose(g_pos.cpu().numpy(), -go['w2o'][3, :, 3] / 0.5, rtol=2e-3, atol=1e-5)   # b = -c/s
+    # recover the hidden sphere's colour from a target in which it is red
     with torch.no_grad():
-        hidden += torch.tensor([0.15, -0.1, 0.1], device=cuda)
+        colour.copy_(torch.tensor([0.9, 0.2, 0.1], device=cuda))
     target = sc.build(seed=3).detach()
     with torch.no_grad():
-        hidden -= torch.tensor([0.15, -0.1, 0.1], device=cuda)
-    train = GDOptimizer().optimize([hidden], lambda: sc.build_mse(target, seed=3), lr=2e-3)
-    losses = [train() for _ in range(40)]
-    assert losses[-1] < 0.5 * losses[0], (losses[0], losses[-1])
+        colour.copy_(torch.tensor([0.2, 0.9, 0.4], device=cuda))
+    losses = []
+    for i in range(60):
+        loss = sc.build_mse(target, seed=3)
+        (g,) = torch.autograd.grad(loss, [colour])
+        losses.append(float(loss))
+        with torch.no_grad():
+            colour -= 0.08 * (0.95 ** i) * g / (g.norm() + 1e-20)
+    assert losses[-1] < 0.05 * losses[0], (losses[0], losses[-1])
+    assert float((colour.detach() - torch.tensor([0.9, 0.2, 0.1], device=cuda)).abs().max()) < 0.1, colour
