@@ -53,6 +53,12 @@ extern "C" {
 
 /* shaders: shader.py:23-53 (Phong), orbit_experiments/shader.py:45,48 (Phong with
  * the specular term commented out), shader.py:9-20 (DepthMapShader) */
+/* Shininess: x ** shininess follows C pow() like Theano's T.pow (shader.py:45): a negative base with a
+ * non-integer exponent gives NaN, which the clip passes on (the pixel becomes NaN, as in the reference).
+ * Deviation, stated: d/d shininess is accumulated only where the base is > 0 (the reference's T.grad would
+ * put NaN there; every reference script keeps shininess constant and never asks for this gradient), and the
+ * reverse pass uses rsqrt / fast-divide / fast-log approximations -- gradients are float32-tolerance
+ * quantities (1e-3 per block), only hit masks and tmin are bit-exact. */
 #define RRT_SHADER_PHONG 0
 #define RRT_SHADER_PHONG_NOSPEC 1
 #define RRT_SHADER_DEPTH 2

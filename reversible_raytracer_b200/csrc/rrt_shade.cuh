@@ -184,7 +184,9 @@ __device__ __forceinline__ void shade(int shader, float max_depth, const Obj& ob
     for (int c = 0; c < 3; c++) {      // shader.py:50-51
         float v = r.ph * mat[4 + c] * g.I[c];
         r.inside[c] = (v >= 0.0f && v <= 1.0f);
-        rgb[c] = fminf(fmaxf(v, 0.0f), 1.0f);
+        // T.clip = switch(x < 0, 0, switch(x > 1, 1, x)): a NaN (negative base ** non-integer
+        // shininess, shader.py:45) stays NaN like in the reference -- fminf/fmaxf would drop it
+        rgb[c] = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
     }
 }
 

@@ -64,20 +64,21 @@ class _WholeStep(object):
             raise ValueError('not a small scene')
         if any(p.dtype != torch.float32 or p.device != dev for p in prog.param_tensors):
             raise ValueError('parameters must be float32 tensors on the scene device')
-        # parameters move INTO the chain's value buffer; the user's tensors become views of it
+        # every check happens BEFORE the user's tensors are touched
         values = prog.values().detach().clone().contiguous()
         off = int(prog.const_block.numel())
         self.param_begin = off
-        for p in prog.param_tensors:
-            p.data = values[off:off + p.numel()].view(p.shape)
-            off += p.numel()
-        if off != values.numel():
+        if off + sum(p.numel() for p in prog.param_tensors) != values.numel():
             raise ValueError('unexpected chain value layout')
         obj_type, _, mat, light, cam = scene.pack(dev)
         jit = scene._jitter_for(cfg.n, cfg.samples, spec['jitter'], spec['seed'], dev)
         self.target = as_tensor(spec['target']).to(dev, torch.float32).contiguous()
         if self.target.numel() != cfg.n * cfg.n * 3:
             raise ValueError('target must be [n, n, 3]')
+        # parameters move INTO the chain's value buffer; the user's tensors become views of it
+        for p in prog.param_tensors:
+            p.data = values[off:off + p.numel()].view(p.shape)
+            off += p.numel()
         G = nat.grad_size(N)
         z = lambda n, dt: torch.zeros(n, dtype=dt, device=dev)
         self.keep = dict(values=values, w2o=z(N * 12, torch.float32).reshape(N, 12), grad=z(G, torch.float32),

@@ -832,3 +832,21 @@ def test_mirror_bounce_parity(general, cuda):
     a = R.render_fused_mse(c, ot, w2o, mat, light, cam, torch.from_numpy(target).to(cuda), None, jit, reflectivity=refl)
     b = R.render_fused_mse(c, ot, w2o, mat, light, cam, torch.from_numpy(target).to(cuda), None, jit, reflectivity=refl)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def test_non_integer_shininess_nan_propagates_like_the_reference(cuda):
+    """shader.py:45 raises (rm . look_at) to `shininess` with Theano's pow: a negative base with a
+    non-integer exponent is NaN, and T.clip passes NaN on -- so does the kernel (its clip is
+    switch-based, not fmin/fmax) and the oracle; pixels agree including where they are NaN."""
+    spec = scenes.optimize_brightness(n=64)
+    spec['material'] = spec['material'].copy()
+    spec['material'][:, 3] = 50.5                              # non-integer shininess
+    ps = oc.PackedScene.from_spec(spec, camera_grad=0)
+    img_o, hit_o, _ = oc.render_forward(ps)
+    assert np.isnan(img_o).any() and np.isfinite(img_o).any()
+    cfg, ot, w2o, mat, light, cam, jit = to_device(ps, cuda)
+    img, hit, _ = R.render_forward(cfg, ot, w2o, mat, light, cam, jit)
+    assert np.array_equal(hit.cpu().numpy().reshape(hit_o.shape), hit_o)
+    got = img.cpu().numpy().reshape(img_o.shape)
+    assert np.array_equal(np.isnan(got), np.isnan(img_o))
+    np.testing.assert_allclose(got, img_o, rtol=1e-3, atol=1e-5, equal_nan=True)
