@@ -160,12 +160,31 @@ int sm_count() {
     return sms;
 }
 
+// The pixel-per-thread form of the small-scene kernel (one thread = one pixel and its S samples):
+// forward and fused modes, S in {1, 2, 4}, no shadows / mirror bounce.  Taken by default when the
+// call has enough pixels to fill the machine with pixel threads (batches of scenes); a single small
+// image keeps one ray per thread (4 x the threads, shorter dependency chains).
+constexpr long long kPixelMinPixels = 96 * 1024;
+bool use_pixel_threads(const KParams& P, int mode) {
+    const rrt_scene& sc = P.sc;
+    const int S = sc.samples;
+    if (mode == MODE_BWD || !(S == 1 || S == 2 || S == 4)) return false;
+    if (sc.flags & (RRT_FLAG_SHADOWS | RRT_FLAG_MIRROR | RRT_FLAG_RAY_THREADS)) return false;
+    if (sc.flags & RRT_FLAG_PIXEL_THREADS) return true;
+    return (long long)P.rows * sc.n * sc.num_scenes >= kPixelMinPixels;
+}
+
 // Persistent grid of the small-scene kernel: at most one resident wave, every CTA >= 1 work item.
-unsigned small_grid(KParams& P) {
+unsigned small_grid(KParams& P, bool pixel = false) {
     const rrt_scene& sc = P.sc;
     const long long rays_scene = (long long)P.rows * sc.n * sc.samples;
-    const long long total = ((rays_scene + kSmallThreads - 1) / kSmallThreads) * sc.num_scenes;
-    const long long cap = (long long)sm_count() * RRT_SMALL_MIN_BLOCKS;
+    long long items_scene = (rays_scene + kSmallThreads - 1) / kSmallThreads;
+    if (pixel) {        // tiles of 8 x 4 pixels, one per warp
+        const long long tiles = (long long)((sc.n + kPixTileW - 1) / kPixTileW) * ((P.rows + kPixTileH - 1) / kPixTileH);
+        items_scene = (tiles + kSmallThreads / 32 - 1) / (kSmallThreads / 32);
+    }
+    const long long total = items_scene * sc.num_scenes;
+    const long long cap = (long long)sm_count() * (pixel ? RRT_PIXEL_MIN_BLOCKS : RRT_SMALL_MIN_BLOCKS);
     long long per = (total + cap - 1) / cap;
     if (per < 1) per = 1;
     P.small_per = (int)per;
@@ -189,9 +208,19 @@ int launch(KParams& P, cudaStream_t st, bool* finalized = nullptr) {
     const int S = sc.samples;
     if (finalized) *finalized = false;
     if (use_small_kernel(P)) {
-        const unsigned grid = small_grid(P);
         const bool geom = MODE != MODE_FWD && (sc.flags & RRT_FLAG_NO_MATERIAL_GRAD);
-        if (sc.flags & RRT_FLAG_MIRROR) {
+        const bool pixel = use_pixel_threads(P, MODE);
+        const unsigned grid = small_grid(P, pixel);
+        if (pixel) {
+            constexpr int PM = MODE == MODE_BWD ? MODE_FUSED : MODE;     // (never taken for MODE_BWD)
+            void (*kern)(const KParams) = nullptr;
+            constexpr bool G = MODE != MODE_FWD;                         // (forward: one instantiation)
+            if (geom) kern = S == 1 ? render_small_kernel<PM, false, G, false, 1> :
+                             S == 2 ? render_small_kernel<PM, false, G, false, 2> : render_small_kernel<PM, false, G, false, 4>;
+            else kern = S == 1 ? render_small_kernel<PM, false, false, false, 1> :
+                        S == 2 ? render_small_kernel<PM, false, false, false, 2> : render_small_kernel<PM, false, false, false, 4>;
+            kern<<<grid, kSmallThreads, 0, st>>>(P);
+        } else if (sc.flags & RRT_FLAG_MIRROR) {
             if (geom) render_small_kernel<MODE, false, true, true><<<grid, kSmallThreads, 0, st>>>(P);
             else render_small_kernel<MODE, false, false, true><<<grid, kSmallThreads, 0, st>>>(P);
         } else if (geom) {

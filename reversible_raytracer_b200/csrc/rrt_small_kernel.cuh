@@ -52,8 +52,45 @@ __device__ __forceinline__ void small_warp_flush(int key, float* acc_col, float*
     }
 }
 
-template <int MODE, bool STEP = false, bool GEOM = false, bool MIRROR = false>
-__global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_small_kernel(const __grid_constant__ KParams P) {
+// SPP > 0 selects the PIXEL-PER-THREAD form (batches of small scenes: the orbit decoder batch is 2.1 M
+// pixels): one thread owns one pixel and its SPP = S anti-alias samples (S in {1, 2, 4}), a warp
+// covers a compact tile of 8 x 4 pixels (a warp meets an object's silhouette about half as often as
+// with a 32 x 1 strip, and the shading / reverse-pass code is only entered by warps that hit
+// something), a work item is 4 consecutive tiles (one per warp).  What the ray-per-thread form pays
+// per RAY is paid per PIXEL: index arithmetic, the camera-space grid ray, the target load, the loss,
+// the image store; the pixel mean is a register sum in sample order (same bits as the shuffles of
+// the ray-per-thread form); the S samples of a pixel give the sweep S independent dependency
+// chains.  Same device routines, same canonical order => same masks.  Forward and fused modes,
+// no shadows / mirror / whole-step (those keep SPP = 0).
+constexpr int kPixTileW = 8, kPixTileH = 4;                 // pixels per warp: 8 x 4
+// a[q] for a run-time q out of a register array (select chain instead of local memory): lets the
+// per-sample shading / reverse-pass loops stay ROLLED -- one copy of that code instead of S, which is
+// what keeps the kernel inside the instruction cache (S unrolled copies: 56 % I-cache hit rate, 7
+// "no instruction" stall cycles per issue, measured)
+template <typename T, int NQ>
+__device__ __forceinline__ void put(T (&a)[NQ], int q, T v) {
+#pragma unroll
+    for (int i = 0; i < NQ; i++) a[i] = (q == i) ? v : a[i];
+}
+__device__ __noinline__ void jitter_offset_pair(float ux, float uy, int s, int S, int n, float& ox, float& oy) {
+    ox = jitter_offset(ux, s, S, n);
+    oy = jitter_offset(uy, s, S, n);
+}
+template <typename T, int NQ>
+__device__ __forceinline__ T pick(const T (&a)[NQ], int q) {
+    T v = a[0];
+#pragma unroll
+    for (int i = 1; i < NQ; i++) v = (q == i) ? a[i] : v;
+    return v;
+}
+#ifndef RRT_PIXEL_MIN_BLOCKS
+#define RRT_PIXEL_MIN_BLOCKS 5
+#endif
+
+template <int MODE, bool STEP = false, bool GEOM = false, bool MIRROR = false, int SPP = 0>
+__global__ void __launch_bounds__(kSmallThreads, SPP > 0 ? RRT_PIXEL_MIN_BLOCKS : RRT_SMALL_MIN_BLOCKS)
+render_small_kernel(const __grid_constant__ KParams P) {
+    static_assert(SPP == 0 || (!STEP && !MIRROR && MODE != MODE_BWD), "pixel-per-thread form: forward / fused only");
     constexpr int NACC = GEOM ? 12 : 19;
     __shared__ float4 tab[kSmallMaxN * 4];
     __shared__ float mat_s[kSmallMaxN * RRT_MAT_STRIDE];
@@ -72,7 +109,11 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
     const unsigned full = 0xffffffffu;
     // 32-bit index arithmetic (the launcher guarantees rows*n*S < 2^31 and a total below 2^31; S is a power of two)
     const unsigned rays_scene = (unsigned)P.rows * (unsigned)n * (unsigned)S;
-    const unsigned bps = (rays_scene + kSmallThreads - 1) / kSmallThreads;      // work items per scene
+    // pixel-per-thread form: tiles of 8 x 4 pixels, 4 tiles (one per warp) per work item
+    const unsigned tiles_x = ((unsigned)n + kPixTileW - 1) / kPixTileW;
+    const unsigned ntiles = tiles_x * (((unsigned)P.rows + kPixTileH - 1) / kPixTileH);
+    const unsigned bps = SPP > 0 ? (ntiles + kSmallThreads / 32 - 1) / (kSmallThreads / 32)
+                                 : (rays_scene + kSmallThreads - 1) / kSmallThreads;      // work items per scene
     const unsigned total = bps * (unsigned)sc.num_scenes;
     const unsigned item0 = blockIdx.x * (unsigned)P.small_per;
     const unsigned item1 = min(total, item0 + (unsigned)P.small_per);
@@ -192,13 +233,17 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
     const float* dl_s = nullptr;
     float* img_s = nullptr;
 #pragma unroll 1
-    for (unsigned item = item0; item < item1; item++, blk++) {
-        if (blk == bps) { blk = 0; scene++; }
-        if (scene != cur_scene) {                          // CTA-uniform
+    for (unsigned item = item0;; item++, blk++) {
+        // (one call site for the scene flush -- the loop also runs once past the last item: the flush
+        // inlines the whole gradient finalisation, and this kernel lives or dies by its code size)
+        const bool done = item >= item1;
+        if (!done && blk == bps) { blk = 0; scene++; }
+        if (done || scene != cur_scene) {                  // CTA-uniform
             if (cur_scene >= 0) {
                 flush_scene(true);
-                __syncthreads();                           // everybody is done with the old tables / slots
+                if (!done) __syncthreads();                // everybody is done with the old tables / slots
             }
+            if (done) break;
             cur_scene = scene;
             scene_items = 0;
             gobj = (MODE != MODE_FWD) ? P.grad + (size_t)scene * RRT_GRAD_SIZE(N) : nullptr;
@@ -257,6 +302,216 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
             __syncthreads();
         }
         scene_items++;
+
+        if (SPP > 0) {
+            // ================= pixel-per-thread form: this thread's pixel and its S = SPP samples
+            constexpr int SP = SPP > 0 ? SPP : 1;
+            const unsigned tile = blk * (kSmallThreads / 32) + (unsigned)warp;
+            const unsigned tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
+            const int al = (int)(tyi * kPixTileH) + (lane >> 3);
+            const int b = (int)(txi * kPixTileW) + (lane & 7);
+            const bool active = (tile < ntiles) && (al < P.rows) && (b < n);
+            const int a = sc.row_begin + al;
+            const unsigned pl = active ? (unsigned)al * (unsigned)n + (unsigned)b : 0u;
+            const unsigned po = pl * 3u;
+
+            // ---- rays: the grid ray once per pixel, jitter per sample (scene.py:24-32,66-74)
+            float rcx[SP], rcy[SP], rcz = 0.f;
+#pragma unroll
+            for (int q = 0; q < SP; q++) rcx[q] = rcy[q] = 0.f;
+            if (active) {
+                const int i = sc.transpose ? b : a, j = sc.transpose ? a : b;
+                float bx, by;
+                if (sc.base_rays) {
+                    const float* br = sc.base_rays + ((size_t)i * n + j) * 3;
+                    bx = __ldg(br); by = __ldg(br + 1); rcz = __ldg(br + 2);
+                } else {
+                    base_ray(n, P.lin_step, i, j, bx, by, rcz);
+                }
+#pragma unroll
+                for (int q = 0; q < SP; q++) {
+                    float jx, jy;
+                    if (sc.jitter_x) {
+                        const size_t off = (size_t)scene * sc.jitter_scene_stride + (size_t)pl * SP + q;   // [rows][n][S]
+                        jx = __ldg(sc.jitter_x + off);
+                        jy = __ldg(sc.jitter_y + off);
+                    } else {
+                        jx = rrt_rng(sc.seed, scene + sc.scene_begin, (uint32_t)(a * n + b), q, 0);
+                        jy = rrt_rng(sc.seed, scene + sc.scene_begin, (uint32_t)(a * n + b), q, 1);
+                    }
+                    float ox, oy;
+                    if (P.pow2) { ox = jitter_offset_pow2(jx, q, P.inv_s, P.inv_n); oy = jitter_offset_pow2(jy, q, P.inv_s, P.inv_n); }
+                    else jitter_offset_pair(jx, jy, q, SP, n, ox, oy);      // (out of line: four IEEE divisions)
+                    rcx[q] = __fadd_rn(bx, ox);
+                    rcy[q] = __fadd_rn(by, oy);
+                }
+            }
+            float tgt[3] = {0.f, 0.f, 0.f};
+            if (MODE == MODE_FUSED && active) { tgt[0] = __ldg(tgt_s + po); tgt[1] = __ldg(tgt_s + po + 1); tgt[2] = __ldg(tgt_s + po + 2); }
+            const bool cam_id = g.cam_identity;
+            // camera.o2w (orbit_experiments/scene.py:80); identity => the fma chain returns its input
+            auto world = [&](float rx, float ry, float& wx, float& wy, float& wz) {
+                wx = rx; wy = ry; wz = rcz;
+                if (!cam_id) {
+                    wx = dot3_canon(g.C[0], g.C[1], g.C[2], rx, ry, rcz);
+                    wy = dot3_canon(g.C[3], g.C[4], g.C[5], rx, ry, rcz);
+                    wz = dot3_canon(g.C[6], g.C[7], g.C[8], rx, ry, rcz);
+                }
+            };
+
+            // ---- nearest hit per sample: list order, strict '<' (scene.py:46-47); objects outer, samples inner
+            float tmin[SP];
+            int idx[SP];
+#pragma unroll
+            for (int q = 0; q < SP; q++) { tmin[q] = inf; idx[q] = -1; }
+            if (active) {
+                float wx[SP], wy[SP], wz[SP];
+#pragma unroll
+                for (int q = 0; q < SP; q++) world(rcx[q], rcy[q], wx[q], wy[q], wz[q]);
+#pragma unroll 1
+                for (int k = 0; k < N; k++) {
+                    Obj ob;
+                    load_rec(tab + 4 * k, ob);
+                    if (ob.flags & 1) {                    // Square: the scalar routine, one sample at a time
+#pragma unroll 1
+                        for (int q = 0; q < SP; q++) {
+                            HitRec h;
+                            const float t = obj_test<true>(ob, pick(wx, q), pick(wy, q), pick(wz, q), h);
+                            if (t < pick(tmin, q)) put(tmin, q, t), put(idx, q, k);
+                        }
+                        continue;
+                    }
+                    // Sphere: the S discriminants side by side (independent chains; the operations and their
+                    // order are obj_test's: d' = A d, vn = d'.d', pd = d'.o', det = fma(pd, pd, vn * -cc)) ...
+                    float vn[SP], pd[SP], det[SP];
+                    bool cand = false;
+#pragma unroll
+                    for (int q = 0; q < SP; q++) {
+                        float d0, d1, d2;
+                        if (!(ob.flags & 2)) {
+                            d0 = __fmul_rn(ob.a[0], wx[q]); d1 = __fmul_rn(ob.a[4], wy[q]); d2 = __fmul_rn(ob.a[8], wz[q]);
+                        } else {
+                            d0 = dot3_canon(ob.a[0], ob.a[1], ob.a[2], wx[q], wy[q], wz[q]);
+                            d1 = dot3_canon(ob.a[3], ob.a[4], ob.a[5], wx[q], wy[q], wz[q]);
+                            d2 = dot3_canon(ob.a[6], ob.a[7], ob.a[8], wx[q], wy[q], wz[q]);
+                        }
+                        vn[q] = dot3_canon(d0, d1, d2, d0, d1, d2);
+                        pd[q] = dot3_canon(d0, d1, d2, ob.o[0], ob.o[1], ob.o[2]);
+                        det[q] = __fmaf_rn(pd[q], pd[q], __fmul_rn(vn[q], ob.ncc));
+                        cand |= det[q] > 0.0f;
+                    }
+                    // ... and the first root only where det > 0 (shape.py:121-125), one copy of the sqrt / divide
+                    if (cand) {
+#pragma unroll 1
+                        for (int q = 0; q < SP; q++) {
+                            const float dq = pick(det, q);
+                            if (dq > 0.0f) {
+                                const float t = __fdiv_rn(__fsub_rn(-pick(pd, q), __fsqrt_rn(dq)), pick(vn, q));
+                                if (t < pick(tmin, q)) put(tmin, q, t), put(idx, q, k);
+                            }
+                        }
+                    }
+                }
+                if (P.hit_out || (MODE == MODE_FWD && P.tmin_out)) {
+#pragma unroll
+                    for (int q = 0; q < SP; q++) {
+                        const size_t ro = (((size_t)scene * SP + q) * P.rows + al) * n + b;
+                        if (P.hit_out) P.hit_out[ro] = idx[q];
+                        if (MODE == MODE_FWD && P.tmin_out) P.tmin_out[ro] = tmin[q];
+                    }
+                }
+            }
+
+            // ---- shade the winners; pixel = mean over the samples, summed in sample order (scene.py:49-50)
+            float sum[3] = {0.f, 0.f, 0.f};
+            bool any_hit = false;
+#pragma unroll
+            for (int q = 0; q < SP; q++) any_hit |= (idx[q] >= 0);
+            if (__any_sync(full, any_hit)) {
+#pragma unroll 1
+                for (int q = 0; q < SP; q++) {
+                    float rgb[3] = {0.f, 0.f, 0.f};
+                    const int kq = pick(idx, q);
+                    if (kq >= 0) {
+                        Obj ob;
+                        HitRec h;
+                        ShadeRec sr;
+                        float m7[7], wx, wy, wz;
+                        load_rec(tab + 4 * kq, ob);
+                        world(pick(rcx, q), pick(rcy, q), wx, wy, wz);
+                        hit_record<false>(ob, wx, wy, wz, pick(tmin, q), h);
+#pragma unroll
+                        for (int v = 0; v < 7; v++) m7[v] = mat_s[kq * RRT_MAT_STRIDE + v];
+                        shade(sc.shader, sc.max_depth, ob, m7, g, h, sr, rgb);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; c++) sum[c] += rgb[c];
+                }
+            }
+            const float v0 = sum[0] * inv, v1 = sum[1] * inv, v2 = sum[2] * inv;
+            if (active && img_s) { img_s[po] = v0; img_s[po + 1] = v1; img_s[po + 2] = v2; }
+            if (MODE == MODE_FUSED) {
+                float gc[3] = {0.f, 0.f, 0.f};
+                if (active) {
+                    const float d0 = v0 - tgt[0], d1 = v1 - tgt[1], d2 = v2 - tgt[2];
+                    loss_part += P.cw[0] * d0 * d0 + P.cw[1] * d1 * d1 + P.cw[2] * d2 * d2;
+                    gc[0] = 2.0f * P.cw[0] * d0 * inv;
+                    gc[1] = 2.0f * P.cw[1] * d1 * inv;
+                    gc[2] = 2.0f * P.cw[2] * d2 * inv;
+                }
+                // ---- reverse pass through the winners: the samples of a pixel usually share their
+                // winner, so their sums meet in registers and reach the thread's column once per pixel
+                const bool gnz = (gc[0] != 0.f) | (gc[1] != 0.f) | (gc[2] != 0.f);
+                if (__any_sync(full, gnz && any_hit)) {
+                    float da[NACC], dg[9];
+#pragma unroll
+                    for (int v = 0; v < NACC; v++) da[v] = 0.f;
+#pragma unroll
+                    for (int v = 0; v < 9; v++) dg[v] = 0.f;
+                    bool pend = false, touched = false;
+#pragma unroll 1
+                    for (int q = 0; q < SP; q++) {
+                        const int key = gnz ? pick(idx, q) : -1;
+                        const bool change = (key >= 0) && (acc_key >= 0) && (key != acc_key);
+                        if (__any_sync(full, change)) {          // some lane's winner changed: flush the warp's sums
+                            if (pend) {
+#pragma unroll
+                                for (int v = 0; v < NACC; v++) { acc_col[v * kSmallThreads] += da[v]; da[v] = 0.f; }
+                                pend = false;
+                            }
+                            small_warp_flush<NACC>(acc_key, acc_col, slots, lane, det_ws);
+                            acc_key = -1;
+                        }
+                        if (key >= 0) {
+                            Obj ob;
+                            HitRec h;
+                            ShadeRec sr;
+                            float m7[7], rgb[3], wx, wy, wz;
+                            const float rx = pick(rcx, q), ry = pick(rcy, q);
+                            load_rec(tab + 4 * key, ob);
+                            world(rx, ry, wx, wy, wz);
+                            hit_record<true>(ob, wx, wy, wz, pick(tmin, q), h);
+#pragma unroll
+                            for (int v = 0; v < 7; v++) m7[v] = mat_s[key * RRT_MAT_STRIDE + v];
+                            shade(sc.shader, sc.max_depth, ob, m7, g, h, sr, rgb);
+                            const float rc3[3] = {rx, ry, rcz};
+                            backward_ray<GEOM, NACC>(sc.shader, sc.max_depth, ob, m7, g, h, sr, rc3, gc, da, dg);
+                            acc_key = key;
+                            pend = touched = true;
+                        }
+                    }
+                    if (pend) {
+#pragma unroll
+                        for (int v = 0; v < NACC; v++) acc_col[v * kSmallThreads] += da[v];
+                    }
+                    if (!GEOM && touched) {            // light / look_at sums are not keyed by object
+#pragma unroll
+                        for (int v = 0; v < 9; v++) gg_col[v * kSmallThreads] += dg[v];
+                    }
+                }
+            }
+            continue;
+        }
         const bool mir = MIRROR && mirror_on && g.cam_identity && g.ct[0] == 0.f && g.ct[1] == 0.f && g.ct[2] == 0.f;
 
         const unsigned gid = blk * kSmallThreads + tid;      // ray index within the scene: [rows][n][S]
@@ -449,7 +704,6 @@ __global__ void __launch_bounds__(kSmallThreads, RRT_SMALL_MIN_BLOCKS) render_sm
             }
         }
     }
-    if (cur_scene >= 0) flush_scene(true);
 
     if (MODE != MODE_FWD && STEP) {
         // ---- the rest of the optimise step, by the LAST CTA to get here (ticket): finalize the

@@ -39,6 +39,8 @@ class RenderConfig:
     use_ticket: int = 1                 # 0: never fold the gradient finalisation into the render kernel (A/B, tests)
     deterministic: int = 0              # 1: RRT_FLAG_DETERMINISTIC -- gradients and loss bit-identical from run to run
                                         # (fixed-point accumulation across warps / CTAs instead of float atomics)
+    pixel_threads: int = 0              # small-scene kernel thread mapping: 0 = the library's choice, 1 = force one pixel per
+                                        # thread where it applies (RRT_FLAG_PIXEL_THREADS), 2 = force one ray per thread
     canonical_sweep: int = 0            # 1: RRT_FLAG_CANONICAL_SWEEP -- no conservative pre-filter in the sweep (same bits,
                                         # every pair evaluated with the reference's arithmetic; A/B, roofline accounting)
 
@@ -148,7 +150,9 @@ class _Tables:
                    (nat.FLAG_SHADOWS if cfg.shadows else 0) | (nat.FLAG_SCALAR_SHADOWS if cfg.shadows == 2 else 0) |
                    (nat.FLAG_NO_MATERIAL_GRAD if cfg.geom_grad_only else 0) |
                    (nat.FLAG_CANONICAL_SWEEP if cfg.canonical_sweep else 0) |
-                   (nat.FLAG_DETERMINISTIC if cfg.deterministic else 0))
+                   (nat.FLAG_DETERMINISTIC if cfg.deterministic else 0) |
+                   (nat.FLAG_PIXEL_THREADS if cfg.pixel_threads == 1 else 0) |
+                   (nat.FLAG_RAY_THREADS if cfg.pixel_threads == 2 else 0))
         d.max_depth, d.camera_grad, d.seed = cfg.max_depth, cfg.camera_grad, cfg.seed & 0xFFFFFFFFFFFFFFFF
         d.obj_type, d.w2o, d.material = self.obj_type.data_ptr(), self.w2o.data_ptr(), self.material.data_ptr()
         d.light, d.camera = self.light.data_ptr(), self.camera.data_ptr()

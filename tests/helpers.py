@@ -7,6 +7,7 @@ from reversible_raytracer_b200.render import RenderConfig
 # Set by the parity module's `kernel_choice` fixture: True forces the general 8-rays-per-thread
 # kernel where the small-scene kernel would be chosen, so every case is checked on both.
 NO_SMALL = False
+PIXEL_THREADS = 0      # 1: force the pixel-per-thread mapping of the small-scene kernel where it applies, 2: ray-per-thread
 USE_RECORDS = True     # False: the kernels build the sweep records per CTA instead of TMA-staging a prebuilt table
 
 
@@ -16,7 +17,7 @@ def to_device(ps, device, with_jitter=True):
                        max_depth=ps.max_depth, camera_grad=ps.camera_grad, seed=ps.seed,
                        row_begin=ps.row_begin, row_count=ps.row_count, scene_begin=getattr(ps, 'scene_begin', 0),
                        no_small=int(NO_SMALL), shadows=int(getattr(ps, 'shadows', 0)),
-                       use_records=int(USE_RECORDS))
+                       use_records=int(USE_RECORDS), pixel_threads=int(PIXEL_THREADS))
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
     w2o = t(ps.w2o) if ps.B > 1 else t(ps.w2o[0])
     jitter = None

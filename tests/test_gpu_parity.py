@@ -18,14 +18,17 @@ from helpers import to_device, block_rel_err
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=['auto', 'general', 'norecords'], autouse=True)
+@pytest.fixture(params=['auto', 'general', 'norecords', 'pixel', 'ray'], autouse=True)
 def kernel_choice(request, monkeypatch):
-    """Every case runs three times: with the library's own choices (small scenes take the
-    one-ray-per-thread kernel, >= 64 objects get a prebuilt record table staged by TMA), with
-    the general kernel forced (RRT_FLAG_NO_SMALL), and with the record table switched off (the
-    kernels build the sweep records per CTA)."""
+    """Every case runs five times: with the library's own choices (small scenes take the small-scene
+    kernel -- one ray per thread for a single image, one pixel per thread for big batches --, >= 64
+    objects get a prebuilt record table staged by TMA), with the general kernel forced
+    (RRT_FLAG_NO_SMALL), with the record table switched off (the kernels build the sweep records
+    per CTA), and with each thread mapping of the small-scene kernel forced (RRT_FLAG_PIXEL_THREADS
+    / RRT_FLAG_RAY_THREADS)."""
     monkeypatch.setattr(helpers, 'NO_SMALL', request.param == 'general')
     monkeypatch.setattr(helpers, 'USE_RECORDS', request.param != 'norecords')
+    monkeypatch.setattr(helpers, 'PIXEL_THREADS', {'pixel': 1, 'ray': 2}.get(request.param, 0))
     return request.param
 
 PIX_RTOL, PIX_ATOL, GRAD_TOL = 1e-4, 1e-5, 1e-3
@@ -629,8 +632,11 @@ def test_no_material_grad_flag_and_in_kernel_finalize(name, cuda):
     assert tk is not None and int(tk.abs().sum()) == 0
 
 
-def test_many_small_scenes_persistent_ctas(cuda):
-    """The small-scene kernel's persistent CTAs walk contiguous ranges of work items that cross
+@pytest.mark.parametrize('mapping', [1, 2])
+def test_many_small_scenes_persistent_ctas(mapping, cuda):
+    """(Both thread mappings of the batch: 1 = one pixel per thread, 2 = one ray per thread; the
+    single-scene launches it is compared with take the library's own choice.)
+    The small-scene kernel's persistent CTAs walk contiguous ranges of work items that cross
     scene boundaries (here 3000 scenes of 2 items: every CTA serves several scenes, flushing its
     sums, reloading the tables and taking a per-scene ticket at each boundary).  Per-scene loss,
     gradient, image and masks must equal single-scene launches of the same scenes."""
@@ -643,7 +649,8 @@ def test_many_small_scenes_persistent_ctas(cuda):
     cfg = R.RenderConfig(n=n, samples=4, shader=tb['shader'], transpose=0, seed=11, camera_grad=1)
     ot, mat, light, cam, w2o_d = t(tb['obj_type']), t(tb['material']), t(tb['light']), t(tb['camera']), t(w2o)
     target = torch.rand((B, n, n, 3), device=cuda)
-    loss, grad, image, hit = R.render_fused_mse(cfg, ot, w2o_d, mat, light, cam, target, want_image=True, want_hit=True)
+    loss, grad, image, hit = R.render_fused_mse(replace(cfg, pixel_threads=mapping), ot, w2o_d, mat, light, cam, target,
+                                                want_image=True, want_hit=True)
     dl = torch.randn_like(image)
     gb = R.render_backward(cfg, ot, w2o_d, mat, light, cam, dl, None)
     for b in (0, 1, 2, 777, 1500, 2998, 2999):
@@ -850,3 +857,46 @@ def test_non_integer_shininess_nan_propagates_like_the_reference(cuda):
     got = img.cpu().numpy().reshape(img_o.shape)
     assert np.array_equal(np.isnan(got), np.isnan(img_o))
     np.testing.assert_allclose(got, img_o, rtol=1e-3, atol=1e-5, equal_nan=True)
+
+
+@pytest.mark.parametrize('name', ['C1_optimize_brightness', 'C2_test_balls_depth', 'C3_match_mirror_square', 'C4_orbit_view1',
+                                  'S1', 'S2', 'ragged_n1', 'ragged_n5'])
+@pytest.mark.parametrize('geom', [0, 1])
+def test_pixel_and_ray_thread_mappings_agree(name, geom, cuda):
+    """The two thread mappings of the small-scene kernel (one pixel per thread with its S samples in
+    registers, 8 x 4 pixel tiles per warp / one ray per thread, samples combined by shuffles) run the
+    same device routines in the same sample order: masks, tmin and pixels are bit-identical, loss and
+    gradients agree up to the reduction order.  Also as row slabs whose height is not a multiple of
+    the tile height, and in deterministic mode (where the two mappings must agree to the last bits
+    the fixed-point sums keep)."""
+    ps = oc.PackedScene.from_spec(CASES[name](), camera_grad=1)
+    cfg, ot, w2o, mat, light, cam, jit = to_device(ps, cuda)
+    cfg = replace(cfg, no_small=0, geom_grad_only=geom)
+    pix, ray = replace(cfg, pixel_threads=1), replace(cfg, pixel_threads=2)
+    a = R.render_forward(pix, ot, w2o, mat, light, cam, jit, want_hit=True, want_tmin=True)
+    b = R.render_forward(ray, ot, w2o, mat, light, cam, jit, want_hit=True, want_tmin=True)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2].view(torch.int32), b[2].view(torch.int32))
+    assert torch.equal(a[0].view(torch.int32), b[0].view(torch.int32)), float((a[0] - b[0]).abs().max())
+    target = (a[0] * 0.5 + 0.1).contiguous()
+    for det in (0, 1):
+        la, ga, ia, ha = R.render_fused_mse(replace(pix, deterministic=det), ot, w2o, mat, light, cam, target, None, jit,
+                                            want_image=True, want_hit=True)
+        lb, gb, ib, hb = R.render_fused_mse(replace(ray, deterministic=det), ot, w2o, mat, light, cam, target, None, jit,
+                                            want_image=True, want_hit=True)
+        assert torch.equal(ha, hb) and torch.equal(ia.view(torch.int32), ib.view(torch.int32))
+        np.testing.assert_allclose(float(la.sum()), float(lb.sum()), rtol=1e-6)
+        assert float(gb.abs().max()) > 0 or ps.n == 1
+        assert float((ga - gb).abs().max()) <= (2e-5 if det else 1e-4) * max(float(gb.abs().max()), 1e-30)
+    # a row slab that starts inside a tile row and is not a multiple of 4 rows high, in-kernel jitter
+    if ps.n >= 5:
+        rb, rc = 1, min(ps.n - 1, 7)
+        sp, sr = replace(pix, row_begin=rb, row_count=rc, seed=77), replace(ray, row_begin=rb, row_count=rc, seed=77)
+        a = R.render_forward(sp, ot, w2o, mat, light, cam, None, want_hit=True, want_tmin=True)
+        b = R.render_forward(sr, ot, w2o, mat, light, cam, None, want_hit=True, want_tmin=True)
+        assert torch.equal(a[1], b[1]) and torch.equal(a[2].view(torch.int32), b[2].view(torch.int32))
+        assert torch.equal(a[0].view(torch.int32), b[0].view(torch.int32))
+        tgt = torch.zeros_like(a[0])
+        la, ga, _, _ = R.render_fused_mse(sp, ot, w2o, mat, light, cam, tgt)
+        lb, gb, _, _ = R.render_fused_mse(sr, ot, w2o, mat, light, cam, tgt)
+        np.testing.assert_allclose(float(la.sum()), float(lb.sum()), rtol=1e-6)
+        assert float((ga - gb).abs().max()) <= 1e-4 * max(float(gb.abs().max()), 1e-30)
