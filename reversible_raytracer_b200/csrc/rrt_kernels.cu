@@ -164,7 +164,7 @@ int sm_count() {
 // forward and fused modes, S in {1, 2, 4}, no shadows / mirror bounce.  Taken by default when the
 // call has enough pixels to fill the machine with pixel threads (batches of scenes); a single small
 // image keeps one ray per thread (4 x the threads, shorter dependency chains).
-constexpr long long kPixelMinPixels = 96 * 1024;
+constexpr long long kPixelMinPixels = 192 * 1024;   // measured crossover on the orbit batch: 16 scene pairs (131 k pixels) ray threads, 32 pixel threads
 bool use_pixel_threads(const KParams& P, int mode) {
     const rrt_scene& sc = P.sc;
     const int S = sc.samples;
@@ -175,16 +175,14 @@ bool use_pixel_threads(const KParams& P, int mode) {
 }
 
 // Persistent grid of the small-scene kernel: at most one resident wave, every CTA >= 1 work item.
-unsigned small_grid(KParams& P, bool pixel = false) {
+unsigned small_grid(KParams& P, bool pixel = false, int pixel_blocks = RRT_PIXEL_MIN_BLOCKS) {
     const rrt_scene& sc = P.sc;
     const long long rays_scene = (long long)P.rows * sc.n * sc.samples;
     long long items_scene = (rays_scene + kSmallThreads - 1) / kSmallThreads;
-    if (pixel) {        // tiles of 8 x 4 pixels, one per warp
-        const long long tiles = (long long)((sc.n + kPixTileW - 1) / kPixTileW) * ((P.rows + kPixTileH - 1) / kPixTileH);
-        items_scene = (tiles + kSmallThreads / 32 - 1) / (kSmallThreads / 32);
-    }
+    if (pixel)          // tiles of 8 x 4 pixels, one per warp; a work item is a 2 x 2 block of tiles
+        items_scene = (long long)((sc.n + 2 * kPixTileW - 1) / (2 * kPixTileW)) * ((P.rows + 2 * kPixTileH - 1) / (2 * kPixTileH));
     const long long total = items_scene * sc.num_scenes;
-    const long long cap = (long long)sm_count() * (pixel ? RRT_PIXEL_MIN_BLOCKS : RRT_SMALL_MIN_BLOCKS);
+    const long long cap = (long long)sm_count() * (pixel ? pixel_blocks : RRT_SMALL_MIN_BLOCKS);
     long long per = (total + cap - 1) / cap;
     if (per < 1) per = 1;
     P.small_per = (int)per;
@@ -210,7 +208,7 @@ int launch(KParams& P, cudaStream_t st, bool* finalized = nullptr) {
     if (use_small_kernel(P)) {
         const bool geom = MODE != MODE_FWD && (sc.flags & RRT_FLAG_NO_MATERIAL_GRAD);
         const bool pixel = use_pixel_threads(P, MODE);
-        const unsigned grid = small_grid(P, pixel);
+        const unsigned grid = small_grid(P, pixel, pixel_min_blocks(MODE, geom));
         if (pixel) {
             constexpr int PM = MODE == MODE_BWD ? MODE_FUSED : MODE;     // (never taken for MODE_BWD)
             void (*kern)(const KParams) = nullptr;

@@ -56,7 +56,7 @@ __device__ __forceinline__ void small_warp_flush(int key, float* acc_col, float*
 // pixels): one thread owns one pixel and its SPP = S anti-alias samples (S in {1, 2, 4}), a warp
 // covers a compact tile of 8 x 4 pixels (a warp meets an object's silhouette about half as often as
 // with a 32 x 1 strip, and the shading / reverse-pass code is only entered by warps that hit
-// something), a work item is 4 consecutive tiles (one per warp).  What the ray-per-thread form pays
+// something), a work item is a 2 x 2 block of tiles (one per warp).  What the ray-per-thread form pays
 // per RAY is paid per PIXEL: index arithmetic, the camera-space grid ray, the target load, the loss,
 // the image store; the pixel mean is a register sum in sample order (same bits as the shuffles of
 // the ray-per-thread form); the S samples of a pixel give the sweep S independent dependency
@@ -83,12 +83,18 @@ __device__ __forceinline__ T pick(const T (&a)[NQ], int q) {
     for (int i = 1; i < NQ; i++) v = (q == i) ? a[i] : v;
     return v;
 }
+// resident CTAs per SM of the pixel-per-thread form (measured on the orbit batch): 5 (<= 102 registers) for the
+// forward and the d/d w2o-only kernels, 4 (<= 128) when all 19 + 9 gradient sums are live (98 / 119 us; 5: 98 / 130 us)
 #ifndef RRT_PIXEL_MIN_BLOCKS
 #define RRT_PIXEL_MIN_BLOCKS 5
 #endif
+#ifndef RRT_PIXEL_MIN_BLOCKS_ALL
+#define RRT_PIXEL_MIN_BLOCKS_ALL 4
+#endif
+constexpr int pixel_min_blocks(int mode, bool geom) { return (mode == MODE_FWD || geom) ? RRT_PIXEL_MIN_BLOCKS : RRT_PIXEL_MIN_BLOCKS_ALL; }
 
 template <int MODE, bool STEP = false, bool GEOM = false, bool MIRROR = false, int SPP = 0>
-__global__ void __launch_bounds__(kSmallThreads, SPP > 0 ? RRT_PIXEL_MIN_BLOCKS : RRT_SMALL_MIN_BLOCKS)
+__global__ void __launch_bounds__(kSmallThreads, SPP > 0 ? pixel_min_blocks(MODE, GEOM) : RRT_SMALL_MIN_BLOCKS)
 render_small_kernel(const __grid_constant__ KParams P) {
     static_assert(SPP == 0 || (!STEP && !MIRROR && MODE != MODE_BWD), "pixel-per-thread form: forward / fused only");
     constexpr int NACC = GEOM ? 12 : 19;
@@ -110,9 +116,11 @@ render_small_kernel(const __grid_constant__ KParams P) {
     // 32-bit index arithmetic (the launcher guarantees rows*n*S < 2^31 and a total below 2^31; S is a power of two)
     const unsigned rays_scene = (unsigned)P.rows * (unsigned)n * (unsigned)S;
     // pixel-per-thread form: tiles of 8 x 4 pixels, 4 tiles (one per warp) per work item
-    const unsigned tiles_x = ((unsigned)n + kPixTileW - 1) / kPixTileW;
-    const unsigned ntiles = tiles_x * (((unsigned)P.rows + kPixTileH - 1) / kPixTileH);
-    const unsigned bps = SPP > 0 ? (ntiles + kSmallThreads / 32 - 1) / (kSmallThreads / 32)
+    // (a work item = the 2 x 2 block of tiles of its 4 warps, 16 x 8 pixels: compact, so the warps of a CTA
+    // meet an object together and reach the scene barriers together)
+    const unsigned items_x = ((unsigned)n + 2 * kPixTileW - 1) / (2 * kPixTileW);
+    const unsigned items_y = ((unsigned)P.rows + 2 * kPixTileH - 1) / (2 * kPixTileH);
+    const unsigned bps = SPP > 0 ? items_x * items_y
                                  : (rays_scene + kSmallThreads - 1) / kSmallThreads;      // work items per scene
     const unsigned total = bps * (unsigned)sc.num_scenes;
     const unsigned item0 = blockIdx.x * (unsigned)P.small_per;
@@ -306,11 +314,10 @@ render_small_kernel(const __grid_constant__ KParams P) {
         if (SPP > 0) {
             // ================= pixel-per-thread form: this thread's pixel and its S = SPP samples
             constexpr int SP = SPP > 0 ? SPP : 1;
-            const unsigned tile = blk * (kSmallThreads / 32) + (unsigned)warp;
-            const unsigned tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
-            const int al = (int)(tyi * kPixTileH) + (lane >> 3);
-            const int b = (int)(txi * kPixTileW) + (lane & 7);
-            const bool active = (tile < ntiles) && (al < P.rows) && (b < n);
+            const unsigned iy = blk / items_x, ix = blk - iy * items_x;
+            const int al = (int)((2u * iy + ((unsigned)warp >> 1)) * kPixTileH) + (lane >> 3);
+            const int b = (int)((2u * ix + ((unsigned)warp & 1u)) * kPixTileW) + (lane & 7);
+            const bool active = (al < P.rows) && (b < n);
             const int a = sc.row_begin + al;
             const unsigned pl = active ? (unsigned)al * (unsigned)n + (unsigned)b : 0u;
             const unsigned po = pl * 3u;
