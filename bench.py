@@ -402,6 +402,11 @@ def c4_sharded(dev, world, rank, timer, scenes=256):
         ms, _ = timer.run(step, 20, warm=3, flush=False)
         info.update(ms_per_step=round(ms / 20, 4), Mrays_s=round(2.0 * total * 64 * 64 * 4 / (ms / 20 * 1e-3) / 1e6, 1),
                     collective='1 NCCL allreduce of the flat encoder-weight gradient + loss per step' if world > 1 else 'none')
+        # the same step captured into ONE CUDA graph (encoder, render launch, NCCL allreduce, SGD update)
+        gstep, ginfo = mod.make_trainer(total, dev=dev, world=world, rank=rank, graph=True)
+        gms, _ = timer.run(gstep, 50, warm=3, flush=False)
+        info.update(cuda_graph=dict(captured=ginfo['cuda_graph'], ms_per_step=round(gms / 50, 4),
+                                    Mrays_s=round(2.0 * total * 64 * 64 * 4 / (gms / 50 * 1e-3) / 1e6, 1)))
         out[key] = info
     return out
 

@@ -32,8 +32,12 @@ class Encoder(torch.nn.Module):
         return torch.cat([c[..., :2], torch.relu(c[..., 2:])], dim=-1)
 
 
-def make_trainer(num_scenes=256, lr=2e-8, n=64, seed=1234, dev=None, world=1, rank=0):
-    """-> (step, info): `step()` runs ONE training step of the batched orbit autoencoder on this
+def make_trainer(num_scenes=256, lr=2e-8, n=64, seed=1234, dev=None, world=1, rank=0, graph=False):
+    """`graph=True`: after three eager steps the WHOLE training step (encoder forward, fused render
+    launch, encoder backward, the NCCL allreduce, SGD update) is captured into ONE CUDA graph and
+    `step()` replays it -- the counterpart of the reference's single compiled `train` function
+    (orbit_experiments/optimize.py:75-93); falls back to eager stepping if the capture fails.
+    -> (step, info): `step()` runs ONE training step of the batched orbit autoencoder on this
     rank's scene range -- encoder forward (stock PyTorch), decoder = ONE fused render + squared
     error + reverse-pass launch (only d/d w2o is requested: materials, light and camera are
     constants, autoencoder_2ly.py:82-91), encoder backward, ONE flat NCCL allreduce of the
@@ -77,11 +81,41 @@ def make_trainer(num_scenes=256, lr=2e-8, n=64, seed=1234, dev=None, world=1, ra
             loss = flat[-1]
         opt.step()
         return loss.detach()
-    return step, dict(scenes_per_rank=count, views_per_rank=B, encoder_parameters=nparam,
-                      allreduce_bytes=(nparam + 1) * 4 if world > 1 else 0, rays_per_rank=B * n * n * 4)
+    info = dict(scenes_per_rank=count, views_per_rank=B, encoder_parameters=nparam,
+                allreduce_bytes=(nparam + 1) * 4 if world > 1 else 0, rays_per_rank=B * n * n * 4, cuda_graph=False)
+    if not graph:
+        return step, info
+    # ---- whole step as one CUDA graph (warm-up on a side stream, like torch's whole-network capture recipe)
+    eager = step
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            eager()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    ok = torch.ones(1, device=dev)
+    g, out = torch.cuda.CUDAGraph(), None
+    try:
+        with torch.cuda.graph(g):
+            out = eager()
+    except Exception as e:          # noqa: BLE001
+        sys.stderr.write('orbit_autoencoder: capture of the training step failed (%r); stepping eagerly\n' % (e,))
+        ok.zero_()
+        torch.cuda.synchronize(dev)
+    if world > 1:                   # all ranks replay, or none does (the graph contains a collective)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if float(ok) < 1:
+        return eager, info
+    info['cuda_graph'] = True
+
+    def replay():
+        g.replay()
+        return out
+    return replay, info
 
 
-def main(num_scenes=256, steps=30, lr=2e-8, n=64, seed=1234, verbose=True):
+def main(num_scenes=256, steps=30, lr=2e-8, n=64, seed=1234, verbose=True, graph=False):
     """Single GPU, or `torchrun --nproc-per-node G examples/orbit_autoencoder.py`: the scene
     batch is sharded across ranks (sharding.scene_range), every rank renders and
     back-propagates its own scenes, and ONE flat allreduce sums the encoder-weight
@@ -93,7 +127,7 @@ def main(num_scenes=256, steps=30, lr=2e-8, n=64, seed=1234, verbose=True):
     dev = torch.device('cuda', local)
     if world > 1 and not dist.is_initialized():
         dist.init_process_group('nccl', device_id=dev)
-    step, _ = make_trainer(num_scenes, lr, n, seed, dev, world, rank)
+    step, _ = make_trainer(num_scenes, lr, n, seed, dev, world, rank, graph=graph)
     losses = []
     for k in range(steps):
         losses.append(float(step()))
@@ -103,4 +137,4 @@ def main(num_scenes=256, steps=30, lr=2e-8, n=64, seed=1234, verbose=True):
 
 
 if __name__ == '__main__':
-    main()
+    main(graph='--graph' in sys.argv)

@@ -303,6 +303,22 @@ def test_batched_autoencoder_decoder_trains(cuda):
     assert np.all(np.isfinite(losses)) and losses[-1] < losses[0]
 
 
+def test_autoencoder_training_step_as_one_cuda_graph(cuda):
+    """The whole training step (encoder forward, fused render launch, encoder backward, SGD update) captured
+    into ONE CUDA graph follows the eager trajectory (same seeds, same data)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('orbit_autoencoder', os.path.join(os.path.dirname(GOLD), '..', 'examples', 'orbit_autoencoder.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    eager, info_e = mod.make_trainer(16, dev=cuda)
+    le = [float(eager()) for _ in range(9)]
+    graphed, info_g = mod.make_trainer(16, dev=cuda, graph=True)           # 3 eager warm-up steps inside
+    assert info_g['cuda_graph'] and not info_e['cuda_graph']
+    lg = [float(graphed()) for _ in range(6)]
+    np.testing.assert_allclose(lg, le[3:], rtol=1e-4)
+    assert lg[-1] < le[0]
+
+
 def test_batched_w2o_helper_and_fused_loss_autograd(cuda):
     rng = np.random.RandomState(3)
     B = 5
