@@ -295,6 +295,10 @@ def other_configs(dev, peak_tf, hbm_gbs, with_cpu=True):
     out = {}
     train, _ = L.c1()
     out['C1_optimize_brightness_step_us'] = round(L.timeit(train, warm=6, iters=100), 1)
+    train, _ = L.c2(False)
+    out['C2_test_balls_step_us'] = round(L.timeit(train, warm=6, iters=100), 1)
+    train, _ = L.c2(True)
+    out['C2_test_balls_fused_step_us'] = round(L.timeit(train, warm=6, iters=100), 1)
     train, _ = L.c3(False)
     out['C3_match_mirror_step_us'] = round(L.timeit(train, warm=6, iters=100), 1)
     train, _ = L.c3('graph')

@@ -104,17 +104,20 @@ class ChainProgram(object):
                 row.append((kind, inv, offs))
             plan.append(row)
         # pass 2: live parameters follow the constant block, each distinct tensor once
-        self.param_tensors, slot_of, p_off = [], {}, n_const
+        # (the _Arg objects are kept, not their tensors: an argument that is a view of a leaf is taken
+        # again at every evaluation, see transform._Arg)
+        self.param_args, slot_of, p_off = [], {}, n_const
         for row in plan:
             for kind, inv, offs in row:
                 for o in offs:
                     if o[0] == 'p':
-                        src = o[1].src
-                        if id(src) not in slot_of:
-                            slot_of[id(src)] = p_off
-                            self.param_tensors.append(src)
-                            p_off += src.numel()
-                        o[1], o[2] = slot_of[id(src)], src.numel()
+                        arg = o[1]
+                        numel = arg.src.numel()
+                        if arg.key not in slot_of:
+                            slot_of[arg.key] = p_off
+                            self.param_args.append(arg)
+                            p_off += numel
+                        o[1], o[2] = slot_of[arg.key], numel
         key = (tuple(tuple((kind, inv, tuple(tuple(o) for o in offs)) for kind, inv, offs in row) for row in plan),
                n_const, p_off)
         st = _STRUCTURES.get((key, str(device)))
@@ -124,8 +127,13 @@ class ChainProgram(object):
             st = _STRUCTURES[(key, str(device))] = _Structure(key, device)
         self.structure = st
         self.ops, self.chain_begin, self.const_block, self.num_values = st.ops, st.chain_begin, st.const_block, st.num_values
-        self.dynamic = len(self.param_tensors) > 0
+        self.dynamic = len(self.param_args) > 0
         self._static_out = None
+
+    @property
+    def param_tensors(self):
+        """the live parameter tensors, in slot order (views of leaves are re-taken on every access)"""
+        return [a.src for a in self.param_args]
 
     def values(self):
         """cat(constants, live parameters) as float32 on the program's device (the cast is done

@@ -64,16 +64,41 @@ class _Arg(object):
     """One argument of a primitive transform: a LIVE parameter (any torch tensor handed in by the
     user -- re-read on every evaluation, cast to float32 lazily so that in-place optimiser updates of
     a float64 / half parameter are seen, like a theano.shared variable) or a constant (host value
-    kept for the chain compiler, device tensor from the by-value cache)."""
-    __slots__ = ('src', 'host', 'param')
+    kept for the chain compiler, device tensor from the by-value cache).
+
+    A live parameter that is a VIEW OF A LEAF tensor -- the reference's idiom
+    `translate(obj_param[:3]) * scale(obj_param[3:])` (test_balls.py:27, autoencoder.py:60) -- is kept
+    as (leaf, size, stride, offset) and the view is taken AGAIN on every evaluation.  Like indexing a
+    theano.shared symbolically, the view then follows the leaf whatever happened in between: it tracks
+    gradients even if `requires_grad_` was set after the slice was written, and its autograd nodes are
+    created inside the optimiser step (on the step's stream) instead of being pinned to the stream of
+    the construction site, which is what lets such a closure be captured into a CUDA graph."""
+    __slots__ = ('_src', '_view', 'host', 'param', 'key')
 
     def __init__(self, x, device=None):
         self.param = isinstance(x, torch.Tensor)
+        self._view = None
         if self.param:
-            self.src, self.host = x, None
+            self.host = None
+            base = x._base if x._is_view() else None
+            if base is not None and base.is_leaf and base.layout == torch.strided and x.layout == torch.strided:
+                self._view = (base, tuple(x.shape), tuple(x.stride()), int(x.storage_offset()))
+                self._src = None
+                self.key = ('view', id(base)) + self._view[1:]      # parameter identity for the chain compiler
+            else:
+                self._src = x
+                self.key = ('tensor', id(x))
         else:
             self.host = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
-            self.src = as_tensor(self.host, device=device)
+            self._src = as_tensor(self.host, device=device)
+            self.key = None
+
+    @property
+    def src(self):
+        if self._view is not None:
+            base, size, stride, offset = self._view
+            return base.as_strided(size, stride, offset)
+        return self._src
 
     @property
     def t(self):
@@ -83,7 +108,7 @@ class _Arg(object):
 
     @property
     def device(self):
-        return self.src.device
+        return self._view[0].device if self._view is not None else self._src.device
 
 
 class RayField(object):

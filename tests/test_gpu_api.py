@@ -272,6 +272,37 @@ def test_graph_capture_survives_reference_closure_style(cuda):
     np.testing.assert_allclose(c_g, c_e, rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize('fused', [False, True])
+def test_graph_capture_with_sliced_leaf_parameters_c2(fused, cuda):
+    """BASELINE config C2 in the reference's idiom (test_balls.py:22-44): two spheres
+    translate(p[:3]) * scale(p[3:]), DepthMapShader, squared error of channel 0, gradient descent
+    directly on the two 6-vectors -- which are made trainable by optimize() AFTER the slices were
+    written.  The slices are re-taken per evaluation (transform._Arg), so gradients reach p, the
+    step is captured into a CUDA graph (no autograd node pinned to the construction stream), and the
+    graph-replayed trajectory equals eager stepping."""
+    def make():
+        p1 = torch.tensor([-.4, -.3, 3., .5, .5, .5], device=cuda)
+        p2 = torch.tensor([.4, .3, 3., .5, .5, .5], device=cuda)
+        m = Material((0.2, 0.9, 0.4), 0.3, 0.7, 0.5, 50.)
+        sc = Scene([Sphere(translate(p[:3]) * scale(p[3:]), m) for p in (p1, p2)],
+                   [Light((-1., -1., 2.), (0.961, 1., 0.87))], Camera(32, 32), DepthMapShader(6.1))
+        X = torch.full((32, 32), 0.25, device=cuda)
+        X3 = X[:, :, None].expand(32, 32, 3).contiguous()
+        cost = (lambda: sc.build_mse(X3, channel_weight=(1., 0., 0.), seed=15)) if fused else \
+            (lambda: ((X - sc.build(seed=15)[:, :, 0]) ** 2).sum())
+        return p1, p2, cost
+    p1, p2, cost = make()
+    train = GDOptimizer().optimize([p1, p2], cost, 0.0005, 0.0)
+    lg = [train() for _ in range(8)]
+    assert train.state['graph'] is not None and not train.state['failed']
+    q1, q2, cost_e = make()
+    eager = GDOptimizer().optimize([q1, q2], cost_e, 0.0005, 0.0, graph=False)
+    le = [eager() for _ in range(8)]
+    np.testing.assert_allclose(lg, le, rtol=1e-4)
+    assert lg[-1] < lg[0] and float((p1 - q1).abs().max()) < 1e-4
+    assert float((p1.detach() - torch.tensor([-.4, -.3, 3., .5, .5, .5], device=cuda)).abs().max()) > 1e-4
+
+
 def test_graph_capture_validation_catches_host_state(cuda):
     """A closure that reads host-side state which changes per call (here: the jitter seed) cannot be
     replayed faithfully; the post-capture validation (replay with lr = 0 vs an eager evaluation)

@@ -107,6 +107,32 @@ def test_lazy_transform_tracks_inplace_updates_and_autograd():
     np.testing.assert_allclose(s.w2o.m[:3, 3].detach().numpy(), [0.0, -0.5, -1.0])   # re-evaluated
 
 
+def test_slices_of_a_leaf_parameter_stay_live_like_indexing_a_shared_variable():
+    """The reference's idiom translate(p[:3]) * scale(p[3:]) (test_balls.py:27): the slices are views of
+    a leaf, taken again on every evaluation -- they follow the leaf even when requires_grad_ is set
+    AFTER the scene was written (GDOptimizer.optimize does that), see in-place updates, share one
+    parameter slot per distinct slice in the chain compiler, and keep no autograd node of the
+    construction site alive."""
+    from reversible_raytracer_b200.chain import ChainProgram, flatten
+    p = torch.tensor([1., 2., 3., 2., 4., 8.])                       # no requires_grad yet
+    tr = T.translate(p[:3]) * T.scale(p[3:])
+    p.requires_grad_(True)
+    w = tr.inverse().m                                               # w2o = S^-1 T^-1
+    np.testing.assert_allclose(w[:3, 3].detach().numpy(), [-0.5, -0.5, -0.375])
+    w[:3, 3].sum().backward()
+    np.testing.assert_allclose(p.grad.numpy(), [-0.5, -0.25, -0.125, 0.25, 0.125, 0.046875])
+    with torch.no_grad():
+        p[:3] = torch.tensor([0., 0., 0.])
+    np.testing.assert_allclose(tr.inverse().m[:3, 3].detach().numpy(), [0., 0., 0.], atol=0)
+    args = [a for _, _, aa in flatten(tr.inverse()) for a in aa]
+    assert all(a.param and a._view is not None and a._src is None for a in args)
+    assert len({a.key for a in args}) == 2 and args[0].src.data_ptr() != args[1].src.data_ptr()
+    # a non-view tensor and a computed (non-leaf) tensor are kept as they are
+    q = torch.tensor([1., 2., 3.], requires_grad=True)
+    a1, a2 = T._Arg(q), T._Arg(q * 2.0)
+    assert a1._view is None and a1.src is q and a2._view is None
+
+
 def _random_chain(rng, depth):
     """A random translate / scale / rotate product, in the product's algebra and the oracle's."""
     prod, ref, flat = None, None, []

@@ -40,6 +40,29 @@ def c1():
     return train, sc
 
 
+def c2(fused=False):
+    """BASELINE config C2 (test_balls.py:22-44): two spheres translate(p[:3]) * scale(p[3:]), DepthMapShader(6.1),
+    32 x 32, loss = sum((X - image[:, :, 0]) ** 2) against the reference's 15.jpg, gradient descent on both
+    6-vectors.  fused: the same cost through Scene.build_mse with channel weights (1, 0, 0)."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    img = np.load(os.path.join(root, 'tests', 'golden', 'balls_15.npy')).astype(np.float32)
+    if img.ndim == 3:
+        img = img[:, :, 0]
+    X = torch.tensor(img / 255.0, device='cuda')
+    p1 = torch.tensor([-.4, -.3, 3., .5, .5, .5], device='cuda', requires_grad=True)   # (before slicing: views made earlier would not track it)
+    p2 = torch.tensor([.4, .3, 3., .5, .5, .5], device='cuda', requires_grad=True)
+    m = Material((0.2, 0.9, 0.4), 0.3, 0.7, 0.5, 50.)
+    shapes = [Sphere(translate(p[:3]) * scale(p[3:]), m) for p in (p1, p2)]
+    sc = Scene(shapes, [Light((-1., -1., 2.), (0.961, 1., 0.87))], Camera(32, 32), DepthMapShader(6.1))
+    if fused:
+        X3 = X[:, :, None].expand(32, 32, 3).contiguous()
+        cost = lambda: sc.build_mse(X3, channel_weight=(1., 0., 0.), seed=15)
+    else:
+        cost = lambda: ((X - sc.build(seed=15)[:, :, 0]) ** 2).sum()
+    return GDOptimizer().optimize([p1, p2], cost, 0.0001, 0.0), sc
+
+
 def c3(fused):
     c1 = torch.tensor([-.5, -.5, 4.], device='cuda')
     c2 = torch.tensor([.5, .5, 4.], device='cuda')
