@@ -20,7 +20,7 @@ from reversible_raytracer_b200.optimize import MGDAutoOptimizer  # noqa: E402
 from reversible_raytracer_b200.util import get_epsilon, draw  # noqa: E402
 
 
-def main(num_epoch=200, epsilon=0.0001, num_capsule=2, out_dir=None, verbose=True):
+def main(num_epoch=200, epsilon=0.0001, num_capsule=2, out_dir=None, verbose=True, graph='auto'):
     dev = torch.device('cuda')
     img = np.load(os.path.join(ROOT, 'tests', 'golden', 'balls_15.npy')).astype(np.float32)
     if img.ndim == 3:
@@ -39,7 +39,8 @@ def main(num_epoch=200, epsilon=0.0001, num_capsule=2, out_dir=None, verbose=Tru
         return Scene(shapes, [light], Camera(img_sz, img_sz), DepthMapShader(6.1)).build(seed=15)
 
     ae = Autoencoder(scene, D, 300, 30, 10, num_capsule, device=dev)
-    train_ae = MGDAutoOptimizer(ae).optimize(train_data)
+    train_ae = MGDAutoOptimizer(ae).optimize(train_data, graph=graph)     # one CUDA-graph replay per epoch after two eager ones
+    main.last_state = train_ae.state
     losses = []
     for n in range(1, num_epoch + 1):
         eps = get_epsilon(epsilon, num_epoch, n)

@@ -251,29 +251,110 @@ class MGDAutoOptimizer(object):
     def __init__(self, ae):
         self.ae = ae
 
-    def optimize(self, train_data, lam=None, fixed_length=3):
+    def optimize(self, train_data, lam=None, fixed_length=3, graph='auto'):
+        """-> opt(lr) -> cost (root, optimize.py:68-84) or opt(i, lr) -> cost (orbit variant: sample index,
+        orbit_experiments/optimize.py:68-97).  Like the reference's ONE compiled `train` function, the whole
+        step (encoder, render, T.grad, update) becomes one CUDA-graph replay after two eager warm-up calls
+        (graph='auto'; same guards as GDOptimizer: replay-vs-eager validation, eager fallback with a
+        warning, `opt.recapture()`, graph=False).  The sample the orbit variant indexes is copied into a
+        static buffer before every replay, so `i` stays live."""
         ae = self.ae
         for p in ae.params:
             p.requires_grad_(True)
         orbit = lam is not None or (hasattr(train_data, 'dim') and train_data.dim() >= 3)
+        bias_scale = 0.1 if orbit else 1.0     # orbit variant: 1-D parameters (biases) move at 0.1 * lr
+        #                                        (orbit_experiments/optimize.py:80-81)
+        params = list(ae.params)
+        tensor_data = isinstance(train_data, torch.Tensor)
+        use_graph = bool(graph) and tensor_data and train_data.is_cuda and all(p.is_cuda for p in params)
+        st = dict(calls=0, graph=None, failed=False, stream=None, lr=None, lr_value=None, host=None, sample=None)
 
-        def step(cost, lr, bias_scale):
-            grads = torch.autograd.grad(cost, ae.params, allow_unused=True)
+        def cost_of(sample):
+            return ae.cost(sample[0], sample[1]) if orbit else ae.cost(sample)
+
+        def step(cost, lr):
+            grads = torch.autograd.grad(cost, params, allow_unused=True)
             with torch.no_grad():
-                for var, g in zip(ae.params, grads):
+                for var, g in zip(params, grads):
                     if g is None:
                         continue
-                    # orbit variant: 1-D parameters (biases) move at 0.1 * lr
-                    # (orbit_experiments/optimize.py:80-81)
-                    var.sub_((bias_scale if var.dim() == 1 else 1.0) * lr * g)
-            return float(cost.detach())
+                    k = bias_scale if var.dim() == 1 else 1.0
+                    if isinstance(lr, torch.Tensor):            # captured step: lr lives on the device
+                        var.addcmul_(g, lr.to(g.dtype), value=-k)
+                    else:
+                        var.sub_(k * lr * g)
+            return cost
+
+        def side_stream():
+            if st['stream'] is None:
+                st['stream'] = torch.cuda.Stream(device=params[0].device)
+            return st['stream']
+
+        def capture(sample):
+            dev = params[0].device
+            st['lr'] = torch.zeros((), dtype=torch.float32, device=dev)
+            st['sample'] = sample.detach().clone()               # static input of the recording
+            side = side_stream()
+            side.wait_stream(torch.cuda.current_stream(dev))
+            saved = [v.detach().clone() for v in params]
+            with torch.cuda.stream(side):
+                step(cost_of(st['sample']), st['lr'])
+            torch.cuda.current_stream(dev).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            st['host'] = torch.zeros((), dtype=torch.float32).pin_memory()
+            with torch.cuda.graph(g, stream=side):
+                value = step(cost_of(st['sample']), st['lr'])
+                st['host'].copy_(value.detach().to(torch.float32), non_blocking=True)
+            g.replay()                                           # lr = 0: validates without moving anything
+            torch.cuda.current_stream(dev).synchronize()
+            replayed = float(st['host'])
+            with torch.no_grad():
+                eager = float(cost_of(st['sample']).detach())
+                for v, s0 in zip(params, saved):
+                    v.copy_(s0)
+            if not abs(replayed - eager) <= 1e-3 * max(1.0, abs(eager)):
+                raise RuntimeError('replayed cost %r != eager cost %r: the cost reads host-side state that a '
+                                   'CUDA graph cannot see (e.g. unseeded anti-alias jitter drawn per call)' % (replayed, eager))
+            st['graph'] = g
+
+        def run(sample, lr):
+            st['calls'] += 1
+            if use_graph and st['graph'] is None and not st['failed'] and st['calls'] > 2:
+                try:
+                    capture(sample)
+                except Exception as e:     # noqa: BLE001
+                    warnings.warn('MGDAutoOptimizer: CUDA-graph capture of the step failed (%r); stepping eagerly' % (e,))
+                    st['failed'], st['graph'] = True, None
+                    torch.cuda.synchronize()
+            if st['graph'] is not None:
+                if st['lr_value'] != float(lr):
+                    st['lr'].fill_(float(lr))
+                    st['lr_value'] = float(lr)
+                if orbit:
+                    st['sample'].copy_(sample)                   # the indexed sample stays live across replays
+                st['graph'].replay()
+                torch.cuda.current_stream(st['lr'].device).synchronize()
+                return float(st['host'])
+            if use_graph:                  # eager steps of a to-be-captured trainer: on the private stream
+                cur, side = torch.cuda.current_stream(params[0].device), side_stream()
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    value = step(cost_of(sample), lr).detach()
+                cur.wait_stream(side)
+                return float(value)
+            return float(step(cost_of(sample), lr).detach())
 
         if orbit:
             def opt(i, lr):
-                return step(ae.cost(train_data[i, 0], train_data[i, 1]), lr, 0.1)
+                return run(train_data[i], lr)
         else:
             def opt(lr):
-                return step(ae.cost(train_data[0]), lr, 1.0)
+                return run(train_data[0], lr)
+
+        def recapture():
+            st['graph'], st['failed'], st['lr_value'] = None, False, None
+            st['calls'] = max(st['calls'], 2)
+        opt.state, opt.recapture = st, recapture
         return opt
 
     def optimizeADAM(self, train_data, beta1=0.1, beta2=0.001, epsilon=1e-8, l=1e-8):
