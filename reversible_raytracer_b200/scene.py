@@ -23,7 +23,7 @@ import torch
 
 from . import _native as nat
 from . import render as R
-from .transform import RayField, Transform, as_tensor, default_device, identity  # noqa: F401
+from .transform import RayField, Transform, _Arg, as_tensor, default_device, identity  # noqa: F401
 from .shape import *  # noqa: F401,F403  (the reference's scene.py re-exports these)
 from .util import *  # noqa: F401,F403
 from .transform import *  # noqa: F401,F403
@@ -46,8 +46,36 @@ def _obj_type_tensor(kinds, device):
     return t
 
 
+def _live_field(name):
+    """A Material / Light / Camera field that behaves like a member holding a theano.shared or a symbolic
+    slice of one: assigning stores a transform._Arg (constants: by-value cached device tensor; tensors:
+    live, cast to float32 at read time; VIEWS OF A LEAF such as `q[:3]` are re-taken on every read, so they
+    follow a later requires_grad_ and in-place updates and pin no autograd node to the construction site),
+    reading returns the current float32 tensor."""
+    slot = '_' + name
+
+    def get(self):
+        return getattr(self, slot).t
+
+    def put(self, value):
+        setattr(self, slot, _Arg(value))
+    return property(get, put)
+
+
+def _field_key(obj, names):
+    """identity of the values behind live fields, for Scene's cache signature"""
+    out = []
+    for n in names:
+        a = getattr(obj, '_' + n)
+        out.append(a.key if a.key is not None else ('const', id(a._src)))
+    return tuple(out)
+
+
 class Material(object):
     """scene.py:89-101"""
+    ks, kd, ka = _live_field('ks'), _live_field('kd'), _live_field('ka')
+    color, shininess = _live_field('color'), _live_field('shininess')
+    FIELDS = ('ka', 'kd', 'ks', 'shininess', 'color')
 
     def __init__(self, color, ks, kd, ka, shininess, reflectivity=0.0):
         """`reflectivity` (extension, default 0 = the reference's behaviour): mirror coefficient k in
@@ -56,11 +84,7 @@ class Material(object):
         self.reflectivity = float(reflectivity)
         # live parameters (torch tensors) are re-read on every build; constants are packed once
         self.dynamic = any(isinstance(v, torch.Tensor) for v in (color, ks, kd, ka, shininess))
-        self.ks = as_tensor(ks)
-        self.kd = as_tensor(kd)
-        self.ka = as_tensor(ka)
-        self.color = as_tensor(color)
-        self.shininess = as_tensor(shininess)
+        self.ks, self.kd, self.ka, self.color, self.shininess = ks, kd, ka, color, shininess
 
     def packed(self, device):
         """-> float32[7] (ka, kd, ks, shininess, r, g, b), differentiable."""
@@ -71,11 +95,12 @@ class Material(object):
 
 class Light(object):
     """Directional light, scene.py:78-86."""
+    direction, intensity = _live_field('direction'), _live_field('intensity')
+    FIELDS = ('direction', 'intensity')
 
     def __init__(self, direction, intensity):
         self.dynamic = isinstance(direction, torch.Tensor) or isinstance(intensity, torch.Tensor)
-        self.direction = as_tensor(direction)
-        self.intensity = as_tensor(intensity)
+        self.direction, self.intensity = direction, intensity
 
     def normed_dir(self):
         d = self.direction
@@ -88,6 +113,7 @@ class Light(object):
 
 class Camera(object):
     """Pin-hole camera.  Two constructors, like the reference's two copies."""
+    look_at = _live_field('look_at')
 
     def __init__(self, x_dims, y_dims, o2w=None, camera_dir=None):
         self.x_dims = int(x_dims)
@@ -95,7 +121,7 @@ class Camera(object):
         self.has_transform = o2w is not None
         self.o2w = o2w if o2w is not None else identity()
         self.w2o = self.o2w.inverse()
-        self.look_at = as_tensor(np.asarray([0, 0, 1.], dtype='float32') if camera_dir is None else camera_dir)
+        self.look_at = np.asarray([0, 0, 1.], dtype='float32') if camera_dir is None else camera_dir
         self.dynamic_look_at = isinstance(camera_dir, torch.Tensor)
         self._rays = None
         self._last_sample = None     # (sampleDist_x, sampleDist_y) of the last build's last sample
@@ -222,10 +248,9 @@ class Scene(object):
         # everything the cached tables were packed from, by identity: shapes, their transforms and
         # materials (and the constant materials' field tensors), the light's fields, the camera
         sig = (device, tuple(id(s) for s in shapes), tuple(id(s.w2o) for s in shapes),
-               tuple((id(s.material),) + tuple(id(getattr(s.material, f)) for f in ('ka', 'kd', 'ks', 'shininess', 'color'))
-                     for s in shapes),
-               id(light), id(light.direction), id(light.intensity),
-               id(self.camera), id(self.camera.o2w), id(self.camera.look_at))
+               tuple((id(s.material),) + _field_key(s.material, Material.FIELDS) for s in shapes),
+               id(light), _field_key(light, Light.FIELDS),
+               id(self.camera), id(self.camera.o2w), _field_key(self.camera, ('look_at',)))
         if st is not None and st['sig'] == sig:
             return st
         from .chain import ChainProgram

@@ -303,6 +303,25 @@ def test_graph_capture_with_sliced_leaf_parameters_c2(fused, cuda):
     assert float((p1.detach() - torch.tensor([-.4, -.3, 3., .5, .5, .5], device=cuda)).abs().max()) > 1e-4
 
 
+def test_sliced_leaf_parameters_in_light_and_material_train(cuda):
+    """Light(q[:3], q[3:]) / Material(q[:3], q[3], q[4], q[5], ...) with q a leaf that only becomes trainable inside
+    optimize(): like indexing a theano.shared, the slices follow the leaf -- gradients reach q, the cost falls,
+    and the step is captured."""
+    tgt = torch.full((64, 64, 3), 0.3, device=cuda)
+    m1 = Material((0.2, 0.9, 0.4), 0.3, 0.7, 0.5, 50.)
+    ql = torch.tensor([-1., -1., 2., 0.9, 1., 0.8], device=cuda)
+    sl = Scene([Sphere(translate((0., 0., 4.)), m1)], [Light(ql[:3], ql[3:])], Camera(64, 64), PhongShader())
+    qm = torch.tensor([0.2, 0.9, 0.4, 0.3, 0.7, 0.5], device=cuda)
+    sm = Scene([Sphere(translate((0., 0., 4.)), Material(qm[:3], qm[3], qm[4], qm[5], 50.))],
+               [Light((-1., -1., 2.), (0.961, 1., 0.87))], Camera(64, 64), PhongShader())
+    for q, cost in ((ql, lambda: ((sl.build(seed=1) - tgt) ** 2).sum()), (qm, lambda: sm.build_mse(tgt, seed=1))):
+        q0 = q.clone()
+        train = GDOptimizer().optimize([q], cost, 1e-4, 0.0)
+        ls = [train() for _ in range(8)]
+        assert train.state['graph'] is not None
+        assert ls[-1] < 0.95 * ls[0] and float((q.detach() - q0).abs().max()) > 1e-3
+
+
 def test_graph_capture_validation_catches_host_state(cuda):
     """A closure that reads host-side state which changes per call (here: the jitter seed) cannot be
     replayed faithfully; the post-capture validation (replay with lr = 0 vs an eager evaluation)

@@ -133,6 +133,35 @@ def test_slices_of_a_leaf_parameter_stay_live_like_indexing_a_shared_variable():
     assert a1._view is None and a1.src is q and a2._view is None
 
 
+def test_material_light_camera_fields_are_live_too():
+    """Material / Light / Camera.look_at fields given as slices of a leaf (or as float64 tensors) are read
+    live as well: gradients reach the leaf although requires_grad_ came after the slices, in-place updates
+    are seen, and re-assigning a field changes the Scene's cache signature."""
+    from reversible_raytracer_b200.scene import Light, Camera, Scene, _field_key
+    q = torch.tensor([0.2, 0.9, 0.4, 0.3, 0.7, 0.5])
+    mat = Material(q[:3], q[3], q[4], q[5], 50.)
+    lq = torch.tensor([-1., -1., 2., .9, 1., .8], dtype=torch.float64)
+    light = Light(lq[:3], lq[3:])
+    q.requires_grad_(True), lq.requires_grad_(True)
+    pm = mat.packed(torch.device('cpu'))                       # (ka, kd, ks, shininess, r, g, b)
+    np.testing.assert_allclose(pm.detach().numpy(), [0.5, 0.7, 0.3, 50., 0.2, 0.9, 0.4], rtol=1e-6)
+    (pm * torch.arange(1., 8.)).sum().backward()
+    np.testing.assert_allclose(q.grad.numpy(), [5., 6., 7., 3., 2., 1.])
+    pl = light.packed(torch.device('cpu'))
+    assert pl.dtype == torch.float32
+    pl.sum().backward()
+    np.testing.assert_allclose(lq.grad.numpy(), np.ones(6))
+    with torch.no_grad():
+        q[0] = 0.75
+        lq[5] = 0.25
+    assert float(mat.color[0].detach()) == 0.75 and float(light.intensity[2].detach()) == 0.25
+    k0 = _field_key(light, Light.FIELDS)
+    light.intensity = (1., 1., 1.)
+    assert _field_key(light, Light.FIELDS) != k0 and float(light.intensity.sum()) == 3.0
+    cam = Camera(8, 8, T.translate((0., 1., 0.)), q[3:])
+    assert cam.look_at.requires_grad and cam.look_at.shape == (3,)
+
+
 def _random_chain(rng, depth):
     """A random translate / scale / rotate product, in the product's algebra and the oracle's."""
     prod, ref, flat = None, None, []
