@@ -322,6 +322,28 @@ def test_sliced_leaf_parameters_in_light_and_material_train(cuda):
         assert ls[-1] < 0.95 * ls[0] and float((q.detach() - q0).abs().max()) > 1e-3
 
 
+def test_mgd_auto_optimizer_orbit_variant_is_captured_with_a_live_sample_index(cuda):
+    """orbit_experiments/optimize.py:68-97: opt(i, lr) trains on sample i (two camera views).  After two eager
+    calls the step is ONE CUDA-graph replay; the indexed sample goes through a static buffer, so changing i
+    between calls is seen -- the captured trajectory equals eager stepping over a schedule of different samples."""
+    from _orbit_ae_helper import OrbitAE
+    from reversible_raytracer_b200.optimize import MGDAutoOptimizer
+    tb = W.orbit_tables(4, seed=3)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    cfg = R.RenderConfig(n=32, samples=4, shader=tb['shader'], transpose=0, seed=9)
+    X, _, _ = R.render_forward(cfg, t(tb['obj_type']), t(tb['w2o']), t(tb['material']), t(tb['light']), t(tb['camera']), None)
+    data = X.reshape(4, 2, 32, 32, 3).contiguous()
+    schedule = [0, 1, 2, 3, 1, 0, 3, 2]
+    out = {}
+    for graph in ('auto', False):
+        ae = OrbitAE(32, cuda)
+        opt = MGDAutoOptimizer(ae).optimize(data, lam=0.0, graph=graph)
+        out[graph] = [opt(i, 2e-7) for i in schedule]
+        assert (opt.state['graph'] is not None) == (graph == 'auto')
+    np.testing.assert_allclose(out['auto'], out[False], rtol=2e-4)
+    assert len({round(v, 3) for v in out['auto']}) > 4          # different samples really give different costs
+
+
 def test_graph_capture_validation_catches_host_state(cuda):
     """A closure that reads host-side state which changes per call (here: the jitter seed) cannot be
     replayed faithfully; the post-capture validation (replay with lr = 0 vs an eager evaluation)
