@@ -1,6 +1,7 @@
 // rrt_small_kernel.cuh -- part of rrt_kernels.cu (one translation unit; included inside its anonymous namespace).
-// render_small_kernel<MODE,STEP,GEOM>: one ray per thread, persistent CTAs; STEP = the whole optimise step
-// in one launch; GEOM = RRT_FLAG_NO_MATERIAL_GRAD (only the 12 transform sums per object are reduced).
+// render_small_kernel<MODE,STEP,GEOM,MIRROR,SPP>: small scenes, persistent CTAs; one ray per thread (SPP = 0) or
+// one pixel and its S = SPP samples per thread (SPP in {1, 2, 4}); STEP = the whole optimise step in one launch;
+// GEOM = RRT_FLAG_NO_MATERIAL_GRAD (only the 12 transform sums per object are reduced); MIRROR = one bounce.
 #pragma once
 
 // ---------------------------------------------------------------- the small-scene kernel
@@ -13,7 +14,8 @@
 // (obj_test / shade / backward_ray), same canonical order, same sample summation order as
 // render_kernel, so the two kernels agree bit for bit on masks.
 //
-// Work items are blocks of kSmallThreads consecutive rays of one scene, numbered scene-major.
+// Work items are blocks of kSmallThreads consecutive rays of one scene (pixel-per-thread form: blocks of 16 x 8
+// pixels, see below), numbered scene-major.
 // The grid is PERSISTENT: at most (SM count x resident CTAs) CTAs, each walking a contiguous
 // range of `small_per` items.  Everything that used to be paid per 128 rays is paid once per
 // CTA and scene: the object-table build and its barrier, the CTA-level reduction barrier and
