@@ -299,6 +299,9 @@ def other_configs(dev, peak_tf, hbm_gbs, with_cpu=True):
     out['C2_test_balls_step_us'] = round(L.timeit(train, warm=6, iters=100), 1)
     train, _ = L.c2(True)
     out['C2_test_balls_fused_step_us'] = round(L.timeit(train, warm=6, iters=100), 1)
+    train, _ = L.c2('whole')
+    if train.state.get('whole_step') is not None:
+        out['C2_test_balls_whole_step_kernel_us'] = round(L.timeit(train, warm=6, iters=100), 1)
     train, _ = L.c3(False)
     out['C3_match_mirror_step_us'] = round(L.timeit(train, warm=6, iters=100), 1)
     train, _ = L.c3('graph')

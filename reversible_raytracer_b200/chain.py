@@ -78,6 +78,30 @@ _STRUCTURES = {}
 _STRUCTURES_MAX = 256
 
 
+class _LeafRef(object):
+    """a whole leaf tensor as one parameter slot (see ChainProgram)"""
+    __slots__ = ('src', 'key')
+
+    def __init__(self, base):
+        self.src, self.key = base, ('leaf', id(base))
+
+
+def _whole_leaf(arg):
+    """(leaf, element offset of the view inside it) when `arg` is a contiguous view of a contiguous leaf"""
+    if arg._view is None:
+        return None
+    base, size, stride, offset = arg._view
+    n = 1
+    for d, st in zip(reversed(size), reversed(stride)):     # contiguous: strides of a dense row-major block
+        if d != 1 and st != n:
+            return None
+        n *= d
+    rel = offset - base.storage_offset()
+    if not base.is_contiguous() or rel < 0 or rel + n > base.numel():
+        return None
+    return base, rel
+
+
 class ChainProgram(object):
     """Compiled op table for a list of Transforms (one output row of 12 floats each), bound to the
     CURRENT live parameter tensors of those transforms."""
@@ -105,7 +129,11 @@ class ChainProgram(object):
             plan.append(row)
         # pass 2: live parameters follow the constant block, each distinct tensor once
         # (the _Arg objects are kept, not their tensors: an argument that is a view of a leaf is taken
-        # again at every evaluation, see transform._Arg)
+        # again at every evaluation, see transform._Arg).  A CONTIGUOUS view of a contiguous leaf --
+        # `translate(p[:3]) * scale(p[3:])`, test_balls.py:27 -- does not even need that: the whole leaf
+        # gets one slot and the op reads its argument at (slot + offset of the view), so the value vector
+        # is cat(constants, leaves), autograd goes straight to the leaves, and GDOptimizer's one-launch
+        # step recognises the leaves as the chains' parameters.
         self.param_args, slot_of, p_off = [], {}, n_const
         for row in plan:
             for kind, inv, offs in row:
@@ -113,6 +141,16 @@ class ChainProgram(object):
                     if o[0] == 'p':
                         arg = o[1]
                         numel = arg.src.numel()
+                        leaf = _whole_leaf(arg)
+                        if leaf is not None:
+                            base, rel = leaf
+                            bkey = ('leaf', id(base))
+                            if bkey not in slot_of:
+                                slot_of[bkey] = p_off
+                                self.param_args.append(_LeafRef(base))
+                                p_off += base.numel()
+                            o[1], o[2] = slot_of[bkey] + rel, numel
+                            continue
                         if arg.key not in slot_of:
                             slot_of[arg.key] = p_off
                             self.param_args.append(arg)

@@ -272,7 +272,7 @@ def test_graph_capture_survives_reference_closure_style(cuda):
     np.testing.assert_allclose(c_g, c_e, rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize('fused', [False, True])
+@pytest.mark.parametrize('fused', [False, True, 'whole'])
 def test_graph_capture_with_sliced_leaf_parameters_c2(fused, cuda):
     """BASELINE config C2 in the reference's idiom (test_balls.py:22-44): two spheres
     translate(p[:3]) * scale(p[3:]), DepthMapShader, squared error of channel 0, gradient descent
@@ -290,11 +290,16 @@ def test_graph_capture_with_sliced_leaf_parameters_c2(fused, cuda):
         X3 = X[:, :, None].expand(32, 32, 3).contiguous()
         cost = (lambda: sc.build_mse(X3, channel_weight=(1., 0., 0.), seed=15)) if fused else \
             (lambda: ((X - sc.build(seed=15)[:, :, 0]) ** 2).sum())
+        if fused == 'whole':      # Scene.mse_cost: the chain compiler gives each leaf ONE slot, the ops read at its
+            cost = sc.mse_cost(X3, channel_weight=(1., 0., 0.), seed=15)   # slices' offsets => one-launch step
         return p1, p2, cost
     p1, p2, cost = make()
     train = GDOptimizer().optimize([p1, p2], cost, 0.0005, 0.0)
     lg = [train() for _ in range(8)]
-    assert train.state['graph'] is not None and not train.state['failed']
+    if fused == 'whole':
+        assert train.state['whole_step'] is not None, train.state.get('whole_step_refused')
+    else:
+        assert train.state['graph'] is not None and not train.state['failed']
     q1, q2, cost_e = make()
     eager = GDOptimizer().optimize([q1, q2], cost_e, 0.0005, 0.0, graph=False)
     le = [eager() for _ in range(8)]

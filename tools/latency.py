@@ -43,7 +43,8 @@ def c1():
 def c2(fused=False):
     """BASELINE config C2 (test_balls.py:22-44): two spheres translate(p[:3]) * scale(p[3:]), DepthMapShader(6.1),
     32 x 32, loss = sum((X - image[:, :, 0]) ** 2) against the reference's 15.jpg, gradient descent on both
-    6-vectors.  fused: the same cost through Scene.build_mse with channel weights (1, 0, 0)."""
+    6-vectors.  fused: the same cost through Scene.build_mse with channel weights (1, 0, 0); 'whole': through
+    Scene.mse_cost (rrt_small_step_mse)."""
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     img = np.load(os.path.join(root, 'tests', 'golden', 'balls_15.npy')).astype(np.float32)
@@ -58,6 +59,8 @@ def c2(fused=False):
     if fused:
         X3 = X[:, :, None].expand(32, 32, 3).contiguous()
         cost = lambda: sc.build_mse(X3, channel_weight=(1., 0., 0.), seed=15)
+        if fused == 'whole':            # Scene.mse_cost: the whole step as one kernel launch
+            cost = sc.mse_cost(X3, channel_weight=(1., 0., 0.), seed=15)
     else:
         cost = lambda: ((X - sc.build(seed=15)[:, :, 0]) ** 2).sum()
     return GDOptimizer().optimize([p1, p2], cost, 0.0001, 0.0), sc
