@@ -295,6 +295,11 @@ def other_configs(dev, peak_tf, hbm_gbs, with_cpu=True):
     out = {}
     train, _ = L.c1()
     out['C1_optimize_brightness_step_us'] = round(L.timeit(train, warm=6, iters=100), 1)
+    train, _ = L.c1('graph')                    # the same loss as a weight image: fused kernel (RRT_FLAG_LINEAR_COST)
+    out['C1_optimize_brightness_fused_step_us'] = round(L.timeit(train, warm=6, iters=100), 1)
+    train, _ = L.c1(True)                       # Scene.linear_cost: whole step = one kernel launch
+    if train.state.get('whole_step') is not None:
+        out['C1_optimize_brightness_whole_step_kernel_us'] = round(L.timeit(train, warm=6, iters=100), 1)
     train, _ = L.c2(False)
     out['C2_test_balls_step_us'] = round(L.timeit(train, warm=6, iters=100), 1)
     train, _ = L.c2(True)

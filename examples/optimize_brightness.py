@@ -6,6 +6,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import torch  # noqa: E402
 import _common as C  # noqa: E402
 from reversible_raytracer_b200.optimize import GDOptimizer  # noqa: E402
 from reversible_raytracer_b200.scene import *  # noqa: E402,F401,F403
@@ -21,7 +22,9 @@ def build_scene(params):
                  [Light((-1., -1., 2.), (0.961, 1., 0.87))], Camera(128, 128), PhongShader())
 
 
-def main(steps=90, out='output', dump=True):
+def main(steps=90, out='output', dump=True, fused=False):
+    """fused=True: the same loss written as a weight image (-1 at the two markers) through
+    Scene.linear_cost -- GDOptimizer then runs the whole step as ONE kernel launch."""
     params = C.centres()
     scene = build_scene(params)
     frame = lambda: scene.build().detach()
@@ -33,10 +36,15 @@ def main(steps=90, out='output', dump=True):
         image = scene.build()
         return -sum(image[a, b].sum() for a, b in MARKERS)
 
+    if fused:
+        weights = torch.zeros((128, 128, 3), device=params[0].device)
+        for a, b in MARKERS:
+            weights[a, b] = -1.0
+        brightness = scene.linear_cost(weights)
     train = GDOptimizer().optimize(params, brightness, 0.0008, 0.1)
     losses = C.run(train, steps, frame, out if dump else None, drawWithMarkers)
     return losses, params[0], params[1]
 
 
 if __name__ == '__main__':
-    main()
+    main(fused='--fused' in sys.argv)

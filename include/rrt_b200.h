@@ -148,6 +148,12 @@ extern "C" {
  * two flags force one or the other where it applies (A/B measurements, tests). */
 #define RRT_FLAG_PIXEL_THREADS 256
 #define RRT_FLAG_RAY_THREADS 512
+/* The fused entry points (rrt_render_fused_mse, rrt_small_step_mse) evaluate a LINEAR cost instead of the
+ * squared error: their `target` argument is read as a weight image W [B][rows][n][3] and
+ *     cost = sum_c w_c * sum(W * image)        d cost / d image = w_c * W
+ * -- the loss of optimize_brightness.py:51, -image[90,85].sum() - image[50,90].sum(), is W = -1 at two
+ * pixels.  Pixels with W = 0 carry no upstream gradient: their rays skip the reverse pass. */
+#define RRT_FLAG_LINEAR_COST 1024
 
 #define RRT_OK 0
 #define RRT_ERR_INVALID (-1)   /* bad argument (message in rrt_last_error)            */

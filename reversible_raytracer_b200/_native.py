@@ -146,7 +146,7 @@ EXPORTS = ['rrt_version', 'rrt_last_error', 'rrt_render_forward', 'rrt_render_ba
            'rrt_small_step_mse']
 
 FLAG_CULL, FLAG_NO_SMALL, FLAG_SHADOWS, FLAG_SCALAR_SHADOWS, FLAG_NO_MATERIAL_GRAD, FLAG_CANONICAL_SWEEP, FLAG_DETERMINISTIC, FLAG_MIRROR = 1, 2, 4, 8, 16, 32, 64, 128
-FLAG_PIXEL_THREADS, FLAG_RAY_THREADS = 256, 512
+FLAG_PIXEL_THREADS, FLAG_RAY_THREADS, FLAG_LINEAR_COST = 256, 512, 1024
 HIT_SHADOWED = 0x40000000
 CHAIN_TRANSLATE, CHAIN_SCALE, CHAIN_ROTATE, CHAIN_INVERT, CHAIN_MAX_OPS = 1, 2, 3, 0x100, 8
 

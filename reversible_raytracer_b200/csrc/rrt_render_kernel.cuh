@@ -502,13 +502,8 @@ __global__ void __launch_bounds__(32 * RRT_MAX_WARPS, RRT_MIN_BLOCKS) render_ker
                 const bool ok = row_ok && b < n;
 #pragma unroll
                 for (int c = 0; c < 3; c++) v[px][c] = pixsum[px][c] * inv;             // scene.py:49-50
-                if (MODE == MODE_FUSED && ok) {
-                    const float d0 = v[px][0] - tg[px][0], d1 = v[px][1] - tg[px][1], d2 = v[px][2] - tg[px][2];
-                    loss_part += P.cw[0] * d0 * d0 + P.cw[1] * d1 * d1 + P.cw[2] * d2 * d2;
-                    gpix[px][0] = 2.0f * P.cw[0] * d0 * inv;
-                    gpix[px][1] = 2.0f * P.cw[1] * d1 * inv;
-                    gpix[px][2] = 2.0f * P.cw[2] * d2 * inv;
-                }
+                if (MODE == MODE_FUSED && ok)
+                    pixel_cost(sc.flags & RRT_FLAG_LINEAR_COST, P.cw, inv, v[px][0], v[px][1], v[px][2], tg[px], loss_part, gpix[px]);
             }
             if (P.image) {
                 if (vec) {

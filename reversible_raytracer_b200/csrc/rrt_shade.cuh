@@ -190,6 +190,28 @@ __device__ __forceinline__ void shade(int shader, float max_depth, const Obj& ob
     }
 }
 
+// ---------------------------------------------------------------- the fused entry points' cost of one pixel
+// Default: squared error against the target, sum_c w_c (v_c - t_c)^2 (match_mirror.py:45).  With
+// RRT_FLAG_LINEAR_COST the `target` buffer holds a WEIGHT image W and the cost is the linear functional
+// sum_c w_c W_c v_c -- optimize_brightness.py:51, -image[90,85].sum() - image[50,90].sum(), is W = -1 at two
+// pixels; pixels with W = 0 carry no upstream gradient, so their rays skip the reverse pass.
+// `inv` = 1/S: d pixel / d sample.
+__device__ __forceinline__ void pixel_cost(bool linear, const float* cw, float inv, float v0, float v1, float v2,
+                                           const float* t, float& loss, float* gc) {
+    if (linear) {
+        loss += cw[0] * t[0] * v0 + cw[1] * t[1] * v1 + cw[2] * t[2] * v2;
+        gc[0] = cw[0] * t[0] * inv;
+        gc[1] = cw[1] * t[1] * inv;
+        gc[2] = cw[2] * t[2] * inv;
+    } else {
+        const float d0 = v0 - t[0], d1 = v1 - t[1], d2 = v2 - t[2];
+        loss += cw[0] * d0 * d0 + cw[1] * d1 * d1 + cw[2] * d2 * d2;
+        gc[0] = 2.0f * cw[0] * d0 * inv;
+        gc[1] = 2.0f * cw[1] * d1 * inv;
+        gc[2] = 2.0f * cw[2] * d2 * inv;
+    }
+}
+
 // ---------------------------------------------------------------- reverse pass, one winning ray
 // Closed form of T.grad through the winner (masks constant).  og[19] receives
 // [M = sum g_d' r_cam^T (9), g_b = sum g_o' (3), d/d(ka,kd,ks,sh,r,g,b)];

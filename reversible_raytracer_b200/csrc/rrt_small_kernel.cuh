@@ -461,13 +461,7 @@ render_small_kernel(const __grid_constant__ KParams P) {
             if (active && img_s) { img_s[po] = v0; img_s[po + 1] = v1; img_s[po + 2] = v2; }
             if (MODE == MODE_FUSED) {
                 float gc[3] = {0.f, 0.f, 0.f};
-                if (active) {
-                    const float d0 = v0 - tgt[0], d1 = v1 - tgt[1], d2 = v2 - tgt[2];
-                    loss_part += P.cw[0] * d0 * d0 + P.cw[1] * d1 * d1 + P.cw[2] * d2 * d2;
-                    gc[0] = 2.0f * P.cw[0] * d0 * inv;
-                    gc[1] = 2.0f * P.cw[1] * d1 * inv;
-                    gc[2] = 2.0f * P.cw[2] * d2 * inv;
-                }
+                if (active) pixel_cost(sc.flags & RRT_FLAG_LINEAR_COST, P.cw, inv, v0, v1, v2, tgt, loss_part, gc);
                 // ---- reverse pass through the winners: the samples of a pixel usually share their
                 // winner, so their sums meet in registers and reach the thread's column once per pixel
                 const bool gnz = (gc[0] != 0.f) | (gc[1] != 0.f) | (gc[2] != 0.f);
@@ -657,11 +651,9 @@ render_small_kernel(const __grid_constant__ KParams P) {
             const float v0 = sum[0] * inv, v1 = sum[1] * inv, v2 = sum[2] * inv;      // scene.py:49-50
             if (active && s == 0 && img_s) { img_s[po] = v0; img_s[po + 1] = v1; img_s[po + 2] = v2; }
             if (MODE == MODE_FUSED && active) {
-                const float d0 = v0 - tgt[0], d1 = v1 - tgt[1], d2 = v2 - tgt[2];
-                if (s == 0) loss_part += P.cw[0] * d0 * d0 + P.cw[1] * d1 * d1 + P.cw[2] * d2 * d2;
-                gc[0] = 2.0f * P.cw[0] * d0 * inv;
-                gc[1] = 2.0f * P.cw[1] * d1 * inv;
-                gc[2] = 2.0f * P.cw[2] * d2 * inv;
+                float lp = 0.f;
+                pixel_cost(sc.flags & RRT_FLAG_LINEAR_COST, P.cw, inv, v0, v1, v2, tgt, lp, gc);
+                if (s == 0) loss_part += lp;                 // once per pixel (its S lanes hold the same value)
             }
         }
 

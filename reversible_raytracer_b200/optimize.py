@@ -59,6 +59,9 @@ class _WholeStep(object):
         if {id(p) for p in prog.param_tensors} != {id(v) for v in tVars}:
             raise ValueError('the optimised variables must be exactly the parameters of the shape transforms')
         cfg = scene.config(spec['antialias_samples'], cull=False)
+        if spec.get('linear'):                      # Scene.linear_cost: RRT_FLAG_LINEAR_COST
+            from dataclasses import replace
+            cfg = replace(cfg, linear_cost=1)
         N, S = len(scene.shapes), cfg.samples
         if N < 1 or N > 32 or S > 32 or (S & (S - 1)) or cfg.shadows or cfg.deterministic or cfg.n * cfg.n * S > (16 << 20):
             raise ValueError('not a small scene')

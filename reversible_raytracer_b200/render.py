@@ -41,6 +41,8 @@ class RenderConfig:
                                         # (fixed-point accumulation across warps / CTAs instead of float atomics)
     pixel_threads: int = 0              # small-scene kernel thread mapping: 0 = the library's choice, 1 = force one pixel per
                                         # thread where it applies (RRT_FLAG_PIXEL_THREADS), 2 = force one ray per thread
+    linear_cost: int = 0                # 1: RRT_FLAG_LINEAR_COST -- the fused entry points read `target` as a weight image W and
+                                        # evaluate cost = sum(W * image) (optimize_brightness.py:51) instead of the squared error
     canonical_sweep: int = 0            # 1: RRT_FLAG_CANONICAL_SWEEP -- no conservative pre-filter in the sweep (same bits,
                                         # every pair evaluated with the reference's arithmetic; A/B, roofline accounting)
 
@@ -151,6 +153,7 @@ class _Tables:
                    (nat.FLAG_NO_MATERIAL_GRAD if cfg.geom_grad_only else 0) |
                    (nat.FLAG_CANONICAL_SWEEP if cfg.canonical_sweep else 0) |
                    (nat.FLAG_DETERMINISTIC if cfg.deterministic else 0) |
+                   (nat.FLAG_LINEAR_COST if cfg.linear_cost else 0) |
                    (nat.FLAG_PIXEL_THREADS if cfg.pixel_threads == 1 else 0) |
                    (nat.FLAG_RAY_THREADS if cfg.pixel_threads == 2 else 0))
         d.max_depth, d.camera_grad, d.seed = cfg.max_depth, cfg.camera_grad, cfg.seed & 0xFFFFFFFFFFFFFFFF

@@ -358,15 +358,35 @@ class Scene(object):
         return R.render(cfg, obj_type, w2o, mat, light, cam, jit, self._refl)
 
     def build_mse(self, target, antialias_samples=4, channel_weight=None, jitter=None, seed=None,
-                  want_image=False, cull=None):
+                  want_image=False, cull=None, linear=False):
         """Fused forward + sum((image-target)^2) + reverse pass in ONE kernel (the cost of
         match_mirror.py:45 and of every autoencoder, autoencoder.py:76).  Returns a
         differentiable scalar loss (float32) -- call .backward() on it -- and, if asked,
         the detached image."""
         device, cfg, (obj_type, w2o, mat, light, cam), jit = self._prepare(antialias_samples, jitter, seed, cull)
+        if linear:                                  # RRT_FLAG_LINEAR_COST: `target` is the weight image W
+            from dataclasses import replace
+            cfg = replace(cfg, linear_cost=1)
         loss, image = _FusedMSE.apply(w2o, mat, light, cam, cfg, obj_type, jit,
                                       as_tensor(target).to(device), channel_weight, want_image, self._refl)
         return (loss, image) if want_image else loss
+
+    def build_linear(self, weights, antialias_samples=4, channel_weight=None, jitter=None, seed=None,
+                     want_image=False, cull=None):
+        """Fused forward + LINEAR cost sum(weights * image) + reverse pass in one kernel: the loss of
+        optimize_brightness.py:51, `-image[90,85].sum() - image[50,90].sum()`, is a weight image that is
+        -1 at two pixels and 0 elsewhere (rays of zero-weight pixels skip the reverse pass).  Returns a
+        differentiable scalar like build_mse."""
+        return self.build_mse(weights, antialias_samples, channel_weight, jitter, seed, want_image, cull, linear=True)
+
+    def linear_cost(self, weights, antialias_samples=4, channel_weight=None, jitter=None, seed=None):
+        """The cost expression `(weights * scene.build()).sum()` as a closure for GDOptimizer.optimize --
+        like mse_cost: fused kernel, and the whole optimise step as ONE launch where the scene qualifies."""
+        def cost():
+            return self.build_linear(weights, antialias_samples, channel_weight, jitter, seed)
+        cost.fused_spec = dict(scene=self, target=weights, antialias_samples=antialias_samples,
+                               channel_weight=channel_weight, jitter=jitter, seed=seed, linear=True)
+        return cost
 
     def mse_cost(self, target, antialias_samples=4, channel_weight=None, jitter=None, seed=None):
         """The cost expression `((scene.build() - target) ** 2).sum()` (match_mirror.py:45) as a

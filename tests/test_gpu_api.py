@@ -349,6 +349,41 @@ def test_mgd_auto_optimizer_orbit_variant_is_captured_with_a_live_sample_index(c
     assert len({round(v, 3) for v in out['auto']}) > 4          # different samples really give different costs
 
 
+def test_linear_cost_whole_step_optimize_brightness(cuda):
+    """BASELINE config C1 (optimize_brightness.py:19-57): the loss -image[90,85].sum() - image[50,90].sum() as a
+    weight image through Scene.linear_cost -> GDOptimizer runs the WHOLE step (chains, render, linear cost, reverse
+    pass, update) as one kernel launch; same trajectory as the reference-style closure on the general path."""
+    def make():
+        c1 = torch.tensor([-.5, -.5, 4.], device=cuda)
+        c2 = torch.tensor([.5, .5, 4.], device=cuda)
+        m1 = Material((0.2, 0.9, 0.4), 0.3, 0.7, 0.5, 50.)
+        m2 = Material((0.87, 0.1, 0.507), 0.3, 0.9, 0.4, 50.)
+        shapes = [Sphere(translate(c1), m1), Sphere(translate(c2) * rotate(90, (0, 0, 1)) * scale((1, 2, 1.5)), m2)]
+        sc = Scene(shapes, [Light((-1., -1., 2.), (0.961, 1., 0.87))], Camera(128, 128), PhongShader())
+        return c1, c2, sc
+    c1, c2, sc = make()
+    Wt = torch.zeros((128, 128, 3), device=cuda)
+    Wt[90, 85] = -1.0
+    Wt[50, 90] = -1.0
+    train = GDOptimizer().optimize([c1, c2], sc.linear_cost(Wt, seed=3), 0.0008, 0.1)
+    lw = [train() for _ in range(10)]
+    assert train.state['whole_step'] is not None, train.state.get('whole_step_refused')
+    d1, d2, sd = make()
+
+    def loss():
+        im = sd.build(seed=3)
+        return -im[90, 85].sum() - im[50, 90].sum()
+    ref = GDOptimizer().optimize([d1, d2], loss, 0.0008, 0.1)
+    lr_ = [ref() for _ in range(10)]
+    np.testing.assert_allclose(lw, lr_, rtol=1e-4, atol=1e-5)
+    assert lw[-1] < lw[0] and float((c1 - d1).abs().max()) < 1e-4 and float((c2 - d2).abs().max()) < 1e-4
+    # and the fused (non-whole-step) form through autograd
+    e1, e2, se = make()
+    fused = GDOptimizer().optimize([e1, e2], lambda: se.build_linear(Wt, seed=3), 0.0008, 0.1)
+    lf = [fused() for _ in range(10)]
+    np.testing.assert_allclose(lf, lr_, rtol=1e-4, atol=1e-5)
+
+
 def test_graph_capture_validation_catches_host_state(cuda):
     """A closure that reads host-side state which changes per call (here: the jitter seed) cannot be
     replayed faithfully; the post-capture validation (replay with lr = 0 vs an eager evaluation)

@@ -900,3 +900,36 @@ def test_pixel_and_ray_thread_mappings_agree(name, geom, cuda):
         lb, gb, _, _ = R.render_fused_mse(sr, ot, w2o, mat, light, cam, tgt)
         np.testing.assert_allclose(float(la.sum()), float(lb.sum()), rtol=1e-6)
         assert float((ga - gb).abs().max()) <= 1e-4 * max(float(gb.abs().max()), 1e-30)
+
+
+@pytest.mark.parametrize('name', ['C1_optimize_brightness', 'C3_match_mirror_square', 'C4_orbit_view0', 'C5_stress_diag', 'S1', 'S2',
+                                  'S8', 'ragged_n5'])
+@pytest.mark.parametrize('dense', [False, True])
+def test_linear_cost_equals_forward_plus_backward(name, dense, cuda):
+    """RRT_FLAG_LINEAR_COST: the fused entry point with a weight image W (optimize_brightness.py:51 is W = -1 at
+    two pixels) == the forward render (image bit for bit, loss = sum(W * image)) + the reverse-pass entry point with
+    dL/dimage = W (whose parity with the oracle is established above) -- on every kernel / thread mapping."""
+    ps = oc.PackedScene.from_spec(CASES[name](), camera_grad=1)
+    cfg, ot, w2o, mat, light, cam, jit = to_device(ps, cuda)
+    img, hit, _ = R.render_forward(cfg, ot, w2o, mat, light, cam, jit, want_hit=True)
+    rng = np.random.RandomState(11)
+    if dense:
+        Wt = torch.from_numpy(rng.normal(size=tuple(img.shape)).astype(np.float32)).to(cuda)
+    else:
+        Wt = torch.zeros_like(img)
+        flat = Wt.view(-1, 3)
+        lit = torch.nonzero((hit.reshape(ps.samples, -1) >= 0).any(0)).reshape(-1)       # pixels that see an object
+        pick_ = lit[torch.from_numpy(rng.choice(len(lit), size=min(3, len(lit)), replace=False)).to(cuda)] if len(lit) else lit
+        flat[pick_] = -1.0
+    cw = (1.0, 0.5, 2.0)
+    loss, grad, image, hit2 = R.render_fused_mse(replace(cfg, linear_cost=1), ot, w2o, mat, light, cam, Wt, cw, jit,
+                                                 want_image=True, want_hit=True)
+    assert torch.equal(hit2, hit) and torch.equal(image.view(torch.int32), img.view(torch.int32))
+    cwt = torch.tensor(cw, device=cuda)
+    expect = float((Wt.double() * img.double() * cwt.double()).sum())
+    assert abs(float(loss.sum()) - expect) <= 1e-5 * max(1.0, float((Wt.abs() * img).sum()))
+    gb = R.render_backward(cfg, ot, w2o, mat, light, cam, (Wt * cwt).contiguous(), None, jit)
+    scale_ = max(float(gb.abs().max()), 1e-30)
+    assert float((grad - gb).abs().max()) <= 2e-4 * scale_
+    if len(torch.nonzero(Wt)) and ps.n > 1:
+        assert float(gb.abs().max()) > 0

@@ -25,7 +25,9 @@ def timeit(fn, warm=5, iters=50):
     return (time.perf_counter() - t0) / iters * 1e6
 
 
-def c1():
+def c1(fused=False):
+    """fused: 'graph' = the loss as a weight image through Scene.build_linear (fused kernel + CUDA graph),
+    True = through Scene.linear_cost (whole step = one kernel launch)"""
     c1 = torch.tensor([-.5, -.5, 4.], device='cuda')
     c2 = torch.tensor([.5, .5, 4.], device='cuda')
     m1 = Material((0.2, 0.9, 0.4), 0.3, 0.7, 0.5, 50.)
@@ -36,6 +38,11 @@ def c1():
     def loss():
         im = sc.build()
         return -im[90, 85].sum() - im[50, 90].sum()
+    if fused:
+        Wt = torch.zeros((128, 128, 3), device='cuda')
+        Wt[90, 85] = -1.0
+        Wt[50, 90] = -1.0
+        loss = (lambda: sc.build_linear(Wt)) if fused == 'graph' else sc.linear_cost(Wt)
     train = GDOptimizer().optimize([c1, c2], loss, 0.0008, 0.1)
     return train, sc
 
