@@ -150,6 +150,20 @@ def cpu_small_configs():
     tgt = np.zeros((1, 64, 64, 3), dtype=np.float32)
     one('C4_orbit_256x2', sp, lambda im: (im ** 2).sum(), mse_target=tgt, views=512)
     out['C4_orbit_256x2']['note'] = 'one 64x64 view timed, x512 views of the batch (the reference renders them one by one)'
+    # BASELINE.md section 3, CPU-A on C5: the dense reference-structured algorithm cannot run the full size in
+    # reasonable time (and Theano could not even compile it), so it is timed at n=192, N=64, S=4 and extrapolated
+    # linearly in rays x objects, flagged as such
+    sp = scenes.stress(n=192, num_objects=64, samples=4)
+    t0 = time.perf_counter()
+    on.render(sp, return_aux=False)
+    t = time.perf_counter() - t0
+    tests = 192.0 * 192 * 4 * 64
+    full = 4096.0 * 4096 * 4 * 1024
+    out['C5_stress'] = dict(cpu_a_numpy=dict(
+        measured_at='n=192, N=64, S=4 (one forward, no warm-up)', forward_s=round(t, 3), ray_object_tests_per_s=round(tests / t, 1),
+        extrapolated_full_size_forward_hours=round(t * full / tests / 3600.0, 2), threads=torch.get_num_threads(), extrapolated=True,
+        what='oracle_numpy.render forward, extrapolated linearly in rays x objects to 4096^2 x 4 x 1024; CPU-B (oracle_c) on the '
+             'REAL full-size scene is the `cpu_baseline` of this line'))
     return out
 
 
