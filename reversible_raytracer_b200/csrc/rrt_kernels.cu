@@ -328,8 +328,17 @@ int rrt_render_fused_mse(const rrt_scene* scene, const float* target, const floa
     P.loss = loss;
     P.grad = grad;
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(grad, 0, sizeof(float) * RRT_GRAD_SIZE(scene->num_objects) * scene->num_scenes, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(loss, 0, sizeof(double) * scene->num_scenes, st);
+    // zero-initialise the outputs: ONE memset when the caller carved loss and grad out of one allocation
+    // (loss directly in front of grad), else two
+    const size_t gbytes = sizeof(float) * RRT_GRAD_SIZE(scene->num_objects) * scene->num_scenes;
+    const size_t lbytes = sizeof(double) * scene->num_scenes;
+    cudaError_t e;
+    if ((const char*)loss + lbytes == (const char*)grad) {
+        e = cudaMemsetAsync(loss, 0, lbytes + gbytes, st);
+    } else {
+        e = cudaMemsetAsync(grad, 0, gbytes, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(loss, 0, lbytes, st);
+    }
     if (e == cudaSuccess && (scene->flags & RRT_FLAG_DETERMINISTIC))
         e = cudaMemsetAsync(scene->det_workspace, 0, RRT_DET_WORKSPACE_BYTES(scene->num_scenes, scene->num_objects), st);
     if (e != cudaSuccess) return fail(RRT_ERR_CUDA, "memset grad/loss: %s", cudaGetErrorString(e));

@@ -246,8 +246,12 @@ def render_fused_mse(cfg, obj_type, w2o, material, light, camera, target, channe
     if channel_weight is not None:
         cw = (C.c_float * 3)(*[float(v) for v in channel_weight])
     with torch.cuda.device(T.device):
-        loss = torch.empty((T.B,), dtype=torch.float64, device=T.device)
-        grad = torch.empty((T.B, nat.grad_size(T.N)), dtype=torch.float32, device=T.device)
+        # loss and grad are carved out of ONE allocation, loss first: the library then zeroes both with one
+        # memset node instead of two (2.3 us of a 100 us decoder batch)
+        G = nat.grad_size(T.N)
+        both = torch.empty((T.B * (8 + 4 * G),), dtype=torch.uint8, device=T.device)
+        loss = both[:T.B * 8].view(torch.float64)
+        grad = both[T.B * 8:].view(torch.float32).view(T.B, G)
         image = torch.empty((T.B, cfg.rows, cfg.n, 3), dtype=torch.float32, device=T.device) if want_image else None
         hit = torch.empty((T.B, cfg.samples, cfg.rows, cfg.n), dtype=torch.int32, device=T.device) if want_hit else None
         rc = nat.lib().rrt_render_fused_mse(C.byref(T.desc), tg.data_ptr(), cw,
