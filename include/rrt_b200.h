@@ -142,7 +142,7 @@ extern "C" {
 /* The small-scene kernel has two thread mappings with identical results (same device routines, same
  * canonical order, same sample summation order): one RAY per thread (the S samples of a pixel in
  * adjacent lanes, combined by shuffles) and one PIXEL per thread (its S samples in registers, a warp
- * covering a compact 8 x 4 pixel tile; forward and fused modes, S in {1, 2, 4}, no shadows / mirror).
+ * covering a compact 8 x 4 pixel tile; S in {1, 2, 4}, no shadows / mirror).
  * By default the library takes pixel threads when the call has enough pixels to fill the GPU with them
  * (batches of scenes, e.g. the orbit decoder batch) and ray threads for a single small image.  These
  * two flags force one or the other where it applies (A/B measurements, tests). */

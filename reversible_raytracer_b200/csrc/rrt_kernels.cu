@@ -161,14 +161,14 @@ int sm_count() {
 }
 
 // The pixel-per-thread form of the small-scene kernel (one thread = one pixel and its S samples):
-// forward and fused modes, S in {1, 2, 4}, no shadows / mirror bounce.  Taken by default when the
+// all three modes, S in {1, 2, 4}, no shadows / mirror bounce.  Taken by default when the
 // call has enough pixels to fill the machine with pixel threads (batches of scenes); a single small
 // image keeps one ray per thread (4 x the threads, shorter dependency chains).
 constexpr long long kPixelMinPixels = 192 * 1024;   // measured crossover on the orbit batch: 16 scene pairs (131 k pixels) ray threads, 32 pixel threads
 bool use_pixel_threads(const KParams& P, int mode) {
     const rrt_scene& sc = P.sc;
     const int S = sc.samples;
-    if (mode == MODE_BWD || !(S == 1 || S == 2 || S == 4)) return false;
+    if (!(S == 1 || S == 2 || S == 4)) return false;
     if (sc.flags & (RRT_FLAG_SHADOWS | RRT_FLAG_MIRROR | RRT_FLAG_RAY_THREADS)) return false;
     if (sc.flags & RRT_FLAG_PIXEL_THREADS) return true;
     return (long long)P.rows * sc.n * sc.num_scenes >= kPixelMinPixels;
@@ -210,7 +210,7 @@ int launch(KParams& P, cudaStream_t st, bool* finalized = nullptr) {
         const bool pixel = use_pixel_threads(P, MODE);
         const unsigned grid = small_grid(P, pixel, pixel_min_blocks(MODE, geom));
         if (pixel) {
-            constexpr int PM = MODE == MODE_BWD ? MODE_FUSED : MODE;     // (never taken for MODE_BWD)
+            constexpr int PM = MODE;
             void (*kern)(const KParams) = nullptr;
             constexpr bool G = MODE != MODE_FWD;                         // (forward: one instantiation)
             if (geom) kern = S == 1 ? render_small_kernel<PM, false, G, false, 1> :

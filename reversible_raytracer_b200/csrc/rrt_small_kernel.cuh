@@ -62,8 +62,8 @@ __device__ __forceinline__ void small_warp_flush(int key, float* acc_col, float*
 // per RAY is paid per PIXEL: index arithmetic, the camera-space grid ray, the target load, the loss,
 // the image store; the pixel mean is a register sum in sample order (same bits as the shuffles of
 // the ray-per-thread form); the S samples of a pixel give the sweep S independent dependency
-// chains.  Same device routines, same canonical order => same masks.  Forward and fused modes,
-// no shadows / mirror / whole-step (those keep SPP = 0).
+// chains.  Same device routines, same canonical order => same masks.  All three modes; no shadows /
+// mirror / whole-step (those keep SPP = 0).
 constexpr int kPixTileW = 8, kPixTileH = 4;                 // pixels per warp: 8 x 4
 // a[q] for a run-time q out of a register array (select chain instead of local memory): lets the
 // per-sample shading / reverse-pass loops stay ROLLED -- one copy of that code instead of S, which is
@@ -98,7 +98,7 @@ constexpr int pixel_min_blocks(int mode, bool geom) { return (mode == MODE_FWD |
 template <int MODE, bool STEP = false, bool GEOM = false, bool MIRROR = false, int SPP = 0>
 __global__ void __launch_bounds__(kSmallThreads, SPP > 0 ? pixel_min_blocks(MODE, GEOM) : RRT_SMALL_MIN_BLOCKS)
 render_small_kernel(const __grid_constant__ KParams P) {
-    static_assert(SPP == 0 || (!STEP && !MIRROR && MODE != MODE_BWD), "pixel-per-thread form: forward / fused only");
+    static_assert(SPP == 0 || (!STEP && !MIRROR), "pixel-per-thread form: no whole-step / mirror variants");
     constexpr int NACC = GEOM ? 12 : 19;
     __shared__ float4 tab[kSmallMaxN * 4];
     __shared__ float mat_s[kSmallMaxN * RRT_MAT_STRIDE];
@@ -220,7 +220,7 @@ render_small_kernel(const __grid_constant__ KParams P) {
     // BWD with one item per CTA (single small image): a CTA none of whose pixels carries upstream
     // gradient (optimize_brightness.py:51 touches two pixels) skips the table build altogether
     bool skip_cta = false;
-    if (MODE == MODE_BWD && item1 - item0 == 1) {
+    if (MODE == MODE_BWD && SPP == 0 && item1 - item0 == 1) {
         const unsigned scene0 = item0 / bps, gid0 = (item0 - scene0 * bps) * kSmallThreads + tid;
         bool nz = false;
         if (gid0 < rays_scene) {
@@ -324,6 +324,13 @@ render_small_kernel(const __grid_constant__ KParams P) {
             const unsigned pl = active ? (unsigned)al * (unsigned)n + (unsigned)b : 0u;
             const unsigned po = pl * 3u;
 
+            float gc[3] = {0.f, 0.f, 0.f};                       // upstream gradient of the pixel, per sample
+            if (MODE == MODE_BWD) {
+                if (active) { gc[0] = dl_s[po] * inv; gc[1] = dl_s[po + 1] * inv; gc[2] = dl_s[po + 2] * inv; }
+                // sparse upstream gradients: a warp without any contributes exactly zero
+                if (!__any_sync(full, (gc[0] != 0.f) | (gc[1] != 0.f) | (gc[2] != 0.f))) continue;
+            }
+
             // ---- rays: the grid ray once per pixel, jitter per sample (scene.py:24-32,66-74)
             float rcx[SP], rcy[SP], rcz = 0.f;
 #pragma unroll
@@ -373,7 +380,15 @@ render_small_kernel(const __grid_constant__ KParams P) {
             int idx[SP];
 #pragma unroll
             for (int q = 0; q < SP; q++) { tmin[q] = inf; idx[q] = -1; }
-            if (active) {
+            if (use_stored) {
+                if (active) {
+#pragma unroll
+                    for (int q = 0; q < SP; q++) {
+                        const int kk = P.hit_in[(((size_t)scene * SP + q) * P.rows + al) * n + b];
+                        idx[q] = (kk >= 0 && kk < N) ? kk : -1;   // never trust an index buffer blindly; a winner flagged
+                    }                                             // RRT_HIT_SHADOWED (>= N) carries no gradient
+                }
+            } else if (active) {
                 float wx[SP], wy[SP], wz[SP];
 #pragma unroll
                 for (int q = 0; q < SP; q++) world(rcx[q], rcy[q], wx[q], wy[q], wz[q]);
@@ -421,7 +436,7 @@ render_small_kernel(const __grid_constant__ KParams P) {
                         }
                     }
                 }
-                if (P.hit_out || (MODE == MODE_FWD && P.tmin_out)) {
+                if (MODE != MODE_BWD && (P.hit_out || (MODE == MODE_FWD && P.tmin_out))) {
 #pragma unroll
                     for (int q = 0; q < SP; q++) {
                         const size_t ro = (((size_t)scene * SP + q) * P.rows + al) * n + b;
@@ -436,7 +451,7 @@ render_small_kernel(const __grid_constant__ KParams P) {
             bool any_hit = false;
 #pragma unroll
             for (int q = 0; q < SP; q++) any_hit |= (idx[q] >= 0);
-            if (__any_sync(full, any_hit)) {
+            if (MODE != MODE_BWD && __any_sync(full, any_hit)) {
 #pragma unroll 1
                 for (int q = 0; q < SP; q++) {
                     float rgb[3] = {0.f, 0.f, 0.f};
@@ -458,10 +473,10 @@ render_small_kernel(const __grid_constant__ KParams P) {
                 }
             }
             const float v0 = sum[0] * inv, v1 = sum[1] * inv, v2 = sum[2] * inv;
-            if (active && img_s) { img_s[po] = v0; img_s[po + 1] = v1; img_s[po + 2] = v2; }
-            if (MODE == MODE_FUSED) {
-                float gc[3] = {0.f, 0.f, 0.f};
-                if (active) pixel_cost(sc.flags & RRT_FLAG_LINEAR_COST, P.cw, inv, v0, v1, v2, tgt, loss_part, gc);
+            if (MODE != MODE_BWD && active && img_s) { img_s[po] = v0; img_s[po + 1] = v1; img_s[po + 2] = v2; }
+            if (MODE != MODE_FWD) {
+                if (MODE == MODE_FUSED && active)
+                    pixel_cost(sc.flags & RRT_FLAG_LINEAR_COST, P.cw, inv, v0, v1, v2, tgt, loss_part, gc);
                 // ---- reverse pass through the winners: the samples of a pixel usually share their
                 // winner, so their sums meet in registers and reach the thread's column once per pixel
                 const bool gnz = (gc[0] != 0.f) | (gc[1] != 0.f) | (gc[2] != 0.f);
@@ -474,7 +489,19 @@ render_small_kernel(const __grid_constant__ KParams P) {
                     bool pend = false, touched = false;
 #pragma unroll 1
                     for (int q = 0; q < SP; q++) {
-                        const int key = gnz ? pick(idx, q) : -1;
+                        int key = gnz ? pick(idx, q) : -1;
+                        if (use_stored && key >= 0) {
+                            // reverse-only entry point with stored winners: the ray parameter comes from the
+                            // canonical test of the stored object; a stale winner (no hit any more) carries nothing
+                            Obj ob0;
+                            HitRec h0;
+                            float wx, wy, wz;
+                            load_rec(tab + 4 * key, ob0);
+                            world(pick(rcx, q), pick(rcy, q), wx, wy, wz);
+                            const float t0 = obj_test<true>(ob0, wx, wy, wz, h0);
+                            if (t0 < inf) put(tmin, q, t0);
+                            else key = -1;
+                        }
                         const bool change = (key >= 0) && (acc_key >= 0) && (key != acc_key);
                         if (__any_sync(full, change)) {          // some lane's winner changed: flush the warp's sums
                             if (pend) {
@@ -493,7 +520,7 @@ render_small_kernel(const __grid_constant__ KParams P) {
                             const float rx = pick(rcx, q), ry = pick(rcy, q);
                             load_rec(tab + 4 * key, ob);
                             world(rx, ry, wx, wy, wz);
-                            hit_record<true>(ob, wx, wy, wz, pick(tmin, q), h);
+                            hit_record<true>(ob, wx, wy, wz, pick(tmin, q), h);   // t is known (sweep, or the test above)
 #pragma unroll
                             for (int v = 0; v < 7; v++) m7[v] = mat_s[key * RRT_MAT_STRIDE + v];
                             shade(sc.shader, sc.max_depth, ob, m7, g, h, sr, rgb);

@@ -887,6 +887,16 @@ def test_pixel_and_ray_thread_mappings_agree(name, geom, cuda):
         np.testing.assert_allclose(float(la.sum()), float(lb.sum()), rtol=1e-6)
         assert float(gb.abs().max()) > 0 or ps.n == 1
         assert float((ga - gb).abs().max()) <= (2e-5 if det else 1e-4) * max(float(gb.abs().max()), 1e-30)
+    # the reverse-only entry point, with stored and with re-swept winners, dense and sparse upstream gradients
+    rng = np.random.RandomState(4)
+    dl = torch.from_numpy(rng.normal(size=tuple(a[0].shape)).astype(np.float32)).to(cuda)
+    sparse = torch.zeros_like(dl)
+    sparse.view(-1, 3)[:: max(1, ps.n * ps.n // 3)] = 1.0
+    for up in (dl, sparse):
+        for stored in (a[1], None):
+            ga = R.render_backward(pix, ot, w2o, mat, light, cam, up, stored, jit)
+            gb = R.render_backward(ray, ot, w2o, mat, light, cam, up, stored, jit)
+            assert float((ga - gb).abs().max()) <= 1e-4 * max(float(gb.abs().max()), 1e-30)
     # a row slab that starts inside a tile row and is not a multiple of 4 rows high, in-kernel jitter
     if ps.n >= 5:
         rb, rc = 1, min(ps.n - 1, 7)

@@ -16,11 +16,15 @@ for scenes_ in [int(a) for a in sys.argv[1:]] or [256, 32]:
     args = (t(tb['obj_type']), t(tb['w2o']), t(tb['material']), t(tb['light']), t(tb['camera']))
     target, _, _ = R.render_forward(cfg, args[0], t(tt['w2o']), *args[2:], None, want_hit=False)
     rays = 2 * scenes_ * 64 * 64 * 4
-    for what in ('fused geom', 'fused all', 'forward'):
+    _, hit_all, _ = R.render_forward(cfg, *args, None, want_hit=True)
+    dl = torch.randn_like(target)
+    for what in ('fused geom', 'fused all', 'forward', 'backward stored', 'backward resweep'):
         for mapping in (1, 2):
             c = replace(cfg, geom_grad_only=int(what == 'fused geom'), pixel_threads=mapping)
             if what == 'forward':
                 fn = lambda: R.render_forward(c, *args, None, want_hit=False)
+            elif what.startswith('backward'):
+                fn = lambda: R.render_backward(c, *args, dl, hit_all if what.endswith('stored') else None)
             else:
                 fn = lambda: R.render_fused_mse(c, *args, target)
             g, s = torch.cuda.CUDAGraph(), torch.cuda.Stream()
