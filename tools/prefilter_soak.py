@@ -39,7 +39,15 @@ for seed in range(first, first + count):
     b = R.render_forward(replace(cfg, canonical_sweep=1), ot, w2o, mat, light, cam_t, jit, want_hit=True, want_tmin=True)
     ok = torch.equal(a[1], b[1]) and torch.equal(a[2].view(torch.int32), b[2].view(torch.int32)) and \
         torch.equal(a[0].view(torch.int32), b[0].view(torch.int32))
+    if ok and os.environ.get('ORACLE') and n <= 40:          # also against the canonical-order C oracle (CPU)
+        img_o, hit_o, tmin_o = oc.render_forward(ps)
+        ok = np.array_equal(a[1].cpu().numpy().reshape(hit_o.shape), hit_o) and \
+            np.array_equal(a[2].cpu().numpy().reshape(tmin_o.shape).view(np.int32), tmin_o.view(np.int32))
+        checked_oracle = globals().get('checked_oracle', 0) + 1
     if not ok:
         bad += 1
         print('MISMATCH seed', seed, 'N', N, 'n', n, int((a[1] != b[1]).sum()), 'rays')
-print('pre-filter soak: %d scenes (seeds %d..%d), mismatching scenes: %d' % (count, first, first + count - 1, bad))
+print('pre-filter soak: %d scenes (seeds %d..%d), mismatching scenes: %d%s' % (
+    count, first, first + count - 1, bad,
+    ' (%d of them also compared with the C oracle: hit_index and tmin bit for bit)' % globals().get('checked_oracle', 0)
+    if os.environ.get('ORACLE') else ''))
