@@ -83,6 +83,24 @@ class Sphere(Shape):
         bad = (det <= 0) | torch.isnan(det)
         return torch.where(bad, torch.full_like(dist, _INF), dist)
 
+    def shadow(self, points, lights):
+        """shape.py:85-97 (dense helper; the kernels' RRT_FLAG_SHADOWS pass follows the same formula per
+        winning ray): for object-space `points` [x, y, 3] the distance along -Lhat at which the unit sphere is
+        entered, -1 where the line misses it (decider <= 0 or NaN) -- "in shadow" where the result is >= 0."""
+        y = points
+        x = torch.tensordot(y, -1.0 * lights[0].normed_dir().to(y.device), dims=1)
+        decider = x * x - (y * y).sum(2) + 1
+        bad = torch.isnan(decider) | (decider <= 0)
+        return torch.where(bad, torch.full_like(x, -1.0), -x - torch.sqrt(torch.clamp(decider, min=0)))
+
+    def surface_pts(self, rayField):
+        """shape.py:100-106: object-space hit points, rays that miss parked at distance 1000.  (The
+        reference's body refers to an undefined name `rays`; the evident intent, rf.rays, is used.)"""
+        rf = self.w2o(rayField)
+        distance = self.distance(rayField)
+        stabilized = torch.where(torch.isinf(distance), torch.full_like(distance, 1000.0), distance)
+        return rf.origin + stabilized.unsqueeze(-1) * rf.rays
+
     def normals(self, rayField):
         """shape.py:128-138: object-space normal (never mapped back to world)."""
         rf = self.w2o(rayField)

@@ -111,6 +111,27 @@ class _Arg(object):
         return self._view[0].device if self._view is not None else self._src.device
 
 
+class Point(object):
+    """transform.py:6-8"""
+
+    def __init__(self, p):
+        self.p = p
+
+
+class PointField(object):
+    """transform.py:11-13"""
+
+    def __init__(self, pf):
+        self.pf = pf
+
+
+class VectorField(object):
+    """transform.py:16-18"""
+
+    def __init__(self, vf):
+        self.vf = vf
+
+
 class RayField(object):
     """transform.py:21-24"""
 

@@ -16,6 +16,28 @@ def broadcasted_switch(a, b, c):
     return torch.where(a.bool().unsqueeze(-1), b, c)
 
 
+def transNorm(transM, vec):
+    """util.py:31-42: vec[x, y, :] @ transM[:3, :3] (normals through the transposed matrix); dense helper."""
+    m = torch.as_tensor(transM, dtype=vec.dtype, device=vec.device)[:3, :3]
+    return torch.tensordot(vec[:, :, :3], m, dims=([2], [0]))
+
+
+def initialize_weight(n_vis, n_hid, W_name=None, numpy_rng=None, rng_dist='uniform', device=None):
+    """util.py:10-20: Glorot-uniform (or 0.01 * normal) [n_vis, n_hid] float32 weight as a trainable tensor
+    (the reference returns a theano.shared named W_name)."""
+    rng = numpy_rng if numpy_rng is not None else np.random
+    if 'uniform' in rng_dist:
+        b = np.sqrt(6. / (n_vis + n_hid))
+        W = rng.uniform(low=-b, high=b, size=(n_vis, n_hid))
+    elif rng_dist == 'normal':
+        W = 0.01 * rng.normal(size=(n_vis, n_hid))
+    else:
+        raise ValueError('rng_dist must be "uniform" or "normal"')
+    from .transform import default_device
+    t = torch.tensor(np.asarray(W, dtype=np.float32), device=device if device is not None else default_device())
+    return t.requires_grad_(True)
+
+
 def get_epsilon(epsilon, n, i):
     """Decaying learning rate, util.py:23-24."""
     return float(epsilon / (1 + i / float(n)))

@@ -162,6 +162,38 @@ def test_material_light_camera_fields_are_live_too():
     assert cam.look_at.requires_grad and cam.look_at.shape == (3,)
 
 
+def test_remaining_dense_helpers_of_the_reference_api():
+    """Sphere.shadow (shape.py:85-97), Sphere.surface_pts (shape.py:100-106), util.transNorm (util.py:31-42),
+    util.initialize_weight (util.py:10-20) and the Point / PointField / VectorField wrappers exist with the
+    reference's meaning (dense helpers for API compatibility; the kernels do not use them)."""
+    from reversible_raytracer_b200.scene import Light, Camera
+    from reversible_raytracer_b200 import util as U
+    light = Light((-1., -1., 2.), (1., 1., 1.))
+    sph = Sphere(T.translate((0., 0., 4.)), Material((1, 1, 1), .3, .7, .5, 50.))
+    # shadow: a point straight "behind" the unit sphere along the light direction is shadowed, one off-axis is not
+    Lh = light.normed_dir()
+    pts = torch.stack([(3.0 * Lh), torch.tensor([5., 0., 0.])]).reshape(1, 2, 3)
+    sh = sph.shadow(pts, [light])
+    assert sh.shape == (1, 2) and float(sh[0, 0]) >= 0 and float(sh[0, 1]) == -1.0
+    np.testing.assert_allclose(float(sh[0, 0]), 2.0, rtol=1e-6)         # enters the unit sphere after 3 - 1
+    # surface points lie on the unit sphere where the ray hits, at distance 1000 where it misses
+    cam = Camera(9, 9)
+    rf = cam.make_rays(9, 9)
+    sp = sph.surface_pts(rf)
+    d = sph.distance(rf)
+    hit = ~torch.isinf(d)
+    assert hit.any() and (~hit).any()
+    np.testing.assert_allclose((sp[hit] ** 2).sum(1).numpy(), 1.0, rtol=1e-5)
+    assert float(((sp[~hit] - sph.w2o(rf).origin) ** 2).sum(1).sqrt().min()) > 900
+    # transNorm == per-pixel vec @ M[:3,:3]
+    rng = np.random.RandomState(0)
+    M, v = rng.normal(size=(4, 4)).astype(np.float32), rng.normal(size=(3, 5, 3)).astype(np.float32)
+    np.testing.assert_allclose(U.transNorm(torch.tensor(M), torch.tensor(v)).numpy(), v @ M[:3, :3], rtol=1e-5, atol=1e-6)
+    W0 = U.initialize_weight(20, 10, 'W', np.random.RandomState(1), 'uniform', device='cpu')
+    assert W0.shape == (20, 10) and W0.requires_grad and float(W0.detach().abs().max()) <= np.sqrt(6. / 30)
+    assert T.Point(1).p == 1 and T.PointField(2).pf == 2 and T.VectorField(3).vf == 3
+
+
 def _random_chain(rng, depth):
     """A random translate / scale / rotate product, in the product's algebra and the oracle's."""
     prod, ref, flat = None, None, []
