@@ -698,7 +698,8 @@ def run_b200(args):
                          '+ 320 per winning ray) / step time.  The default sweep decides 99.9 % of the pairs with a 5-FMA '
                          'float32 quadratic form that conservatively bounds the sign of the reference discriminant and '
                          'hands the rest to the canonical arithmetic (bit-identical masks, tested), so `frac` may exceed '
-                         'the 0.727 ceiling of the canonical arithmetic (16 credited flops per 22 FMA-lane-ops); '
+                         'the 0.727 ceiling of the canonical arithmetic (16 credited flops per 22 FMA-lane-ops) and even 1.0 '
+                         '(credited flops are those of the reference arithmetic; 10 per pair are executed); '
                          '`executed` is the FMA-pipe work actually issued, `canonical_sweep` the same step with every '
                          'pair in the reference arithmetic.',
                     executed=dict(flops=exec_flops, tflops=exec_flops / (prefilter_ms * 1e-3) / 1e12,
