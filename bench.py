@@ -53,6 +53,9 @@ def parse():
                     help="c5 (default): the headline stress scene; c4: BASELINE config 4, the orbit autoencoder's "
                          "decoder batch (256 scenes x 2 views, 64x64, S=4), scene ranges sharded across ranks")
     ap.add_argument('--scenes', type=int, default=256)
+    ap.add_argument('--uniform-slabs', action='store_true',
+                    help='N > 1: row slabs of equal HEIGHT (default: contiguous slabs of equal estimated COST, from the '
+                         'per-row hit counts of a first render; sharding.balanced_row_slabs)')
     return ap.parse_args()
 
 
@@ -476,6 +479,49 @@ def run_b200(args):
     # reference's compiled-in constant `flipped`, match_mirror.py:45)
     target, hit, _ = R.render_forward(cfg, obj_type, w2o_target, d['material'], d['light'], d['camera'], None, want_hit=False)
     _, hit, _ = R.render_forward(cfg, obj_type, d['w2o'], d['material'], d['light'], d['camera'], None, want_hit=True)
+    slab_rows = None
+    if world > 1 and not args.uniform_slabs:
+        # Load balance: the sweep costs the same for every ray, shading + the reverse pass follow the winning rays
+        # (138.3 vs 128.2 us per wave with / without hits at 57 % winning rays => a winning ray costs
+        # ~0.14 of a ray's sweep on top).  Per-row hit counts of this first render (each rank its uniform slab, one
+        # allreduce) -> contiguous slabs of equal estimated cost; every rank computes the same partition.
+        from reversible_raytracer_b200 import sharding as Sh
+        row_hits = torch.zeros(n, dtype=torch.float64, device=dev)
+        row_hits[rb:rb + rc] = (hit >= 0).sum(dim=(0, 2)).to(torch.float64)
+        dist.all_reduce(row_hits)
+        cost = float(n * S) + 0.14 * row_hits.cpu().numpy()
+        def take(slabs_):
+            nonlocal rb, rc, cfg, target, hit
+            if slabs_[rank] != (rb, rc):
+                rb, rc = slabs_[rank]
+                cfg = replace(cfg, row_begin=rb, row_count=rc)
+                target, _, _ = R.render_forward(cfg, obj_type, w2o_target, d['material'], d['light'], d['camera'], None, want_hit=False)
+                _, hit, _ = R.render_forward(cfg, obj_type, d['w2o'], d['material'], d['light'], d['camera'], None, want_hit=True)
+        slabs = Sh.balanced_row_slabs(cost, world, align=4)
+        take(slabs)
+        # one measured correction (still set-up, before warm-up and timing): three fused launches per rank, the
+        # per-rank kernel times rescale the cost model of each rank's rows (minus the per-launch constant), and the
+        # partition is taken again -- what an optimisation loop would do every few hundred steps
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        R.render_fused_mse(cfg, obj_type, d['w2o'], d['material'], d['light'], d['camera'], target, want_image=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record()
+        for _ in range(3):
+            R.render_fused_mse(cfg, obj_type, d['w2o'], d['material'], d['light'], d['camera'], target, want_image=True)
+        e1.record()
+        torch.cuda.synchronize()
+        t_me = torch.tensor([e0.elapsed_time(e1) / 3.0], dtype=torch.float64, device=dev)
+        t_all = [torch.zeros_like(t_me) for _ in range(world)]
+        dist.all_gather(t_all, t_me)
+        t_all = np.array([float(x) for x in t_all])
+        c0 = 0.085                                             # ms per launch that does not scale with the slab
+        corr = np.clip((t_all - c0) / max(float(np.mean(t_all)) - c0, 1e-6), 0.8, 1.25)
+        for r_, (b_, c_) in enumerate(slabs):
+            cost[b_:b_ + c_] *= corr[r_]
+        slabs = Sh.balanced_row_slabs(cost, world, align=4)
+        take(slabs)
+        slab_rows = [c for _, c in slabs]
     hit_rays = torch.tensor([int((hit >= 0).sum())], dtype=torch.float64, device=dev)
     del hit
     timer = Timer(dev, world)
@@ -733,7 +779,10 @@ def run_b200(args):
                    warmup=max(args.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling='strong',
                    vs_baseline=None, dtype='f32', data='synthetic',
                    config=dict(workload=WORKLOAD if not args.general else WORKLOAD.replace('translate*scale', 'translate*rotate*scale'),
-                               n=n, samples=S, objects=N, sharding='row slabs, %d rows per GPU' % rows_per,
+                               n=n, samples=S, objects=N,
+                               sharding=('row slabs, %d rows per GPU' % rows_per) if slab_rows is None else
+                               'contiguous row slabs of equal estimated cost (rays + 0.14 x winning rays per row from a first '
+                               'render, corrected once by measured per-rank kernel times; set-up, before warm-up): rows per GPU %s' % slab_rows,
                                collective=collective,
                                l2='256 MiB flush write between timed iterations (outside the timed intervals)',
                                host_cpus_bound_to_gpu_numa_node=numa_cpus,

@@ -27,6 +27,37 @@ def row_slab(n, world, rank):
     return begin, base + (1 if rank < extra else 0)
 
 
+def balanced_row_slabs(row_cost, world, align=4):
+    """Contiguous row slabs of (nearly) EQUAL TOTAL COST instead of equal height: `row_cost[a]` is the estimated
+    cost of image row a (e.g. rays + k * winning rays, from a previous render's hit mask -- the sweep costs the
+    same everywhere, shading and the reverse pass follow where the objects are).  Slab boundaries are multiples
+    of `align` rows (the render kernel's CTAs are 4 rows high), every rank gets at least `align` rows (or one
+    row when there are fewer rows than that), the slabs cover [0, n) in rank order.  Deterministic: every rank
+    computes the same partition from the same costs.  -> list of (row_begin, row_count) per rank."""
+    import numpy as np
+    cost = np.asarray(row_cost, dtype=np.float64).reshape(-1)
+    n = int(cost.size)
+    if world < 1 or n < world:
+        raise ValueError('need at least one row per rank')
+    if not np.all(np.isfinite(cost)) or np.any(cost < 0) or cost.sum() <= 0:
+        cost = np.ones(n)
+    align = max(1, int(align))
+    if n < world * align:
+        align = 1
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    bounds = [0]
+    for r in range(1, world):
+        target = cum[-1] * r / world
+        b = int(np.searchsorted(cum, target))                 # first boundary whose prefix cost reaches the target
+        if b > 0 and abs(cum[b - 1] - target) <= abs(cum[b] - target):
+            b -= 1
+        b = int(round(b / align)) * align
+        lo, hi = bounds[-1] + align, n - (world - r) * align  # leave room for the ranks before and after
+        bounds.append(min(max(b, lo), hi))
+    bounds.append(n)
+    return [(bounds[r], bounds[r + 1] - bounds[r]) for r in range(world)]
+
+
 def scene_range(num_scenes, world, rank):
     """(first, count) of the scenes of `rank` (same split rule as row_slab)."""
     return row_slab(num_scenes, world, rank)

@@ -423,6 +423,28 @@ def test_mgd_auto_optimizer_adam():
 
 
 # ---- sharding
+def test_balanced_row_slabs():
+    """sharding.balanced_row_slabs: contiguous, aligned slabs covering every row once, of nearly equal total cost."""
+    rng = np.random.RandomState(0)
+    n = 4096
+    cost = n * 4 + 0.14 * n * 4 * rng.uniform(0, 1, n) * np.linspace(0.3, 1.7, n)      # hits concentrated at the bottom
+    for world in (1, 2, 3, 4, 8):
+        slabs = sharding.balanced_row_slabs(cost, world)
+        assert slabs[0][0] == 0 and sum(c for _, c in slabs) == n
+        assert all(slabs[r][0] + slabs[r][1] == slabs[r + 1][0] for r in range(world - 1))
+        assert all(b % 4 == 0 for b, _ in slabs) and all(c >= 4 for _, c in slabs)
+        tot = np.array([cost[b:b + c].sum() for b, c in slabs])
+        assert tot.max() / tot.mean() < 1.01
+        uni = np.array([cost[b:b + c].sum() for b, c in (sharding.row_slab(n, world, r) for r in range(world))])
+        assert tot.max() <= uni.max() + 1e-9
+    # degenerate inputs: fewer rows than alignment allows, all-zero / non-finite costs (=> uniform)
+    assert sharding.balanced_row_slabs(np.ones(5), 3) == [(0, 2), (2, 1), (3, 2)]
+    assert sharding.balanced_row_slabs(np.zeros(64), 4) == [(0, 16), (16, 16), (32, 16), (48, 16)]
+    assert sharding.balanced_row_slabs(np.full(32, np.nan), 2) == [(0, 16), (16, 16)]
+    with pytest.raises(ValueError):
+        sharding.balanced_row_slabs(np.ones(3), 4)
+
+
 def test_row_slabs_partition():
     for n, world in ((4096, 8), (4096, 3), (7, 8), (64, 1), (33, 4)):
         rows = [sharding.row_slab(n, world, r) for r in range(world)]
