@@ -125,14 +125,15 @@ class PeerSum(object):
 
 
 def render_fused_mse_sharded(cfg, obj_type, w2o, material, light, camera, target_slab, channel_weight=None,
-                             jitter_slab=None, group=None, peer_sum=None):
+                             jitter_slab=None, group=None, peer_sum=None, slab=None):
     """Row-slab sharded fused forward + MSE + reverse pass: this rank renders rows
-    row_slab(n, world, rank) against its resident `target_slab`, then the gradient
+    row_slab(n, world, rank) -- or `slab` = (row_begin, row_count), e.g. this rank's entry of
+    balanced_row_slabs(...) -- against its resident `target_slab`, then the gradient
     vector and loss are summed over ranks.  Returns (loss, grad) identical on every rank."""
     from . import render as R
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    rb, rc = row_slab(cfg.n, world, rank)
+    rb, rc = slab if slab is not None else row_slab(cfg.n, world, rank)
     loss, grad, _, _ = R.render_fused_mse(cfg.slab(rb, rc), obj_type, w2o, material, light, camera, target_slab,
                                           channel_weight, jitter_slab)
     if peer_sum is not None:               # our kernel over NVLink peer memory instead of NCCL
