@@ -53,6 +53,8 @@ def parse():
                     help="c5 (default): the headline stress scene; c4: BASELINE config 4, the orbit autoencoder's "
                          "decoder batch (256 scenes x 2 views, 64x64, S=4), scene ranges sharded across ranks")
     ap.add_argument('--scenes', type=int, default=256)
+    ap.add_argument('--no-graph-step', action='store_true',
+                    help='launch the step\'s kernels from Python every time instead of replaying them as one CUDA graph')
     ap.add_argument('--uniform-slabs', action='store_true',
                     help='N > 1: row slabs of equal HEIGHT (default: contiguous slabs of equal estimated COST, from the '
                          'per-row hit counts of a first render; sharding.balanced_row_slabs)')
@@ -573,14 +575,56 @@ def run_b200(args):
         return step
     step = make_step(cfg)
 
+    # The step as an optimisation loop runs it (GDOptimizer captures its step the same way): its launches --
+    # rrt_build_records, the memset, the fused render kernel, the peer exchange -- recorded once into ONE CUDA
+    # graph and replayed, so that no step waits for Python (after the barrier that opens the timed region the
+    # first step would otherwise start with ~100 us of host enqueue time, 5 % of a 2 ms step at 8 GPUs).
+    # Falls back to launching from Python if the capture fails.
+    graphed = None
+    timed_step = step
+    if not args.no_graph_step:
+        try:
+            for _ in range(2):
+                step()                                            # eager warm-up (per-stream scratch exists afterwards)
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            keep_kev = kev
+            kev = []                                              # (timing events cannot be recorded inside a capture)
+
+            def captured_body():
+                loss, grad, _, _ = R.render_fused_mse(cfg, obj_type, d['w2o'], d['material'], d['light'], d['camera'], target,
+                                                       want_image=True)
+                return exchange(loss, grad) if world > 1 else (loss, grad)
+            with torch.cuda.stream(side):
+                captured_body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_, stream=side):
+                g_out = captured_body()
+            graphed = g_
+            kev = keep_kev
+
+            def timed_step():
+                graphed.replay()
+                return g_out
+        except Exception as e:          # noqa: BLE001
+            sys.stderr.write('rank %d: CUDA-graph capture of the step failed (%r); launching from Python\n' % (rank, e))
+            torch.cuda.synchronize()
+            graphed, timed_step = None, step
+
     # everything with host-side start-up cost (NVML init, event creation) happens BEFORE the
     # barrier, so that all ranks enter the timed region together
     sampler = ClockSampler(local)
     sampler.start()
-    total_ms, per_step = timer.run(step, args.steps, warm=max(args.warmup, 3))
+    total_ms, per_step = timer.run(timed_step, args.steps, warm=max(args.warmup, 3))
     sampler.stop_flag = True
     kernel_ms = None
     if world > 1:
+        if graphed is not None:     # per-rank render time (events cannot be recorded inside the graph): the same K steps
+            kev = []                # launched from Python, same flush / barrier protocol, for the record only
+            timer.run(step, args.steps, warm=1)
         km = torch.tensor([sum(a.elapsed_time(b) for a, b in kev[-args.steps:]) / args.steps], dtype=torch.float64, device=dev)
         gathered = [torch.zeros_like(km) for _ in range(world)]
         dist.all_gather(gathered, km)
@@ -786,7 +830,8 @@ def run_b200(args):
                                collective=collective,
                                l2='256 MiB flush write between timed iterations (outside the timed intervals)',
                                host_cpus_bound_to_gpu_numa_node=numa_cpus,
-                               jitter='in-kernel counter RNG, seed 4321'),
+                               jitter='in-kernel counter RNG, seed 4321',
+                               step_launch='one CUDA-graph replay per step' if graphed is not None else 'launched from Python'),
                    e2e=dict(value=e2e_streamed_value, unit='Mrays/s', h2d_bytes_per_step=h2d + full_bytes,
                             d2h_bytes_per_step=d2h + full_bytes,
                             note='every step: scene-parameter tables AND the target slab come from pinned host memory, '
