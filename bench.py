@@ -4,9 +4,11 @@
 Metric (BASELINE.json): Mrays/s forward+backward on the synthetic stress scene C5
 (4096 x 4096 image, 4 anti-alias samples, 1024 spheres), one "step" = one fused
 forward + squared-error loss + reverse pass over the whole image; with N GPUs the
-image's row slabs are sharded across ranks (total work fixed => strong scaling)
-and the small parameter-gradient vector + loss are summed by ONE kernel of our own over
-NVLink peer memory (rrt_peer_allreduce; NCCL allreduce as the fallback).
+image's row slabs are sharded across ranks (total work fixed => strong scaling; contiguous
+slabs of equal estimated COST, sharding.balanced_row_slabs, chosen during set-up) and the small
+parameter-gradient vector + loss are summed by ONE kernel of our own over NVLink peer memory
+(rrt_peer_allreduce; NCCL allreduce as the fallback).  The step's launches are recorded once
+and replayed as one CUDA graph, the way an optimiser loop runs them (--no-graph-step: from Python).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            this framework
     python bench.py --impl reference [...]                         CPU restatement of the
