@@ -424,7 +424,25 @@ def c4_sharded(dev, world, rank, timer, scenes=256):
         steps = 50
         ms, _ = timer.run(lambda: [fn() for _ in range(steps)], 3, warm=1, flush=False)
         us = ms / 3 / steps * 1e3
-        return dict(us_per_batch=round(us, 1), Mrays_s=round(2.0 * total_scenes * 64 * 64 * 4 / us, 1), scenes_per_gpu=count)
+        out_ = dict(us_per_batch=round(us, 1), Mrays_s=round(2.0 * total_scenes * 64 * 64 * 4 / us, 1), scenes_per_gpu=count)
+        # the same call replayed from a CUDA graph: a 32-scene shard is a ~27 us launch, less than the ~40 us of
+        # Python it takes to enqueue it, so launched from Python the shard is host-bound
+        try:
+            g, s_ = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+            s_.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s_):
+                fn()
+            torch.cuda.current_stream().wait_stream(s_)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=s_):
+                fn()
+            gms, _ = timer.run(lambda: [g.replay() for _ in range(steps)], 3, warm=1, flush=False)
+            gus = gms / 3 / steps * 1e3
+            out_.update(us_per_batch_graph_replay=round(gus, 1), Mrays_s_graph_replay=round(2.0 * total_scenes * 64 * 64 * 4 / gus, 1))
+        except Exception as e:      # noqa: BLE001
+            out_['graph_replay_error'] = repr(e)
+            torch.cuda.synchronize()
+        return out_
     out['decoder_batch_256_scenes_total'] = decoder(scenes)
     out['decoder_batch_256_scenes_per_gpu'] = decoder(scenes * world)
     spec = importlib.util.spec_from_file_location('orbit_autoencoder', os.path.join(ROOT, 'examples', 'orbit_autoencoder.py'))
