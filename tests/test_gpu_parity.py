@@ -419,8 +419,11 @@ def test_streamed_host_buffers_equal_single_launch(num_objects, cuda):
     assert not torch.equal(ref[0][2], ref[1][2])
     pin_t = target.cpu().pin_memory()
     pin_i = torch.empty_like(pin_t).pin_memory()
-    for slabs in (1, 3, 5):
-        st = R.StreamedFusedMSE(cfg, w2o.shape[0], cuda, slabs=slabs)
+    # uniform slab counts, and an explicit graded schedule (short slabs at both ends, the kind the automatic
+    # choice takes for tall images) including a slab that is not a multiple of 4 rows high
+    for slabs in (1, 3, 5, [4, 8, 16, 40, 18, 8, 2]):
+        st = R.StreamedFusedMSE(cfg, w2o.shape[0], cuda, slabs=slabs) if isinstance(slabs, int) else \
+            R.StreamedFusedMSE(cfg, w2o.shape[0], cuda, heights=[h for h in slabs[:-2]] + [slabs[-2] + slabs[-1]])
         for rep in range(4):                     # later calls reuse buffers / events, scene alternates
             loss0, grad0, img0, _ = ref[rep & 1]
             pin_i.zero_()
@@ -432,6 +435,8 @@ def test_streamed_host_buffers_equal_single_launch(num_objects, cuda):
             assert float((grad - grad0).abs().max()) <= 1e-4 * s_
     with pytest.raises(ValueError):
         st(ot, w2o, mat, light, cam, target.cpu(), pin_i)       # not pinned
+    with pytest.raises(ValueError):
+        R.StreamedFusedMSE(cfg, w2o.shape[0], cuda, heights=[4, 8])          # does not cover the image
 
 
 def test_sparse_upstream_gradient_early_out(cuda):
