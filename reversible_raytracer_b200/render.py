@@ -280,18 +280,18 @@ class StreamedFusedMSE:
     bits as the whole-image launch (rays are keyed by image row, RenderConfig.slab); the
     per-slab gradient vectors and losses are summed on the caller's stream.  Buffers,
     streams and events are created once (the equivalent of the reference's compile step,
-    optimize.py:29); __call__ only enqueues work.  `slabs=None` picks the slab count from the
-    image height."""
+    optimize.py:29); __call__ only enqueues work.  `slabs=None` picks the slab schedule from the
+    image height (uniform slabs; graded heights from 2048 rows on), `slabs=k` asks for k uniform slabs,
+    `heights=[...]` for an explicit schedule."""
 
     def __init__(self, cfg, num_objects, device, slabs=None, want_image=True, heights=None):
         self.cfg, self.N, self.device = cfg, int(num_objects), torch.device(device)
-        slabs_auto, explicit_heights = slabs is None, heights
+        auto, explicit_heights = slabs is None, heights
         if slabs is None:
             # measured on C5 (tools/streamed_probe.py): 4096 rows: 16 / 24 / 32 slabs -> 24.89 / 24.67 /
             # 24.62 ms against 24.28 ms resident; a 512-row slab (one of 8 GPUs): 3 / 6 / 12 / 16 slabs ->
             # 3.53 / 3.35 / 3.31 / 3.35 ms against 3.14 ms.  => slabs of >= ~44 rows, at most 32 of them
             slabs = max(1, min(32, cfg.rows // 44))
-        auto = slabs_auto
         rows, slabs = cfg.rows, max(1, min(int(slabs), cfg.rows))
         per = (rows + slabs - 1) // slabs
         per = (per + 3) // 4 * 4                      # whole CTAs (4 rows each) per slab
