@@ -266,6 +266,46 @@ def render_fused_mse(cfg, obj_type, w2o, material, light, camera, target, channe
     return loss, grad, image, hit
 
 
+def slab_schedule(rows, slabs=None, heights=None):
+    """Row slabs of StreamedFusedMSE -> [(first_row, height), ...] covering [0, rows) in order.
+    `heights=[...]`: the caller's schedule (multiples of 4 rows keep whole CTAs); `slabs=k`: k uniform slabs;
+    neither: the automatic choice -- uniform slabs of >= ~44 rows, at most 32 of them, and for tall images
+    (>= 2048 rows) graded heights."""
+    rows = int(rows)
+    if heights is not None:
+        hs = [int(h) for h in heights]
+        if sum(hs) != rows or any(h <= 0 for h in hs):
+            raise ValueError('heights must be positive and sum to the rows of the call')
+        out, r0 = [], 0
+        for h in hs:
+            out.append((r0, h))
+            r0 += h
+        return out
+    auto = slabs is None
+    if slabs is None:
+        # measured on C5 (tools/streamed_probe.py): 4096 rows: 16 / 24 / 32 slabs -> 24.89 / 24.67 /
+        # 24.62 ms against 24.28 ms resident; a 512-row slab (one of 8 GPUs): 3 / 6 / 12 / 16 slabs ->
+        # 3.53 / 3.35 / 3.31 / 3.35 ms against 3.14 ms.  => slabs of >= ~44 rows, at most 32 of them
+        slabs = max(1, min(32, rows // 44))
+    slabs = max(1, min(int(slabs), rows))
+    per = (rows + slabs - 1) // slabs
+    per = (per + 3) // 4 * 4                      # whole CTAs (4 rows each) per slab
+    if auto and rows >= 2048:
+        # Tall images: graded heights.  The pipeline cannot start before the FIRST slab's target has arrived
+        # and is not done before the LAST slab's image has left, so the slabs at both ends are short (16, 32,
+        # 64, 128 rows, mirrored at the end) and the ones in between tall (~ rows / 21 >= 128: every launch
+        # has a constant cost, DESIGN.md 7).  tools/streamed_schedule_probe.py on C5, 4096 rows: 32 uniform
+        # slabs 15.80 ms, graded ends + 128-row middle 15.65, + 192..512-row middle 15.54 (resident 15.30).
+        # Short images (a rank's slab at 4-8 GPUs) keep uniform slabs: 4..16-row launches cost more than
+        # they save there (512 rows: 2.19 ms uniform, 2.32 graded).
+        mid = max(128, (rows // 21 + 3) // 4 * 4)
+        ramp = [16, 32, 64] + ([128] if mid > 128 else [])
+        left = rows - 2 * sum(ramp)
+        hs = list(ramp) + [mid] * (left // mid) + ([left % mid] if left % mid else []) + ramp[::-1]
+        return slab_schedule(rows, heights=hs)
+    return [(r0, min(per, rows - r0)) for r0 in range(0, rows, per)]
+
+
 class StreamedFusedMSE:
     """Fused forward + squared-error loss + reverse pass of ONE big image whose target (and,
     optionally, rendered image) live in pinned HOST memory: the image is cut into row slabs
@@ -286,45 +326,8 @@ class StreamedFusedMSE:
 
     def __init__(self, cfg, num_objects, device, slabs=None, want_image=True, heights=None):
         self.cfg, self.N, self.device = cfg, int(num_objects), torch.device(device)
-        auto, explicit_heights = slabs is None, heights
-        if slabs is None:
-            # measured on C5 (tools/streamed_probe.py): 4096 rows: 16 / 24 / 32 slabs -> 24.89 / 24.67 /
-            # 24.62 ms against 24.28 ms resident; a 512-row slab (one of 8 GPUs): 3 / 6 / 12 / 16 slabs ->
-            # 3.53 / 3.35 / 3.31 / 3.35 ms against 3.14 ms.  => slabs of >= ~44 rows, at most 32 of them
-            slabs = max(1, min(32, cfg.rows // 44))
-        rows, slabs = cfg.rows, max(1, min(int(slabs), cfg.rows))
-        per = (rows + slabs - 1) // slabs
-        per = (per + 3) // 4 * 4                      # whole CTAs (4 rows each) per slab
-        self.bounds = [(r0, min(per, rows - r0)) for r0 in range(0, rows, per)]
-        if auto and rows >= 2048:
-            # Tall images: graded heights.  The pipeline cannot start before the FIRST slab's target has arrived
-            # and is not done before the LAST slab's image has left, so the slabs at both ends are short (16, 32,
-            # 64, 128 rows, mirrored at the end) and the ones in between tall (~ rows / 21 >= 128: every launch
-            # has a constant cost).  tools/streamed_schedule_probe.py on C5, 4096 rows: 32 uniform
-            # slabs 15.80 ms, graded ends + 128-row middle 15.65, + 192..512-row middle 15.54 (resident 15.30).
-            # Short images (a rank's slab at 4-8 GPUs) keep uniform slabs: 4..16-row launches cost more than
-            # they save there (512 rows: 2.19 ms uniform, 2.32 graded).
-            mid = max(128, (rows // 21 + 3) // 4 * 4)
-            ramp = [16, 32, 64] + ([128] if mid > 128 else [])
-            heights = list(ramp)
-            left = rows - 2 * sum(ramp)
-            heights += [mid] * (left // mid)
-            if left % mid:
-                heights.append(left % mid)
-            heights += ramp[::-1]
-            self.bounds, r0 = [], 0
-            for h in heights:
-                self.bounds.append((r0, h))
-                r0 += h
-            assert r0 == rows
-        if explicit_heights is not None:              # caller-chosen slab heights (multiples of 4 rows keep whole CTAs)
-            hs = [int(h) for h in explicit_heights]
-            if sum(hs) != rows or any(h <= 0 for h in hs):
-                raise ValueError('heights must be positive and sum to the rows of the call')
-            self.bounds, r0 = [], 0
-            for h in hs:
-                self.bounds.append((r0, h))
-                r0 += h
+        self.bounds = slab_schedule(cfg.rows, slabs, heights)
+        rows = cfg.rows
         K = len(self.bounds)
         with torch.cuda.device(self.device):
             self.dev_target = torch.empty((rows, cfg.n, 3), dtype=torch.float32, device=self.device)

@@ -445,6 +445,25 @@ def test_balanced_row_slabs():
         sharding.balanced_row_slabs(np.ones(3), 4)
 
 
+def test_streamed_slab_schedule():
+    """render.slab_schedule (row slabs of StreamedFusedMSE): slabs cover the rows once, in order; tall images get
+    short slabs at both ends; uniform and explicit schedules are honoured; bad explicit schedules are refused."""
+    for rows in (1, 3, 47, 100, 512, 516, 1024, 2047, 2048, 3001, 4096, 16384):
+        b = R.slab_schedule(rows)
+        assert b[0][0] == 0 and all(b[i][0] + b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+        assert b[-1][0] + b[-1][1] == rows and all(h > 0 for _, h in b) and len(b) <= 64
+        if rows >= 2048:
+            hs = [h for _, h in b]
+            assert hs[:3] == [16, 32, 64] and hs[-3:] == [64, 32, 16] and max(hs) >= 128
+        else:
+            assert len({h for _, h in b[:-1]}) <= 1                     # uniform (the last slab may be shorter)
+    assert R.slab_schedule(96, slabs=3) == [(0, 32), (32, 32), (64, 32)]
+    assert R.slab_schedule(96, heights=[4, 8, 84]) == [(0, 4), (4, 8), (12, 84)]
+    for bad in ([4, 8], [100], [50, 0, 46], [-4, 100]):
+        with pytest.raises(ValueError):
+            R.slab_schedule(96, heights=bad)
+
+
 def test_row_slabs_partition():
     for n, world in ((4096, 8), (4096, 3), (7, 8), (64, 1), (33, 4)):
         rows = [sharding.row_slab(n, world, r) for r in range(world)]
