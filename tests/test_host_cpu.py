@@ -475,7 +475,7 @@ def test_row_slabs_partition():
         assert max(c for _, c in rows) - min(c for _, c in rows) <= 1
 
 
-def _gloo_worker(rank, world, port, q):
+def _gloo_worker(rank, world, port, q, balanced=False):
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
@@ -486,6 +486,17 @@ def _gloo_worker(rank, world, port, q):
         img, _, _ = oc.render_forward(ps, want_aux=False)
         target = np.ascontiguousarray(img[0][:, ::-1, :])
         rb, rc = sharding.row_slab(ps.n, world, rank)
+        if balanced:
+            # bench.py's protocol at N > 1: per-row hit counts of each rank's uniform slab, ONE allreduce, then
+            # every rank computes the same cost-balanced partition and takes its own slab
+            _, hit, _ = oc.render_forward(ps.slab(rb, rc))
+            row_hits = torch.zeros(ps.n, dtype=torch.float64)
+            row_hits[rb:rb + rc] = torch.from_numpy((hit[0] >= 0).sum(axis=(0, 2)).astype(np.float64))
+            dist.all_reduce(row_hits)
+            cost = float(ps.n * ps.samples) + 0.14 * row_hits.numpy()
+            slabs = sharding.balanced_row_slabs(cost, world, align=4)
+            assert sum(c for _, c in slabs) == ps.n
+            rb, rc = slabs[rank]
         _, _, loss, grad = oc.render_fused_mse(ps.slab(rb, rc), target[rb:rb + rc])
         l, g = sharding.allreduce_loss_grad(torch.from_numpy(loss), torch.from_numpy(grad[0]).float())
         q.put((rank, float(l[0]), g.double().numpy()))
@@ -493,12 +504,13 @@ def _gloo_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_sharded_gradient_sum_gloo_world2():
+@pytest.mark.parametrize('balanced', [False, True])
+def test_sharded_gradient_sum_gloo_world2(balanced):
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + (1 if balanced else 0)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q, balanced)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in range(2)]
